@@ -1,0 +1,200 @@
+/*
+ * nanograd_b200 — C ABI of the sm_100a device backend for nanograd's tensor hot path.
+ *
+ * The reference (PABannier/nanograd) has no FFI: its device backend is PyOpenCL kernels
+ * embedded as strings in nanograd/nn/ops_gpu.py.  Every entry point below replaces one of
+ * those OpenCL launchers (or a composition of primitives that the reference runs as many
+ * launches); the citation next to each prototype names the reference code it stands in for.
+ * The Python binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; ng_last_error() then holds a
+ *     human-readable message (the Python bridge raises Exception, matching the reference's
+ *     plain-Exception error style, tensor.py:165,201,223).
+ *   - device pointers are passed as uint64_t; all tensors are contiguous row-major float32
+ *     (reference: nn/buffer.py:17 — GPUBuffer.dtype is always np.float32).
+ *   - layouts are the reference's: activations NCHW, filters KCRS (ops_cpu.py:350-351).
+ *   - all work is enqueued on one in-order compute stream per process (reference: one
+ *     in-order OpenCL queue, tensor.py:30).  Only ng_d2h / ng_sync / ng_event_sync block.
+ *   - plain C types only: no torch, no C++ types in signatures.
+ */
+#ifndef NANOGRAD_B200_H
+#define NANOGRAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ runtime -------- */
+/* replaces get_gpu_context_and_queue(), tensor.py:16-30 */
+int ng_init(int device_ordinal);
+const char* ng_last_error(void);
+int ng_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem_bytes);
+int ng_sync(void);
+/* number of kernels this library has launched since ng_init (bench.py's gpu_launches) */
+int ng_launch_count(uint64_t* out);
+
+/* replaces cl.Buffer(...) in GPUBuffer.__init__, nn/buffer.py:22-23.  Stream-ordered,
+ * size-bucketed caching pool: freed blocks are reused by later same-size requests. */
+int ng_malloc(uint64_t* out_ptr, uint64_t bytes);
+int ng_free(uint64_t ptr);
+int ng_mem_stats(uint64_t* live_bytes, uint64_t* pooled_bytes, uint64_t* n_device_allocs);
+int ng_pool_release(void);
+int ng_memset_zero(uint64_t ptr, uint64_t bytes);
+/* replaces cl.enqueue_copy host<->device, tensor.py:171,180 */
+int ng_h2d(uint64_t dst, const void* src, uint64_t bytes);
+int ng_d2h(void* dst, uint64_t src, uint64_t bytes); /* blocking, like is_blocking=True */
+int ng_d2d(uint64_t dst, uint64_t src, uint64_t bytes);
+int ng_pinned_alloc(void** out, uint64_t bytes);
+int ng_pinned_free(void* p);
+/* CUDA-event timers on the compute stream */
+int ng_event_create(uint64_t* out_ev);
+int ng_event_record(uint64_t ev);
+int ng_event_sync(uint64_t ev);
+int ng_event_elapsed_ms(uint64_t ev_start, uint64_t ev_stop, float* out_ms);
+int ng_event_destroy(uint64_t ev);
+/* writes a scratch buffer larger than the 126 MB L2 (timing hygiene between iterations) */
+int ng_flush_l2(void);
+/* FFMA-saturating microkernel: measured FP32 SIMT peak (TFLOP/s) for the roofline */
+int ng_measure_ffma_peak(int iters, float* out_tflops);
+
+/* --------------------------------------------------------------- elementwise ------- */
+/* unary op codes — replaces unary_op(), ops_gpu.py:79-85,127-131 */
+enum {
+  NG_U_COPY = 0, NG_U_NEG = 1, NG_U_EXP = 2, NG_U_LOG = 3, NG_U_RELU = 4,
+  NG_U_SIGMOID = 5, NG_U_TANH = 6, NG_U_SQRT = 7, NG_U_RECIP = 8
+};
+int ng_unary(int op, uint64_t out, uint64_t a, int64_t n);
+/* binary op codes — replaces element_wise_binary_op(), ops_gpu.py:51-77,114-125.
+ * out = f(a, b) with NumPy broadcasting expressed as per-operand element strides
+ * (stride 0 on broadcast axes) over the output shape. */
+enum {
+  NG_B_ADD = 0, NG_B_MUL = 1, NG_B_POW = 2, NG_B_DIV = 3, NG_B_SUB = 4,
+  NG_B_EQ = 5,          /* (a == b) ? 1 : 0                 Max/Min backward mask, ops_cpu.py:125 */
+  NG_B_RELU_BWD = 6,    /* a * (b >= 0)                     ops_cpu.py:263, ops_gpu.py:530 */
+  NG_B_EXP_BWD = 7,     /* a * exp(b)                       ops_cpu.py:228 */
+  NG_B_LOG_BWD = 8,     /* a / b                            ops_cpu.py:216 */
+  NG_B_SIGMOID_BWD = 9, /* a * s(b) * (1 - s(b))            ops_cpu.py:275 */
+  NG_B_TANH_BWD = 10,   /* a * (1 - tanh(b)^2)              ops_cpu.py:287 */
+  NG_B_POW_DBASE = 11,  /* b * a^(b-1)                      ops_cpu.py:250 */
+  NG_B_POW_DEXP = 12    /* a^b * log(a)                     ops_cpu.py:251 */
+};
+int ng_binary(int op, uint64_t out, uint64_t a, uint64_t b, int ndim,
+              const int64_t* out_shape, const int64_t* a_strides, const int64_t* b_strides);
+/* scalar immediates (the reference wraps every Python scalar in a 1-element device tensor,
+ * tensor.py:482-483; here the value rides in the launch arguments).  scalar_is_lhs selects
+ * f(s, a) instead of f(a, s). */
+int ng_binary_scalar(int op, uint64_t out, uint64_t a, float s, int scalar_is_lhs, int64_t n);
+int ng_fill(uint64_t out, float value, int64_t n);
+/* out[i] += a[i]  (gradient accumulation, tensor.py:243) */
+int ng_accumulate(uint64_t out, uint64_t a, int64_t n);
+
+/* ----------------------------------------------------------------- reductions ------ */
+/* replaces reduce_op(), ops_gpu.py:87-112,133-155 (serial loop per output there). */
+enum { NG_R_SUM = 0, NG_R_MAX = 1, NG_R_MIN = 2 };
+int ng_reduce(int op, uint64_t out, uint64_t in, int ndim, const int64_t* shape,
+              const int32_t* reduce_axis_mask);
+/* out[c] = sum over n, p of in[n, c, p] — the bias-gradient reduction that Add.backward's
+ * unbroadcast performs (ops_cpu.py:12-18,174-176; module.py:476) */
+int ng_channel_sum(uint64_t out, uint64_t in, int64_t n_outer, int64_t channels, int64_t inner);
+
+/* ----------------------------------------------------------------- shape ops ------- */
+/* replaces inner_slice()/gslice, ops_cpu.py:20-33, ops_gpu.py:187-208: N-d slice, zero fill
+ * outside the source (this is also how padding works, tensor.py:408-429). */
+int ng_slice(uint64_t out, uint64_t in, int ndim, const int64_t* in_shape,
+             const int64_t* out_shape, const int64_t* start);
+/* replaces perm_axis_op, ops_gpu.py:162-181 */
+int ng_permute(uint64_t out, uint64_t in, int ndim, const int64_t* in_shape, const int32_t* perm);
+/* replaces one_hot_encoding, ops_gpu.py:234-248 (labels are float32-encoded integers) */
+int ng_onehot(uint64_t out, uint64_t labels, int64_t rows, int64_t classes);
+
+/* ------------------------------------------------------------ GEMM / convolution --- */
+/* flags for the contraction kernels */
+enum { NG_F_RELU = 1, NG_F_TF32 = 2 };
+/* C[M,N] = op(A) @ op(B) (+ bias[N]) ; row-major; op = transpose when the flag is set.
+ * replaces matmul_op, ops_gpu.py:214-232, and the perm+matmul chain in MatMul.backward,
+ * ops_gpu.py:452-459.  batch > 1: equally strided batches of A, B and C. */
+int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
+            int trans_a, int trans_b, int64_t batch, uint64_t bias, int flags);
+/* y[N,K,OH,OW] = conv(x[N,C,H,W], w[K,C,R,S]) (+ bias[K]) ; cross-correlation, one stride for
+ * both axes, zero padding pad_t/pad_l (bottom/right padding is implied by OH/OW).
+ * replaces conv2d_op, ops_gpu.py:343-374 (ops_cpu.py:345-375) plus the pad2d slice copy
+ * (tensor.py:419-429) and the bias Add (module.py:476).  Conv1d = H=R=1 (ops_gpu.py:308-333). */
+int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias,
+                    int N, int C, int H, int W, int K, int R, int S,
+                    int stride, int pad_t, int pad_l, int OH, int OW, int flags);
+/* dx = dgrad(dy, w): replaces conv_backward_x, ops_gpu.py:769-795 (ops_cpu.py:388-398) */
+int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w,
+                    int N, int C, int H, int W, int K, int R, int S,
+                    int stride, int pad_t, int pad_l, int OH, int OW, int flags);
+/* dw = wgrad(dy, x): replaces conv_backward_weight, ops_gpu.py:797-820 (ops_cpu.py:386);
+ * deterministic split-K (two passes, no atomics) */
+int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x,
+                    int N, int C, int H, int W, int K, int R, int S,
+                    int stride, int pad_t, int pad_l, int OH, int OW, int flags);
+
+/* -------------------------------------------------------------------- pooling ------ */
+/* fused replacements for Tensor._pool2d → Slice, Reshape, Max/Sum(axis=(3,5)), Mul
+ * (tensor.py:370-406) and Max.backward's tie-splitting mask (ops_cpu.py:121-127).
+ * Window = stride = (ph, pw); the H % ph / W % pw remainder is cropped. */
+int ng_maxpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, int pw);
+int ng_maxpool2d_bwd(uint64_t dx, uint64_t dy, uint64_t x, uint64_t y,
+                     int64_t NC, int H, int W, int ph, int pw);
+int ng_avgpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, int pw);
+int ng_avgpool2d_bwd(uint64_t dx, uint64_t dy, int64_t NC, int H, int W, int ph, int pw);
+
+/* ----------------------------------------------------------------- loss head ------- */
+/* fused Tensor.log_softmax (tensor.py:327-331, nine primitive nodes in the reference) */
+int ng_logsoftmax_fwd(uint64_t out, uint64_t in, int64_t rows, int64_t cols);
+int ng_logsoftmax_bwd(uint64_t dx, uint64_t dy, uint64_t logp, int64_t rows, int64_t cols);
+/* fused NLLLoss.forward = -(logp * onehot(labels)).mean() over rows*cols (module.py:684-686) */
+int ng_nll_fwd(uint64_t loss1, uint64_t logp, uint64_t labels, int64_t rows, int64_t cols);
+int ng_nll_bwd(uint64_t dlogp, uint64_t dloss1, uint64_t labels, int64_t rows, int64_t cols);
+
+/* ------------------------------------------------------------------ batch norm ----- */
+/* fused BatchNorm2d.forward/_normalize (module.py:356-391): biased variance normalises,
+ * unbiased variance feeds running_var, momentum update in place. */
+int ng_bn2d_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
+                      uint64_t running_mean, uint64_t running_var,
+                      uint64_t save_mean, uint64_t save_invstd,
+                      int64_t N, int64_t C, int64_t HW, float eps, float momentum);
+int ng_bn2d_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
+                     uint64_t running_mean, uint64_t running_var,
+                     int64_t N, int64_t C, int64_t HW, float eps);
+int ng_bn2d_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x,
+                uint64_t gamma, uint64_t save_mean, uint64_t save_invstd,
+                int64_t N, int64_t C, int64_t HW);
+
+/* ------------------------------------------------------------------- optimizers ---- */
+/* one multi-tensor launch per step for the whole parameter list.
+ * SGD:   m = m*momentum + lr*(g*grad_scale); p -= m                (optimizer.py:52-55)
+ * Adam:  m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *        p -= lr * (m/bc1) / (sqrt(v/bc2) + eps)                    (optimizer.py:79-89)
+ * AdamW: p = p*(1 - lr*wd) - (lr/bc1) * m / (sqrt(v/bc2) + eps)     (optimizer.py:115-128)
+ * bc1 = 1 - b1^t, bc2 = 1 - b2^t are computed by the caller.  Parameters are updated in
+ * place (the reference rebinds p.data to a fresh buffer; values are identical). */
+int ng_multi_sgd(int count, const uint64_t* params, const uint64_t* grads, const uint64_t* moms,
+                 const int64_t* numels, float lr, float momentum, float grad_scale);
+int ng_multi_adam(int count, const uint64_t* params, const uint64_t* grads,
+                  const uint64_t* exp_avg, const uint64_t* exp_avg_sq, const int64_t* numels,
+                  float lr, float beta1, float beta2, float eps, float bc1, float bc2,
+                  float weight_decay, int adamw, float grad_scale);
+/* gather `count` tensors into one flat bucket / scatter back (gradient bucket for allreduce) */
+int ng_multi_pack(int count, const uint64_t* srcs, const int64_t* numels, uint64_t dst_flat);
+int ng_multi_unpack(int count, const uint64_t* dsts, const int64_t* numels, uint64_t src_flat);
+
+/* ---------------------------------------------------------- data-parallel (NCCL) --- */
+/* New functionality (the reference has no multi-device support, device.py:10-11).  One
+ * process per GPU; libnccl is dlopen()ed on first use.  The allreduce runs on a dedicated
+ * communication stream fenced against the compute stream with events. */
+int ng_nccl_unique_id(void* out_128_bytes);
+int ng_nccl_init(const void* id_128_bytes, int world_size, int rank);
+int ng_nccl_allreduce_sum(uint64_t buf, int64_t count);
+int ng_nccl_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANOGRAD_B200_H */

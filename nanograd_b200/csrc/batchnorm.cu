@@ -1,0 +1,264 @@
+// Fused BatchNorm2d: training forward (one statistics pass + one normalise pass, running-stat
+// update in place), evaluation forward, and backward (one reduction pass + one dx pass).
+//
+// The reference composes BatchNorm2d.forward / _normalize from ~30 primitive Tensor ops
+// (nanograd/nn/module.py:356-391): mean over (0,2,3); biased variance normalises; the unbiased
+// variance sum/(NHW-1) feeds running_var; running = (1-m)*running + m*batch; eps inside sqrt.
+// Algorithmic traffic: forward 12 B/element (x read twice, y written), backward 20 B/element.
+// Statistics are accumulated around a per-channel shift (the channel's first element) so the
+// single pass does not suffer E[x^2]-E[x]^2 cancellation on offset data.
+#include "ng_common.h"
+
+#include <math.h>
+
+namespace ng {
+
+// MODE 0: a = x - shift[c], b = a*a          (forward statistics)
+// MODE 1: a = dy,           b = dy*(x-mean)  (backward reductions)
+// partial layout: [S][C][2]; grid = (C, S)
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ partial, const float* __restrict__ x,
+                                                        const float* __restrict__ dy, const float* __restrict__ mean,
+                                                        int64_t N, int64_t C, int64_t P, int64_t n_per_split,
+                                                        int vec_ok) {
+  __shared__ float scratch[32];
+  const int64_t c = blockIdx.x, s = blockIdx.y;
+  const int64_t n0 = s * n_per_split;
+  int64_t n1 = n0 + n_per_split;
+  if (n1 > N) n1 = N;
+  const float ref = (MODE == 0) ? x[c * P] : mean[c];
+  float sa = 0.f, sb = 0.f;
+  if (vec_ok) {
+    const int64_t P4 = P >> 2;
+    const int64_t items = (n1 - n0) * P4;
+    for (int64_t i = threadIdx.x; i < items; i += blockDim.x) {
+      const int64_t n = n0 + i / P4, p4 = i % P4;
+      const int64_t off = (n * C + c) * P + (p4 << 2);
+      const float4 xv = *reinterpret_cast<const float4*>(x + off);
+      if (MODE == 0) {
+        const float a0 = xv.x - ref, a1 = xv.y - ref, a2 = xv.z - ref, a3 = xv.w - ref;
+        sa += (a0 + a1) + (a2 + a3);
+        sb += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      } else {
+        const float4 g = *reinterpret_cast<const float4*>(dy + off);
+        sa += (g.x + g.y) + (g.z + g.w);
+        sb += (g.x * (xv.x - ref) + g.y * (xv.y - ref)) + (g.z * (xv.z - ref) + g.w * (xv.w - ref));
+      }
+    }
+  } else {
+    const int64_t items = (n1 - n0) * P;
+    for (int64_t i = threadIdx.x; i < items; i += blockDim.x) {
+      const int64_t n = n0 + i / P, p = i % P;
+      const int64_t off = (n * C + c) * P + p;
+      if (MODE == 0) {
+        const float a = x[off] - ref;
+        sa += a;
+        sb += a * a;
+      } else {
+        const float g = dy[off];
+        sa += g;
+        sb += g * (x[off] - ref);
+      }
+    }
+  }
+  const float ta = block_sum(sa, scratch);
+  const float tb = block_sum(sb, scratch);
+  if (threadIdx.x == 0) {
+    partial[(s * C + c) * 2 + 0] = ta;
+    partial[(s * C + c) * 2 + 1] = tb;
+  }
+}
+
+// one thread per channel: fold the split partials, produce mean / invstd, update running stats
+__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ x,
+                                                              float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                                              float* running_mean, float* running_var, int64_t C,
+                                                              int64_t P, int S, float count, float eps, float momentum) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sa = 0.f, sb = 0.f;
+  for (int s = 0; s < S; ++s) {
+    sa += partial[(s * C + c) * 2 + 0];
+    sb += partial[(s * C + c) * 2 + 1];
+  }
+  const float shift = x[c * P];
+  const float d = sa / count;               // mean - shift
+  const float mean = shift + d;
+  float ssd = sb - sa * d;                  // sum (x-mean)^2 = sum a^2 - (sum a)^2 / n
+  if (ssd < 0.f) ssd = 0.f;
+  const float var_b = ssd / count;          // module.py:366
+  save_mean[c] = mean;
+  save_invstd[c] = 1.f / sqrtf(var_b + eps);
+  if (running_mean) {
+    const float var_u = ssd / (count - 1.f);  // module.py:367-368
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var_u;
+  }
+}
+
+// y = (x - mean[c]) * gamma[c] * invstd[c] + beta[c]
+// use_var: invstd is computed on the fly from a variance array (evaluation mode)
+__global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, const float* __restrict__ x,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ mean, const float* __restrict__ inv_or_var,
+                                                       int64_t total, int64_t C, int64_t P, float eps, int use_var,
+                                                       int vec_ok) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok) {
+    const int64_t n4 = total >> 2;
+    for (int64_t i = tid; i < n4; i += nth) {
+      const int64_t c = ((i << 2) / P) % C;
+      const float inv = use_var ? 1.f / sqrtf(inv_or_var[c] + eps) : inv_or_var[c];
+      const float a = gamma[c] * inv, mu = mean[c], b = beta[c];
+      float4 v = reinterpret_cast<const float4*>(x)[i];
+      v.x = (v.x - mu) * a + b; v.y = (v.y - mu) * a + b; v.z = (v.z - mu) * a + b; v.w = (v.w - mu) * a + b;
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+  } else {
+    for (int64_t i = tid; i < total; i += nth) {
+      const int64_t c = (i / P) % C;
+      const float inv = use_var ? 1.f / sqrtf(inv_or_var[c] + eps) : inv_or_var[c];
+      y[i] = (x[i] - mean[c]) * (gamma[c] * inv) + beta[c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial,
+                                                              const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ sums, int64_t C,
+                                                              int S) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sa = 0.f, sb = 0.f;
+  for (int s = 0; s < S; ++s) {
+    sa += partial[(s * C + c) * 2 + 0];
+    sb += partial[(s * C + c) * 2 + 1];
+  }
+  dbeta[c] = sa;
+  dgamma[c] = sb * invstd[c];
+  sums[c * 2 + 0] = sa;  // sum dy
+  sums[c * 2 + 1] = sb;  // sum dy * (x - mean)
+}
+
+// dx = gamma*invstd * (dy - sum_dy/n - (x-mean) * invstd^2 * sum_dy_xmu / n)
+__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(float* __restrict__ dx, const float* __restrict__ dy,
+                                                        const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                        const float* __restrict__ sums, int64_t total, int64_t C, int64_t P,
+                                                        float inv_count, int vec_ok) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok) {
+    const int64_t n4 = total >> 2;
+    for (int64_t i = tid; i < n4; i += nth) {
+      const int64_t c = ((i << 2) / P) % C;
+      const float inv = invstd[c], mu = mean[c];
+      const float k0 = gamma[c] * inv, k1 = sums[c * 2] * inv_count, k2 = inv * inv * sums[c * 2 + 1] * inv_count;
+      const float4 g = reinterpret_cast<const float4*>(dy)[i];
+      const float4 xv = reinterpret_cast<const float4*>(x)[i];
+      float4 o;
+      o.x = k0 * (g.x - k1 - (xv.x - mu) * k2); o.y = k0 * (g.y - k1 - (xv.y - mu) * k2);
+      o.z = k0 * (g.z - k1 - (xv.z - mu) * k2); o.w = k0 * (g.w - k1 - (xv.w - mu) * k2);
+      reinterpret_cast<float4*>(dx)[i] = o;
+    }
+  } else {
+    for (int64_t i = tid; i < total; i += nth) {
+      const int64_t c = (i / P) % C;
+      const float inv = invstd[c];
+      const float k0 = gamma[c] * inv, k1 = sums[c * 2] * inv_count, k2 = inv * inv * sums[c * 2 + 1] * inv_count;
+      dx[i] = k0 * (dy[i] - k1 - (x[i] - mean[c]) * k2);
+    }
+  }
+}
+
+static int bn_split(int64_t N, int64_t C, int64_t P, int64_t* n_per) {
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  int64_t S = ceil_div((int64_t)sms * 4, C);
+  if (S > N) S = N;
+  while (S > 1 && (N / S) * P < 8192) S--;
+  *n_per = ceil_div(N, S);
+  return (int)ceil_div(N, *n_per);
+}
+
+static inline int bgrid(int64_t n) {
+  int64_t g = ceil_div(n, 256);
+  const int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace ng
+
+using namespace ng;
+
+extern "C" {
+
+int ng_bn2d_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
+                      uint64_t running_var, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C,
+                      int64_t HW, float eps, float momentum) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_fwd_train: empty input");
+  NG_REQUIRE(C <= 65535, "ng_bn2d_fwd_train: too many channels");
+  int64_t n_per = 0;
+  const int S = bn_split(N, C, HW, &n_per);
+  float* partial = nullptr;
+  if (pool_alloc((void**)&partial, (uint64_t)S * C * 2 * sizeof(float))) return 1;
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
+  NG_LAUNCH((bn_reduce_kernel<0>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
+            (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec);
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(bn_fwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, dptr<const float>(x),
+            dptr<float>(save_mean), dptr<float>(save_invstd), running_mean ? dptr<float>(running_mean) : nullptr,
+            running_var ? dptr<float>(running_var) : nullptr, C, HW, S, (float)(N * HW), eps, momentum);
+  NG_CHECK_LAUNCH();
+  const int64_t total = N * C * HW;
+  NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
+            dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(save_mean),
+            dptr<const float>(save_invstd), total, C, HW, eps, 0, vec);
+  NG_CHECK_LAUNCH();
+  pool_free(partial);
+  return 0;
+}
+
+int ng_bn2d_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
+                     uint64_t running_var, int64_t N, int64_t C, int64_t HW, float eps) {
+  NG_ENSURE_INIT();
+  const int64_t total = N * C * HW;
+  if (total <= 0) return 0;
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
+  NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
+            dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(running_mean),
+            dptr<const float>(running_var), total, C, HW, eps, 1, vec);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_bn2d_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x, uint64_t gamma,
+                uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C, int64_t HW) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_bwd: empty input");
+  NG_REQUIRE(C <= 65535, "ng_bn2d_bwd: too many channels");
+  int64_t n_per = 0;
+  const int S = bn_split(N, C, HW, &n_per);
+  float* partial = nullptr;
+  if (pool_alloc((void**)&partial, (uint64_t)(S + 1) * C * 2 * sizeof(float))) return 1;
+  float* sums = partial + (int64_t)S * C * 2;
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0) && ((dx & 15u) == 0);
+  NG_LAUNCH((bn_reduce_kernel<1>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
+            dptr<const float>(dy), dptr<const float>(save_mean), N, C, HW, n_per, vec);
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial,
+            dptr<const float>(save_invstd), dptr<float>(dgamma), dptr<float>(dbeta), sums, C, S);
+  NG_CHECK_LAUNCH();
+  const int64_t total = N * C * HW;
+  NG_LAUNCH(bn_bwd_dx_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(dx), dptr<const float>(dy),
+            dptr<const float>(x), dptr<const float>(gamma), dptr<const float>(save_mean),
+            dptr<const float>(save_invstd), (const float*)sums, total, C, HW, 1.f / (float)(N * HW), vec);
+  NG_CHECK_LAUNCH();
+  pool_free(partial);
+  return 0;
+}
+
+}  // extern "C"

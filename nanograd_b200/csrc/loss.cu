@@ -1,0 +1,128 @@
+// Fused log-softmax and negative-log-likelihood kernels (row-wise reductions, one warp per row).
+//
+// The reference builds log_softmax out of nine primitive graph nodes
+// (nanograd/tensor.py:327-331: max -> reshape -> sub -> exp -> sum -> log -> reshape -> sub) and
+// NLLLoss as onehot -> mul -> mean -> neg (nanograd/nn/module.py:674-686; OneHot:
+// nanograd/nn/ops_cpu.py:39-49).  Note the reference's NLL divides by rows*cols, not rows.
+#include "ng_common.h"
+
+#include <math.h>
+
+namespace ng {
+
+__global__ void __launch_bounds__(256) logsoftmax_fwd_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                             int64_t rows, int64_t cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* x = in + r * cols;
+    float m = -INFINITY;
+    for (int64_t c = lane; c < cols; c += 32) m = fmaxf(m, x[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int64_t c = lane; c < cols; c += 32) s += expf(x[c] - m);
+    s = warp_sum(s);
+    const float lse = logf(s);
+    float* o = out + r * cols;
+    for (int64_t c = lane; c < cols; c += 32) o[c] = (x[c] - m) - lse;
+  }
+}
+
+// dx = dy - exp(logp) * sum_j dy_j   (the max term cancels analytically)
+__global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy,
+                                                             const float* __restrict__ logp, int64_t rows,
+                                                             int64_t cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* g = dy + r * cols;
+    const float* lp = logp + r * cols;
+    float s = 0.f;
+    for (int64_t c = lane; c < cols; c += 32) s += g[c];
+    s = warp_sum(s);
+    float* o = dx + r * cols;
+    for (int64_t c = lane; c < cols; c += 32) o[c] = g[c] - expf(lp[c]) * s;
+  }
+}
+
+// loss[0] = -(sum_b logp[b, label_b]) / (rows * cols); single block → deterministic order
+__global__ void __launch_bounds__(256) nll_fwd_kernel(float* __restrict__ loss, const float* __restrict__ logp,
+                                                       const float* __restrict__ labels, int64_t rows, int64_t cols) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
+    int64_t lab = (int64_t)labels[r];
+    if (lab < 0) lab += cols;
+    if (lab >= 0 && lab < cols) acc += logp[r * cols + lab];
+  }
+  const float t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) loss[0] = -t / (float)(rows * cols);
+}
+
+__global__ void __launch_bounds__(256) nll_bwd_kernel(float* __restrict__ dlogp, const float* __restrict__ dloss,
+                                                      const float* __restrict__ labels, int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  const float g = -dloss[0] / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    int64_t lab = (int64_t)labels[r];
+    if (lab < 0) lab += cols;
+    dlogp[i] = (lab == c) ? g : 0.f;
+  }
+}
+
+static inline int row_grid(int64_t rows) {
+  int64_t g = ceil_div(rows, 8);  // 8 warps per block
+  const int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace ng
+
+using namespace ng;
+
+extern "C" {
+
+int ng_logsoftmax_fwd(uint64_t out, uint64_t in, int64_t rows, int64_t cols) {
+  NG_ENSURE_INIT();
+  if (rows <= 0 || cols <= 0) return 0;
+  NG_LAUNCH(logsoftmax_fwd_kernel, row_grid(rows), 256, 0, dptr<float>(out), dptr<const float>(in), rows, cols);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_logsoftmax_bwd(uint64_t dx, uint64_t dy, uint64_t logp, int64_t rows, int64_t cols) {
+  NG_ENSURE_INIT();
+  if (rows <= 0 || cols <= 0) return 0;
+  NG_LAUNCH(logsoftmax_bwd_kernel, row_grid(rows), 256, 0, dptr<float>(dx), dptr<const float>(dy),
+            dptr<const float>(logp), rows, cols);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_nll_fwd(uint64_t loss1, uint64_t logp, uint64_t labels, int64_t rows, int64_t cols) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(rows > 0 && cols > 0, "ng_nll_fwd: empty input");
+  NG_LAUNCH(nll_fwd_kernel, 1, 256, 0, dptr<float>(loss1), dptr<const float>(logp), dptr<const float>(labels), rows,
+            cols);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_nll_bwd(uint64_t dlogp, uint64_t dloss1, uint64_t labels, int64_t rows, int64_t cols) {
+  NG_ENSURE_INIT();
+  if (rows <= 0 || cols <= 0) return 0;
+  int64_t g = ceil_div(rows * cols, 256);
+  const int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 16;
+  if (g > cap) g = cap;
+  NG_LAUNCH(nll_bwd_kernel, (int)g, 256, 0, dptr<float>(dlogp), dptr<const float>(dloss1),
+            dptr<const float>(labels), rows, cols);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+// Fused max / average pooling, forward and backward (window = stride, remainder cropped).
+//
+// The reference has no pooling Function: Tensor._pool2d composes Slice (crop) -> Reshape to
+// (N,C,H/ph,ph,W/pw,pw) -> Max or Sum over axes (3,5) -> Mul (nanograd/tensor.py:370-406), and
+// the max backward is Max.backward's equality mask with the gradient split equally among
+// ties (nanograd/nn/ops_cpu.py:121-127: mask * dy / count).  These kernels do each direction
+// in one pass over the activation; HBM-bound, one thread per output window (2x2 windows are
+// read as two 64-bit loads).
+#include "ng_common.h"
+
+#include <math.h>
+
+namespace ng {
+
+struct PoolP {
+  int64_t NC;
+  int H, W, ph, pw, OH, OW;
+  int fast2;  // ph == pw == 2, W even and base pointers 8-byte aligned
+};
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256) pool_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, PoolP p) {
+  const int64_t total = p.NC * p.OH * p.OW;
+  const float scale = 1.f / (float)(p.ph * p.pw);
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(o % p.OW);
+    const int64_t t = o / p.OW;
+    const int oh = (int)(t % p.OH);
+    const int64_t nc = t / p.OH;
+    const float* src = x + (nc * p.H + (int64_t)oh * p.ph) * p.W + (int64_t)ow * p.pw;
+    float acc;
+    if (p.fast2) {
+      const float2 r0 = *reinterpret_cast<const float2*>(src);
+      const float2 r1 = *reinterpret_cast<const float2*>(src + p.W);
+      acc = IS_MAX ? fmaxf(fmaxf(r0.x, r0.y), fmaxf(r1.x, r1.y)) : ((r0.x + r0.y) + (r1.x + r1.y));
+    } else {
+      acc = IS_MAX ? -INFINITY : 0.f;
+      for (int i = 0; i < p.ph; ++i)
+        for (int j = 0; j < p.pw; ++j) {
+          const float v = src[i * p.W + j];
+          acc = IS_MAX ? fmaxf(acc, v) : acc + v;
+        }
+    }
+    y[o] = IS_MAX ? acc : acc * scale;
+  }
+}
+
+// One thread per output window writes the whole input window of dx.  Rows/columns cropped by
+// the forward pass receive zero from a preceding memset (only when H % ph or W % pw != 0).
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256) pool_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy,
+                                                       const float* __restrict__ x, const float* __restrict__ y,
+                                                       PoolP p) {
+  const int64_t total = p.NC * p.OH * p.OW;
+  const float scale = 1.f / (float)(p.ph * p.pw);
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(o % p.OW);
+    const int64_t t = o / p.OW;
+    const int oh = (int)(t % p.OH);
+    const int64_t nc = t / p.OH;
+    const int64_t base = (nc * p.H + (int64_t)oh * p.ph) * p.W + (int64_t)ow * p.pw;
+    const float g = dy[o];
+    if (IS_MAX) {
+      const float m = y[o];
+      if (p.fast2) {
+        const float2 r0 = *reinterpret_cast<const float2*>(x + base);
+        const float2 r1 = *reinterpret_cast<const float2*>(x + base + p.W);
+        const int e00 = r0.x == m, e01 = r0.y == m, e10 = r1.x == m, e11 = r1.y == m;
+        const float share = g / (float)(e00 + e01 + e10 + e11);
+        float2 o0, o1;
+        o0.x = e00 ? share : 0.f; o0.y = e01 ? share : 0.f;
+        o1.x = e10 ? share : 0.f; o1.y = e11 ? share : 0.f;
+        *reinterpret_cast<float2*>(dx + base) = o0;
+        *reinterpret_cast<float2*>(dx + base + p.W) = o1;
+      } else {
+        int cnt = 0;
+        for (int i = 0; i < p.ph; ++i)
+          for (int j = 0; j < p.pw; ++j) cnt += (x[base + i * p.W + j] == m);
+        const float share = g / (float)cnt;
+        for (int i = 0; i < p.ph; ++i)
+          for (int j = 0; j < p.pw; ++j) {
+            const int64_t a = base + i * p.W + j;
+            dx[a] = (x[a] == m) ? share : 0.f;
+          }
+      }
+    } else {
+      const float share = g * scale;
+      if (p.fast2) {
+        float2 v; v.x = share; v.y = share;
+        *reinterpret_cast<float2*>(dx + base) = v;
+        *reinterpret_cast<float2*>(dx + base + p.W) = v;
+      } else {
+        for (int i = 0; i < p.ph; ++i)
+          for (int j = 0; j < p.pw; ++j) dx[base + i * p.W + j] = share;
+      }
+    }
+  }
+}
+
+static int make_pool(PoolP& p, const char* who, int64_t NC, int H, int W, int ph, int pw, uint64_t a, uint64_t b) {
+  NG_REQUIRE(NC >= 0 && H > 0 && W > 0 && ph > 0 && pw > 0, "%s: invalid dimensions", who);
+  p.NC = NC; p.H = H; p.W = W; p.ph = ph; p.pw = pw;
+  p.OH = H / ph; p.OW = W / pw;
+  p.fast2 = (ph == 2 && pw == 2 && (W % 2 == 0) && (a % 8 == 0) && (b % 8 == 0)) ? 1 : 0;
+  return 0;
+}
+
+static inline int pgrid(int64_t n) {
+  int64_t g = ceil_div(n, 256);
+  const int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace ng
+
+using namespace ng;
+
+extern "C" {
+
+int ng_maxpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, int pw) {
+  NG_ENSURE_INIT();
+  PoolP p;
+  if (make_pool(p, "ng_maxpool2d_fwd", NC, H, W, ph, pw, x, x)) return 1;
+  const int64_t n = NC * p.OH * p.OW;
+  if (n <= 0) return 0;
+  NG_LAUNCH((pool_fwd_kernel<true>), pgrid(n), 256, 0, dptr<float>(y), dptr<const float>(x), p);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_avgpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, int pw) {
+  NG_ENSURE_INIT();
+  PoolP p;
+  if (make_pool(p, "ng_avgpool2d_fwd", NC, H, W, ph, pw, x, x)) return 1;
+  const int64_t n = NC * p.OH * p.OW;
+  if (n <= 0) return 0;
+  NG_LAUNCH((pool_fwd_kernel<false>), pgrid(n), 256, 0, dptr<float>(y), dptr<const float>(x), p);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_maxpool2d_bwd(uint64_t dx, uint64_t dy, uint64_t x, uint64_t y, int64_t NC, int H, int W, int ph, int pw) {
+  NG_ENSURE_INIT();
+  PoolP p;
+  if (make_pool(p, "ng_maxpool2d_bwd", NC, H, W, ph, pw, x, dx)) return 1;
+  if (NC * H * W <= 0) return 0;
+  if (H % ph || W % pw) NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(dx), 0, (size_t)(NC * H * W) * sizeof(float), g_stream));
+  const int64_t n = NC * p.OH * p.OW;
+  if (n <= 0) return 0;
+  NG_LAUNCH((pool_bwd_kernel<true>), pgrid(n), 256, 0, dptr<float>(dx), dptr<const float>(dy),
+            dptr<const float>(x), dptr<const float>(y), p);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_avgpool2d_bwd(uint64_t dx, uint64_t dy, int64_t NC, int H, int W, int ph, int pw) {
+  NG_ENSURE_INIT();
+  PoolP p;
+  if (make_pool(p, "ng_avgpool2d_bwd", NC, H, W, ph, pw, dx, dx)) return 1;
+  if (NC * H * W <= 0) return 0;
+  if (H % ph || W % pw) NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(dx), 0, (size_t)(NC * H * W) * sizeof(float), g_stream));
+  const int64_t n = NC * p.OH * p.OW;
+  if (n <= 0) return 0;
+  NG_LAUNCH((pool_bwd_kernel<false>), pgrid(n), 256, 0, dptr<float>(dx), dptr<const float>(dy),
+            (const float*)nullptr, (const float*)nullptr, p);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+// Runtime: device selection, the single compute stream, a stream-ordered caching allocator,
+// host<->device copies, CUDA-event timers and two measurement helpers.
+//
+// Replaces the PyOpenCL context/queue bootstrap and buffer management of the reference
+// (nanograd/tensor.py:14-30,153-182; nanograd/nn/buffer.py:14-26).
+#include "ng_common.h"
+
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+namespace ng {
+
+cudaStream_t g_stream = nullptr;
+int g_device = -1;
+int g_sm_count = 0;
+uint64_t g_launches = 0;
+
+static thread_local char t_err[1024] = "";
+static char g_err[1024] = "";
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+  memcpy(g_err, t_err, sizeof(g_err));
+  return 1;
+}
+
+int ensure_init() {
+  if (g_device < 0) return ng_init(0);
+  return 0;
+}
+
+// ---- caching allocator -------------------------------------------------------------------------
+// All kernels run on one in-order stream, so a block returned to the pool can be handed to
+// the next request immediately: any kernel still reading it is ordered before any kernel the
+// new owner will launch.  Training repeats the same shapes every step → after the first step
+// no cudaMalloc is issued.
+struct Pool {
+  std::mutex mu;
+  std::map<uint64_t, std::vector<void*>> free_by_size;
+  std::unordered_map<void*, uint64_t> size_of;  // every block we ever allocated and still own
+  uint64_t live = 0, pooled = 0, n_allocs = 0;
+};
+static Pool& pool() {
+  static Pool* p = new Pool();  // leaked on purpose: outlive Python's teardown order
+  return *p;
+}
+
+static uint64_t round_size(uint64_t b) {
+  if (b == 0) b = 1;
+  const uint64_t q = (b < (1u << 20)) ? 512 : (1u << 16);
+  return (b + q - 1) / q * q;
+}
+
+static void release_pooled_locked(Pool& P) {
+  for (auto& kv : P.free_by_size) {
+    for (void* p : kv.second) {
+      cudaFree(p);
+      P.size_of.erase(p);
+    }
+  }
+  P.free_by_size.clear();
+  P.pooled = 0;
+}
+
+int pool_alloc(void** out, uint64_t bytes) {
+  Pool& P = pool();
+  const uint64_t sz = round_size(bytes);
+  std::lock_guard<std::mutex> lk(P.mu);
+  auto it = P.free_by_size.find(sz);
+  if (it != P.free_by_size.end() && !it->second.empty()) {
+    *out = it->second.back();
+    it->second.pop_back();
+    P.pooled -= sz;
+    P.live += sz;
+    return 0;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, sz);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaStreamSynchronize(g_stream);
+    release_pooled_locked(P);
+    e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return set_error("device out of memory: %llu bytes requested (%llu live, pool emptied): %s",
+                       (unsigned long long)sz, (unsigned long long)P.live, cudaGetErrorString(e));
+    }
+  }
+  P.n_allocs++;
+  P.size_of[p] = sz;
+  P.live += sz;
+  *out = p;
+  return 0;
+}
+
+int pool_free(void* p) {
+  if (!p) return 0;
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  auto it = P.size_of.find(p);
+  if (it == P.size_of.end()) return set_error("ng_free: pointer %p is not owned by the pool", p);
+  const uint64_t sz = it->second;
+  P.free_by_size[sz].push_back(p);
+  P.live -= sz;
+  P.pooled += sz;
+  return 0;
+}
+
+// ---- FFMA peak microkernel -----------------------------------------------------------------------
+__global__ void ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float r0 = threadIdx.x, r1 = r0 + 1.f, r2 = r0 + 2.f, r3 = r0 + 3.f;
+  float r4 = r0 + 4.f, r5 = r0 + 5.f, r6 = r0 + 6.f, r7 = r0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      r0 = fmaf(r0, a, b); r1 = fmaf(r1, a, b); r2 = fmaf(r2, a, b); r3 = fmaf(r3, a, b);
+      r4 = fmaf(r4, a, b); r5 = fmaf(r5, a, b); r6 = fmaf(r6, a, b); r7 = fmaf(r7, a, b);
+    }
+  }
+  const float s = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+  if (s == 123.456f) out[0] = s;  // keeps the chain alive, practically never true
+}
+
+}  // namespace ng
+
+using namespace ng;
+
+extern "C" {
+
+int ng_init(int device_ordinal) {
+  if (g_device >= 0) {
+    NG_REQUIRE(g_device == device_ordinal || device_ordinal < 0,
+               "ng_init: already initialised on device %d (requested %d)", g_device, device_ordinal);
+    return 0;
+  }
+  if (device_ordinal < 0) device_ordinal = 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return set_error("ng_init: no CUDA device available (%s); nanograd_b200 has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  NG_REQUIRE(device_ordinal < n, "ng_init: device %d out of range (%d devices)", device_ordinal, n);
+  NG_CHECK_CUDA(cudaSetDevice(device_ordinal));
+  cudaDeviceProp prop;
+  NG_CHECK_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+  g_sm_count = prop.multiProcessorCount;
+  NG_CHECK_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  g_device = device_ordinal;
+  return 0;
+}
+
+const char* ng_last_error(void) { return g_err; }
+
+int ng_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem_bytes) {
+  NG_ENSURE_INIT();
+  cudaDeviceProp prop;
+  NG_CHECK_CUDA(cudaGetDeviceProperties(&prop, g_device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (total_mem_bytes) *total_mem_bytes = (uint64_t)prop.totalGlobalMem;
+  return 0;
+}
+
+int ng_sync(void) {
+  NG_ENSURE_INIT();
+  NG_CHECK_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int ng_launch_count(uint64_t* out) {
+  *out = g_launches;
+  return 0;
+}
+
+int ng_malloc(uint64_t* out_ptr, uint64_t bytes) {
+  NG_ENSURE_INIT();
+  void* p = nullptr;
+  int r = pool_alloc(&p, bytes);
+  if (r) return r;
+  *out_ptr = (uint64_t)(uintptr_t)p;
+  return 0;
+}
+
+int ng_free(uint64_t ptr) { return pool_free(dptr<void>(ptr)); }
+
+int ng_mem_stats(uint64_t* live_bytes, uint64_t* pooled_bytes, uint64_t* n_device_allocs) {
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  if (live_bytes) *live_bytes = P.live;
+  if (pooled_bytes) *pooled_bytes = P.pooled;
+  if (n_device_allocs) *n_device_allocs = P.n_allocs;
+  return 0;
+}
+
+int ng_pool_release(void) {
+  NG_ENSURE_INIT();
+  NG_CHECK_CUDA(cudaStreamSynchronize(g_stream));
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  release_pooled_locked(P);
+  return 0;
+}
+
+int ng_memset_zero(uint64_t ptr, uint64_t bytes) {
+  NG_ENSURE_INIT();
+  if (bytes == 0) return 0;
+  NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(ptr), 0, bytes, g_stream));
+  return 0;
+}
+
+int ng_h2d(uint64_t dst, const void* src, uint64_t bytes) {
+  NG_ENSURE_INIT();
+  if (bytes == 0) return 0;
+  // Pageable sources are staged by the driver before the call returns; pinned sources
+  // (ng_pinned_alloc) are copied asynchronously on the compute stream.
+  NG_CHECK_CUDA(cudaMemcpyAsync(dptr<void>(dst), src, bytes, cudaMemcpyHostToDevice, g_stream));
+  return 0;
+}
+
+int ng_d2h(void* dst, uint64_t src, uint64_t bytes) {
+  NG_ENSURE_INIT();
+  if (bytes) NG_CHECK_CUDA(cudaMemcpyAsync(dst, dptr<void>(src), bytes, cudaMemcpyDeviceToHost, g_stream));
+  NG_CHECK_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int ng_d2d(uint64_t dst, uint64_t src, uint64_t bytes) {
+  NG_ENSURE_INIT();
+  if (bytes == 0) return 0;
+  NG_CHECK_CUDA(cudaMemcpyAsync(dptr<void>(dst), dptr<void>(src), bytes, cudaMemcpyDeviceToDevice, g_stream));
+  return 0;
+}
+
+int ng_pinned_alloc(void** out, uint64_t bytes) {
+  NG_ENSURE_INIT();
+  NG_CHECK_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+
+int ng_pinned_free(void* p) {
+  if (p) NG_CHECK_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int ng_event_create(uint64_t* out_ev) {
+  NG_ENSURE_INIT();
+  cudaEvent_t ev;
+  NG_CHECK_CUDA(cudaEventCreate(&ev));
+  *out_ev = (uint64_t)(uintptr_t)ev;
+  return 0;
+}
+int ng_event_record(uint64_t ev) {
+  NG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)(uintptr_t)ev, g_stream));
+  return 0;
+}
+int ng_event_sync(uint64_t ev) {
+  NG_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)(uintptr_t)ev));
+  return 0;
+}
+int ng_event_elapsed_ms(uint64_t a, uint64_t b, float* out_ms) {
+  NG_CHECK_CUDA(cudaEventElapsedTime(out_ms, (cudaEvent_t)(uintptr_t)a, (cudaEvent_t)(uintptr_t)b));
+  return 0;
+}
+int ng_event_destroy(uint64_t ev) {
+  NG_CHECK_CUDA(cudaEventDestroy((cudaEvent_t)(uintptr_t)ev));
+  return 0;
+}
+
+int ng_flush_l2(void) {
+  NG_ENSURE_INIT();
+  static void* scratch = nullptr;
+  const uint64_t bytes = 256ull << 20;  // 2x the 126 MB L2
+  if (!scratch) NG_CHECK_CUDA(cudaMalloc(&scratch, bytes));
+  static int v = 0;
+  NG_CHECK_CUDA(cudaMemsetAsync(scratch, (v++) & 0xff, bytes, g_stream));
+  return 0;
+}
+
+int ng_measure_ffma_peak(int iters, float* out_tflops) {
+  NG_ENSURE_INIT();
+  if (iters <= 0) iters = 4096;
+  float* d = nullptr;
+  int r = pool_alloc((void**)&d, 64);
+  if (r) return r;
+  const int blocks = g_sm_count * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  NG_CHECK_CUDA(cudaEventCreate(&e0));
+  NG_CHECK_CUDA(cudaEventCreate(&e1));
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // rep 0 is the warm-up
+    NG_CHECK_CUDA(cudaEventRecord(e0, g_stream));
+    NG_LAUNCH(ffma_peak_kernel, blocks, threads, 0, d, iters, 0.999f, 0.001f);
+    NG_CHECK_LAUNCH();
+    NG_CHECK_CUDA(cudaEventRecord(e1, g_stream));
+    NG_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    NG_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  pool_free(d);
+  const double flops = 2.0 * 8 * 16 * (double)iters * threads * (double)blocks;
+  *out_tflops = (float)(flops / (best_ms * 1e-3) / 1e12);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+"""Device buffer held by ``Tensor.data`` on ``Device.GPU``.
+
+Mirror of the reference's ``GPUBuffer`` (nanograd/nn/buffer.py:14-26): exposes ``.shape`` (tuple,
+compared against gradients in Tensor.backward, tensor.py:238) and ``.dtype`` (always float32,
+buffer.py:17); constructing one from another buffer aliases the same allocation under a new
+shape (buffer.py:19-20 — how Reshape/Squeeze/Unsqueeze are free on the device).  The
+allocation belongs to the base buffer and returns to the library's stream-ordered pool when
+the last alias is garbage-collected.
+"""
+import ctypes
+
+import numpy as np
+
+from nanograd_b200 import backend
+
+
+def _numel(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+class DeviceBuffer:
+    def __init__(self, shape, hostbuf=None):
+        if isinstance(shape, (int, np.integer)):
+            shape = (int(shape),)
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.float32
+        self.size = _numel(self.shape)
+        self._base = None
+        self._ptr = 0
+        if isinstance(hostbuf, DeviceBuffer):
+            if hostbuf.size != self.size:
+                raise Exception(f"cannot view a buffer of {hostbuf.size} elements as shape {self.shape}")
+            self._base = hostbuf._base if hostbuf._base is not None else hostbuf
+            self._ptr = hostbuf.ptr
+        else:
+            self._ptr = backend.malloc(self.size * 4)
+            if hostbuf is not None:
+                host = np.ascontiguousarray(hostbuf, dtype=np.float32)
+                if host.size != self.size:
+                    raise Exception(f"host array of {host.size} elements does not fill shape {self.shape}")
+                if self.size:
+                    backend.lib().ng_h2d(self._ptr, host.ctypes.data_as(ctypes.c_void_p), self.size * 4)
+
+    @property
+    def ptr(self):
+        return self._ptr
+
+    @property
+    def nbytes(self):
+        return self.size * 4
+
+    def view(self, shape):
+        """Zero-copy alias with a new shape."""
+        return DeviceBuffer(shape, hostbuf=self)
+
+    def numpy(self):
+        """Blocking device-to-host copy (the only synchronising operation besides sync())."""
+        out = np.empty(self.shape, dtype=np.float32)
+        backend.lib().ng_d2h(out.ctypes.data_as(ctypes.c_void_p), self.ptr, self.size * 4)
+        return out
+
+    def copy_from_host(self, host):
+        host = np.ascontiguousarray(host, dtype=np.float32)
+        if host.size != self.size:
+            raise Exception(f"host array of {host.size} elements does not fill shape {self.shape}")
+        backend.lib().ng_h2d(self.ptr, host.ctypes.data_as(ctypes.c_void_p), self.size * 4)
+        return self
+
+    def __del__(self):
+        try:
+            if self._base is None and self._ptr:
+                backend.free(self._ptr)
+                self._ptr = 0
+        except Exception:
+            pass
+
+    def __repr__(self):
+        return f"<DeviceBuffer with shape {self.shape}>"
+
+
+class ScalarBuffer(DeviceBuffer):
+    """A Python scalar travelling as a 1-element tensor.
+
+    The reference wraps every non-Tensor positional argument into ``Tensor(np.array([x]))`` on
+    the input's device (tensor.py:482-483) — a 4-byte host-to-device copy per ``x * 0.5``.  Here
+    the value stays on the host and rides in the kernel arguments; device memory is only
+    materialised if some op really needs a pointer.
+    """
+
+    def __init__(self, value):
+        self.shape = (1,)
+        self.dtype = np.float32
+        self.size = 1
+        self._base = None
+        self._ptr = 0
+        self.value = float(value)
+
+    @property
+    def ptr(self):
+        if not self._ptr:
+            self._ptr = backend.malloc(4)
+            host = np.array([self.value], dtype=np.float32)
+            backend.lib().ng_h2d(self._ptr, host.ctypes.data_as(ctypes.c_void_p), 4)
+        return self._ptr
+
+    def numpy(self):
+        return np.array([self.value], dtype=np.float32)
+
+
+# the reference's name for the same role
+GPUBuffer = DeviceBuffer

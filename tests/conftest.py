@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _oracle_cpu_namespace():
+    """Tests run identical model code on both devices: the NumPy oracle is registered as the
+    Device.CPU operator namespace (test infrastructure only — the package ships GPU ops only)."""
+    from nanograd_b200.device import Device
+    from nanograd_b200.tensor import register_ops
+    from oracle import cpu_namespace
+    register_ops(cpu_namespace, device=Device.CPU)
+    yield

@@ -1,0 +1,59 @@
+"""TEST INFRASTRUCTURE ONLY: compile nanograd_b200/csrc/*.cu for the host (-DNG_EMU) with g++.
+
+The result (tests/emu/_build/libng_emu.so) exposes the same C ABI as the CUDA library and lets
+the CPU-only test run exercise kernel indexing and the ctypes marshalling.  It is never
+imported by the nanograd_b200 package; tests load it explicitly through
+``nanograd_b200.backend.load_library(path)``.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "nanograd_b200", "csrc")
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libng_emu.so")
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu") and not f.startswith("umma_"))
+
+
+def _deps():
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hdrs += [os.path.join(HERE, "ng_emu.h"), os.path.join(HERE, "ng_emu.cpp"),
+             os.path.join(ROOT, "include", "nanograd_b200.h")]
+    return hdrs
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    srcs = _sources() + [os.path.join(HERE, "ng_emu.cpp")]
+    newest = max(os.path.getmtime(p) for p in srcs + _deps())
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
+    flags = ["-std=c++20", "-O2", "-g", "-DNG_EMU", "-fPIC", "-pthread", "-I", HERE, "-I", CSRC,
+             "-Wno-unused-result", "-Wno-attributes"]
+    objs = []
+
+    def compile_one(src):
+        obj = os.path.join(OUT_DIR, os.path.basename(src) + ".o")
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) >= max(os.path.getmtime(src), max(os.path.getmtime(d) for d in _deps()))):
+            return obj
+        cmd = ["g++", "-x", "c++"] + flags + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    subprocess.run(["g++", "-shared", "-pthread", "-o", LIB] + objs, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

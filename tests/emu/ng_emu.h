@@ -1,0 +1,121 @@
+// TEST INFRASTRUCTURE ONLY — never shipped, never loaded by the nanograd_b200 package.
+//
+// Host emulation of the small slice of CUDA that nanograd_b200/csrc uses, so the kernel
+// *sources* can be compiled with g++ (-DNG_EMU) and executed in the GPU-less build container:
+// every CUDA thread of a block runs as a host thread, __syncthreads() is a real barrier and
+// warp shuffles exchange values between the 32 host threads of a warp.  It exists to catch
+// indexing / marshalling bugs before GPU time is spent; it is neither a fallback nor a product
+// path (the shipped library is built by nvcc for sm_100a and ng_init fails without a GPU).
+#pragma once
+
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__
+#define __grid_constant__
+#define __shared__ static
+#define __align__(n) alignas(n)
+
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+  dim3(int a) : x((unsigned)a), y(1), z(1) {}
+  dim3(long a) : x((unsigned)a), y(1), z(1) {}
+  dim3(long long a) : x((unsigned)a), y(1), z(1) {}
+};
+
+extern thread_local uint3 threadIdx;
+extern thread_local uint3 blockIdx;
+extern thread_local dim3 blockDim;
+extern thread_local dim3 gridDim;
+
+// ---- minimal runtime API ---------------------------------------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+typedef struct ng_emu_stream* cudaStream_t;
+typedef struct ng_emu_event* cudaEvent_t;
+struct ng_emu_event { std::chrono::steady_clock::time_point t; };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaEventDisableTiming = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+struct cudaDeviceProp { int multiProcessorCount, major, minor; size_t totalGlobalMem; };
+
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+  p->multiProcessorCount = 4; p->major = 10; p->minor = 0; p->totalGlobalMem = 8ull << 30; return cudaSuccess;
+}
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t n) {
+  // 256-byte aligned like cudaMalloc, plus a poisoned tail to expose overruns in tests
+  *p = aligned_alloc(256, (n + 255) / 256 * 256);
+  if (*p) memset(*p, 0xCD, (n + 255) / 256 * 256);
+  return *p ? cudaSuccess : 2;
+}
+template <typename T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaHostAlloc(void** p, size_t n, int) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new ng_emu_event(); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) { *e = new ng_emu_event(); return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess;
+}
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+
+// ---- device intrinsics -----------------------------------------------------------------------
+namespace ng_emu {
+void sync_block();
+float shfl(float v, int src_lane);
+void* dyn_smem_ptr();
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+}  // namespace ng_emu
+
+inline void __syncthreads() { ng_emu::sync_block(); }
+inline float __shfl_xor_sync(unsigned, float v, int mask) {
+  const int lane = (int)(threadIdx.x & 31);
+  return ng_emu::shfl(v, lane ^ mask);
+}
+inline float __shfl_down_sync(unsigned, float v, int delta) {
+  const int lane = (int)(threadIdx.x & 31);
+  return ng_emu::shfl(v, lane + delta < 32 ? lane + delta : lane);
+}
+inline float __shfl_sync(unsigned, float v, int src) { return ng_emu::shfl(v, src & 31); }
+inline float __ldg(const float* p) { return *p; }
+inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
+
+#ifndef INFINITY
+#define INFINITY (__builtin_inff())
+#endif

@@ -1,0 +1,170 @@
+"""Shared test helpers: tolerance definition, reference loader, device selection, model zoo."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE_ROOT = "/root/reference"
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# FP32 parity bar of BASELINE.json's north_star: rtol 1e-4 (1e-2 in TF32 mode), evaluated
+# scale-relative — allclose(rtol=R, atol=R*max|ref|) — because outputs that are sums of
+# zero-mean products land arbitrarily close to zero and a pure elementwise rtol is unattainable
+# even for the oracle against itself.
+RTOL_FP32 = 1e-4
+RTOL_TF32 = 1e-2
+
+
+def assert_close(actual, expected, rtol=RTOL_FP32, what=""):
+    actual = np.asarray(actual, dtype=np.float64)
+    expected = np.asarray(expected, dtype=np.float64)
+    assert actual.shape == expected.shape, f"{what}: shape {actual.shape} != {expected.shape}"
+    if expected.size == 0:
+        return
+    scale = float(np.max(np.abs(expected)))
+    np.testing.assert_allclose(actual, expected, rtol=rtol, atol=rtol * scale + 1e-30, err_msg=what)
+
+
+def assert_exact(actual, expected, what=""):
+    actual, expected = np.asarray(actual), np.asarray(expected)
+    assert actual.shape == expected.shape, f"{what}: shape {actual.shape} != {expected.shape}"
+    assert np.array_equal(actual, expected), f"{what}: not bit-exact ({np.sum(actual != expected)} mismatches)"
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+_REF = None
+
+
+def load_reference():
+    """Import the real reference (read-only /root/reference) next to this repo's packages.
+
+    Returns a dict of its modules, or None when the reference is not present (the GPU box).
+    The reference imports ``graphviz`` unconditionally; tests/_shim carries a stub.
+    """
+    global _REF
+    if _REF is not None:
+        return _REF or None
+    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "nanograd")):
+        _REF = {}
+        return None
+    import importlib
+    import warnings
+    shim = os.path.join(ROOT, "tests", "_shim")
+    saved_path = list(sys.path)
+    dont_write = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True  # /root/reference is read-only
+    try:
+        sys.path.insert(0, shim)
+        sys.path.insert(0, REFERENCE_ROOT)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mods = {
+                "tensor": importlib.import_module("nanograd.tensor"),
+                "module": importlib.import_module("nanograd.nn.module"),
+                "optim": importlib.import_module("nanograd.optim.optimizer"),
+                "ops_cpu": importlib.import_module("nanograd.nn.ops_cpu"),
+                "device": importlib.import_module("nanograd.device"),
+            }
+    finally:
+        sys.path[:] = saved_path
+        sys.dont_write_bytecode = dont_write
+    _REF = mods
+    return mods
+
+
+# ---------------------------------------------------------------------------- device libs
+def use_emulated_library():
+    """Bind the host-emulated build of the kernels (tests/emu) — CPU-only test runs."""
+    from nanograd_b200 import backend
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    path = build_emu.build()
+    if backend.library_path() not in (None, path):
+        import pytest
+        pytest.skip("a different device library is already bound in this process")
+    backend.load_library(path)
+    backend.init(0)
+
+
+def use_cuda_library():
+    from nanograd_b200 import backend
+    if backend.library_path() not in (None, backend.DEFAULT_LIB):
+        import pytest
+        pytest.skip("the emulated library is already bound in this process")
+    backend.load_library(backend.DEFAULT_LIB)
+    backend.init()
+
+
+# ---------------------------------------------------------------------------- op harness
+def run_on_both(shapes, fn, discrete=False, loc=30.0, scale=1.0, backward=True, seed=0, inputs=None):
+    """The reference's make_test_ops pattern (tests/helpers.py:86-132) with the NumPy oracle in
+    place of PyTorch: same seeded inputs on Device.CPU (oracle) and Device.GPU, loss = out.mean().
+    Returns (out_cpu, out_gpu, grads_cpu, grads_gpu) as NumPy arrays."""
+    from nanograd_b200.device import Device
+    from nanograd_b200.tensor import Tensor
+    rng = np.random.RandomState(seed)
+    if inputs is None:
+        inputs = []
+        for shape in shapes:
+            if discrete:
+                inputs.append(rng.randint(0, 10, shape).astype(np.float32))
+            else:
+                inputs.append(rng.normal(loc, scale, shape).astype(np.float32))
+    results = []
+    for device in (Device.CPU, Device.GPU):
+        tensors = [Tensor(a.copy(), requires_grad=backward, device=device) for a in inputs]
+        out = fn(*tensors)
+        grads = None
+        if backward:
+            out.mean().backward()
+            grads = [t.grad.numpy() for t in tensors]
+        results.append((out.numpy(), grads))
+    return results[0][0], results[1][0], results[0][1], results[1][1]
+
+
+def check_op(shapes, fn, rtol=RTOL_FP32, **kw):
+    out_c, out_g, gr_c, gr_g = run_on_both(shapes, fn, **kw)
+    assert_close(out_g, out_c, rtol, "forward")
+    if gr_c is not None:
+        for i, (gc, gg) in enumerate(zip(gr_c, gr_g)):
+            assert_close(gg, gc, rtol, f"grad of input {i}")
+
+
+# ---------------------------------------------------------------------------- models
+def build_mnist_cnn(nn):
+    """The README / tests/test_mnist.py:73-85 CNN: Conv2d(1,8,3)-relu-pool-Conv2d(8,16,3)-relu-pool-
+    flatten-Linear(400,10)-log_softmax."""
+    class CNN(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(1, 8, 3)
+            self.conv2 = nn.Conv2d(8, 16, 3)
+            self.l1 = nn.Linear(400, 10)
+
+        def forward(self, x):
+            x = x.reshape(shape=[-1, 1, 28, 28])
+            x = self.conv1(x).relu().max_pool2d()
+            x = self.conv2(x).relu().max_pool2d()
+            x = x.flatten()
+            return self.l1(x).log_softmax()
+    return CNN()
+
+
+def build_vgg(nn, widths=(64, 128, 256), in_ch=3, image=32, hidden=256, classes=10):
+    """BASELINE config 2: [Conv3x3(pad 1)-BN-ReLU]x2-MaxPool per stage, then FC."""
+    layers, c = [], in_ch
+    for w in widths:
+        layers += [nn.Conv2d(c, w, 3, 1, 1), nn.BatchNorm2d(w), nn.ReLU(),
+                   nn.Conv2d(w, w, 3, 1, 1), nn.BatchNorm2d(w), nn.ReLU(), nn.MaxPool2d(2)]
+        c = w
+        image //= 2
+    layers += [nn.Flatten(), nn.Linear(c * image * image, hidden), nn.ReLU(), nn.Linear(hidden, classes)]
+    return nn.Sequential(*layers)
+
+
+def params_to_numpy(model):
+    return [p.numpy().copy() for p in model.parameters()]
