@@ -21,3 +21,15 @@ def _oracle_cpu_namespace():
     from oracle import cpu_namespace
     register_ops(cpu_namespace, device=Device.CPU)
     yield
+
+
+@pytest.fixture(params=[pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)])
+def device_lib(request):
+    """Binds the device library for a test: the host-emulated build of the kernels on the
+    GPU-less container ("emu", small shapes), the real sm_100a library on a B200 ("cuda")."""
+    import helpers
+    if request.param == "emu":
+        helpers.use_emulated_library()
+    else:
+        helpers.use_cuda_library()
+    return request.param

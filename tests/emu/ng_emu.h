@@ -66,7 +66,7 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
-  p->multiProcessorCount = 4; p->major = 10; p->minor = 0; p->totalGlobalMem = 8ull << 30; return cudaSuccess;
+  p->multiProcessorCount = 148; p->major = 10; p->minor = 0; p->totalGlobalMem = 8ull << 30; return cudaSuccess;
 }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
