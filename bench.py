@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py — train images/sec of the CIFAR-shaped VGG/BatchNorm CNN on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" is one full training step (forward, NLL loss, backward, Adam) of BASELINE config 2 —
+[Conv3x3(pad 1)-BatchNorm2d-ReLU]x2-MaxPool for 64/128/256 channels, Linear(4096,256)-ReLU-
+Linear(256,10), log_softmax + NLLLoss, Adam(lr 1e-3) — on a batch of 512 synthetic 3x32x32 images
+per GPU.  With N GPUs (launched by torchrun, one rank per GPU) every rank trains its own shard of
+the global batch 512*N and gradients are summed by one NCCL allreduce per step (N = 8 is
+BASELINE config 4, global batch 4096): weak scaling.
+
+Printed JSON line (rank 0):
+  value        images/s with inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e          the same step through the public API with the step's batch copied from pinned
+               host memory and the loss read back to the host, inside the timed region
+  roofline     dominant kernel class (conv fprop/dgrad/wgrad or GEMM), timed with CUDA events
+               on the compute stream during the timed steps; FP32 SIMT path => the bound is the
+               FFMA pipe, peak = FFMA-saturating microkernel measured in this run
+  cpu_baseline the NumPy oracle (port of the reference's CPU path) timed on this box's host
+               cores on a bounded sample of the same workload (rank 0, N = 1 only)
+  conv2d_sweep BASELINE config 1 (Conv2d 3x3, 32x32, BS 256, C=K in 16..256): TFLOP/s per pass
+  mnist_cnn    BASELINE config 0 (README MNIST CNN, BS 128, SGD) images/s on the device
+
+--impl reference times the reference's CPU implementation of the same step (the oracle port:
+the reference is pure Python and /root/reference does not exist on the GPU box) on all host
+cores, each step a bounded sample (batch 64) of the workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PER_GPU_BATCH = 512
+CPU_SAMPLE_BATCH = 64
+LR = 1e-3
+WORKLOAD = "cifar_vgg_bn_adam_bs512_per_gpu (BASELINE configs[2]; x8 GPUs = configs[4], global batch 4096)"
+
+
+# ----------------------------------------------------------------------------- model / data
+def build_model(nn):
+    layers, c = [], 3
+    for w in (64, 128, 256):
+        layers += [nn.Conv2d(c, w, 3, 1, 1), nn.BatchNorm2d(w), nn.ReLU(),
+                   nn.Conv2d(w, w, 3, 1, 1), nn.BatchNorm2d(w), nn.ReLU(), nn.MaxPool2d(2)]
+        c = w
+    layers += [nn.Flatten(), nn.Linear(256 * 4 * 4, 256), nn.ReLU(), nn.Linear(256, 10)]
+    return nn.Sequential(*layers)
+
+
+def synthetic_batch(batch, seed):
+    rng = np.random.RandomState(seed)
+    return rng.randn(batch, 3, 32, 32).astype(np.float32), rng.randint(0, 10, batch).astype(np.float32)
+
+
+def train_step(model, opt, criterion, xb, yb):
+    out = model(xb).log_softmax()
+    opt.zero_grad()
+    loss = criterion(out, yb)
+    loss.backward()
+    opt.step()
+    return loss
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index, self.lines, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_oracle_images_per_sec(steps, warmup, batch=CPU_SAMPLE_BATCH):
+    """The oracle port of the reference's NumPy path: this repo's device-agnostic Tensor/Module/
+    Optimizer code on Device.CPU with oracle/cpu_namespace registered (composition of primitives,
+    exactly the reference's graph).  Parameters are re-created before each timed step so every
+    step starts in float32 like the reference's first step (it drifts to float64 afterwards)."""
+    import nanograd_b200.nn.module as nn
+    import nanograd_b200.optim.optimizer as optim
+    from nanograd_b200.device import Device
+    from nanograd_b200.tensor import Tensor, register_ops
+    from oracle import cpu_namespace
+    register_ops(cpu_namespace, device=Device.CPU)
+    X, Y = synthetic_batch(batch, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        np.random.seed(0)
+        model = build_model(nn)
+        opt = optim.Adam(model.parameters(), lr=LR)
+        crit = nn.NLLLoss()
+        t0 = time.perf_counter()
+        loss = train_step(model, opt, crit, Tensor(X), Tensor(Y))
+        float(loss.data[0])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return batch / float(np.mean(times)), float(np.mean(times))
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_threads()
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    # keep the whole run within a few minutes: ~3-6 s per sampled step
+    steps, warmup = min(steps, 20), min(warmup, 3)
+    ips, sec = cpu_oracle_images_per_sec(steps, warmup)
+    sample = f"{steps} steps of batch {CPU_SAMPLE_BATCH} (of {PER_GPU_BATCH}) of the same model/optimizer, float32 in"
+    line = {
+        "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (NumPy, drifts to f64)",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "per_step_sample_batch": CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- device arm
+def prof_read(lib, cls):
+    ms, n, fl, by = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_double(0), ctypes.c_double(0)
+    lib.ng_prof_read(cls, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl), ctypes.byref(by))
+    return {"ms": ms.value, "launches": n.value, "flops": fl.value, "bytes": by.value}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_class):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(kernel_class)
+        except Exception:
+            return None
+    return None
+
+
+def conv2d_sweep(B, lib, ffma_peak):
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    rows = []
+    rng = np.random.RandomState(0)
+    N, H, W, R, S = 256, 32, 32, 3, 3
+    OH, OW = H - R + 1, W - S + 1
+    for ch in (16, 32, 64, 128, 256):
+        C = K = ch
+        x = DeviceBuffer((N, C, H, W), hostbuf=rng.randn(N, C, H, W).astype(np.float32))
+        w = DeviceBuffer((K, C, R, S), hostbuf=(rng.randn(K, C, R, S) / np.sqrt(9 * C)).astype(np.float32))
+        dy = DeviceBuffer((N, K, OH, OW), hostbuf=rng.randn(N, K, OH, OW).astype(np.float32))
+        y, dx, dw = DeviceBuffer((N, K, OH, OW)), DeviceBuffer((N, C, H, W)), DeviceBuffer((K, C, R, S))
+        dims = (N, C, H, W, K, R, S, 1, 0, 0, OH, OW, 0)
+        calls = {"fprop": lambda: lib.ng_conv2d_fprop(y.ptr, x.ptr, w.ptr, 0, *dims),
+                 "dgrad": lambda: lib.ng_conv2d_dgrad(dx.ptr, dy.ptr, w.ptr, *dims),
+                 "wgrad": lambda: lib.ng_conv2d_wgrad(dw.ptr, dy.ptr, x.ptr, *dims)}
+        flops = 2.0 * N * K * C * R * S * OH * OW
+        row, total = {"C=K": ch}, 0.0
+        iters = 20 if ch <= 64 else 5
+        for name, fn in calls.items():
+            for _ in range(3):
+                fn()
+            e0, e1 = B.Event().record(), B.Event()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_ms(e1) / iters
+            total += ms
+            row[f"{name}_tflops"] = round(flops / (ms * 1e-3) / 1e12, 2)
+        row["fwd_bwd_tflops"] = round(3 * flops / (total * 1e-3) / 1e12, 2)
+        row["frac_of_ffma_peak"] = round(row["fwd_bwd_tflops"] / ffma_peak, 3) if ffma_peak else None
+        rows.append(row)
+        del x, w, dy, y, dx, dw
+    return rows
+
+
+def mnist_cnn_images_per_sec(B, steps=30, warmup=5):
+    import helpers
+    import nanograd_b200.nn.module as nn
+    import nanograd_b200.optim.optimizer as optim
+    from nanograd_b200.device import Device
+    from nanograd_b200.tensor import Tensor
+    np.random.seed(0)
+    model = helpers.build_mnist_cnn(nn)
+    model.gpu()
+    opt = optim.SGD(model.parameters(), lr=0.01, momentum=0)
+    crit = nn.NLLLoss()
+    X = np.random.rand(128, 784).astype(np.float32)
+    Y = np.random.randint(0, 10, 128).astype(np.float32)
+    xb, yb = Tensor(X, device=Device.GPU), Tensor(Y, device=Device.GPU)
+
+    def step():
+        out = model(xb)
+        opt.zero_grad()
+        loss = crit(out, yb)
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(warmup):
+        step()
+    B.sync()
+    e0, e1 = B.Event().record(), B.Event()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_ms(e1) / steps
+    return {"workload": "README MNIST CNN, BS 128, SGD (BASELINE configs[0])", "images_per_sec": round(128 / (ms * 1e-3), 1),
+            "ms_per_step": round(ms, 4), "loss": float(loss.numpy()[0])}
+
+
+def run_device_arm(args):
+    from nanograd_b200 import backend as B
+    from nanograd_b200 import dist
+    import nanograd_b200.nn.module as nn
+    import nanograd_b200.optim.optimizer as optim
+    from nanograd_b200.device import Device
+    from nanograd_b200.tensor import Tensor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nnodes=1 "
+                             f"--nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus}")
+    dist.init(use_device=True)
+    rank, world = dist.rank(), dist.world_size()
+    lib = B.lib()
+    B.init(dist.local_rank())
+
+    # identical parameters on every rank: host-side NumPy init under the same seed
+    np.random.seed(0)
+    model = build_model(nn)
+    model.gpu()
+    opt = optim.Adam(model.parameters(), lr=LR)
+    crit = nn.NLLLoss()
+    n_params = sum(int(np.prod(p.shape)) for p in model.parameters())
+
+    # this rank's shard of the global synthetic batch
+    Xh, Yh = synthetic_batch(PER_GPU_BATCH, seed=1000 + rank)
+    x_res, y_res = Tensor(Xh, device=Device.GPU), Tensor(Yh, device=Device.GPU)
+    x_pin, y_pin = B.pinned_empty(Xh.shape), B.pinned_empty(Yh.shape)
+    x_pin[...] = Xh
+    y_pin[...] = Yh
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    for _ in range(W):
+        loss = train_step(model, opt, crit, x_res, y_res)
+    float(loss.numpy()[0])
+    ffma_peak = ctypes.c_float(0)
+    lib.ng_measure_ffma_peak(4096, ctypes.byref(ffma_peak))
+    lib.ng_prof_reset()
+    lib.ng_prof_enable(1)
+    dist.barrier()
+    B.sync()
+    launches0 = B.launch_count()
+    with ClockSampler(dist.local_rank()) as clocks:
+        e0, e1 = B.Event().record(), B.Event()
+        for _ in range(K):
+            loss = train_step(model, opt, crit, x_res, y_res)
+        e1.record()
+        e1.synchronize()
+        B.sync()
+    dist.barrier()
+    lib.ng_prof_enable(0)
+    ms_total = dist.all_reduce_max(e0.elapsed_ms(e1))
+    launches = B.launch_count() - launches0
+    loss_value = float(loss.numpy()[0])
+    prof = {name: prof_read(lib, cls) for name, cls in
+            (("conv_fprop", 0), ("conv_dgrad", 1), ("conv_wgrad", 2), ("gemm", 3))}
+    lib.ng_prof_reset()
+    ms_per_step = ms_total / K
+    value = PER_GPU_BATCH * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: pinned host batch -> device each step, loss read back each step ----------------
+    for _ in range(2):
+        loss = train_step(model, opt, crit, Tensor(x_pin, device=Device.GPU), Tensor(y_pin, device=Device.GPU))
+        float(loss.numpy()[0])
+    dist.barrier()
+    B.sync()
+    e0, e1 = B.Event().record(), B.Event()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        xb = Tensor(x_pin, device=Device.GPU)   # H2D of this step's inputs (pinned source, async)
+        yb = Tensor(y_pin, device=Device.GPU)
+        loss = train_step(model, opt, crit, xb, yb)
+        float(loss.numpy()[0])                  # D2H of the step's result (blocking)
+    e1.record()
+    e1.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dist.barrier()
+    e2e_ms = dist.all_reduce_max(max(e0.elapsed_ms(e1), wall_ms)) / K
+    e2e_value = PER_GPU_BATCH * world / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        dist.shutdown()
+        return
+
+    # ---- roofline of the dominant kernel class -----------------------------------------------
+    peaks, peak_src = measured_peaks()
+    dominant = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dominant]
+    achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+    kernel_ms = sum(v["ms"] for v in prof.values())
+    roofline = {
+        "kernel": {"conv_fprop": "conv_gather_kernel<8,false> (fprop)", "conv_dgrad": "conv_gather_kernel<8,false> (dgrad)",
+                   "conv_wgrad": "conv_wgrad_kernel<8> + splitk_reduce_kernel", "gemm": "gemm_kernel"}[dominant],
+        "bound": "fp32_ffma", "achieved": round(achieved, 2), "peak": round(float(ffma_peak.value), 2),
+        "unit": "TFLOP/s", "frac": round(achieved / ffma_peak.value, 4) if ffma_peak.value else None,
+        "traffic": ncu_traffic(dominant),
+        "peak_source": "FFMA-saturating microkernel measured in this run (nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4); "
+                       "the default path is FP32 SIMT, so the tensor peak of %s (bf16 %.0f TFLOP/s) does not bound it"
+                       % (peak_src, peaks.get("bf16_tflops", 0.0)),
+        "avg_launch_ms": round(d["ms"] / max(d["launches"], 1), 4), "launches": d["launches"],
+        "share_of_step": round(d["ms"] / (ms_per_step * K), 4),
+        "contraction_share_of_step": round(kernel_ms / (ms_per_step * K), 4),
+        "per_class": {k: {"ms_per_step": round(v["ms"] / K, 4), "launches_per_step": v["launches"] / K,
+                          "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None}
+                      for k, v in prof.items()},
+        "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_src,
+    }
+
+    line = {
+        "metric": "train_images_per_sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": PER_GPU_BATCH * world, "per_gpu_batch": PER_GPU_BATCH,
+                   "image": "3x32x32", "optimizer": "Adam(lr=1e-3)", "loss": "log_softmax + NLLLoss",
+                   "params": n_params, "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": "no flush: one step touches ~1.9 GB of activations, far larger than the 126 MB L2",
+                   "math": "FP32 SIMT (FFMA) implicit-GEMM conv / GEMM"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(e2e_ms, 4),
+                "h2d_bytes_per_step": int(Xh.nbytes + Yh.nbytes), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "launches_per_step": launches / K, "loss": loss_value,
+        "clocks": clocks.summary(), "roofline": roofline,
+    }
+
+    if world == 1 and not args.no_extras:
+        # free the training graph before the side measurements
+        del loss, x_res, y_res
+        line["conv2d_sweep"] = {"workload": "Conv2d 3x3 s1 p0, x(256,C,32,32), BASELINE configs[1]",
+                                "ffma_peak_tflops": round(float(ffma_peak.value), 2),
+                                "rows": conv2d_sweep(B, lib, float(ffma_peak.value))}
+        line["mnist_cnn"] = mnist_cnn_images_per_sec(B)
+        t0 = time.perf_counter()
+        cpu_ips, cpu_sec = cpu_oracle_images_per_sec(steps=2, warmup=1)
+        line["cpu_baseline"] = {
+            "value": round(cpu_ips, 2), "unit": "images/s", "cores": host_threads(), "kind": "port",
+            "sample": f"2 steps (+1 warm-up) of batch {CPU_SAMPLE_BATCH} (of {PER_GPU_BATCH}), same model/optimizer, "
+                      f"{cpu_sec:.2f} s per step, {time.perf_counter() - t0:.1f} s total"}
+    print(json.dumps(line), flush=True)
+    dist.shutdown()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="device", choices=["device", "reference"])
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the conv2d sweep / MNIST CNN / CPU baseline side measurements (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_device_arm(args)
+
+
+if __name__ == "__main__":
+    main()

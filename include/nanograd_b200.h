@@ -59,6 +59,12 @@ int ng_event_destroy(uint64_t ev);
 int ng_flush_l2(void);
 /* FFMA-saturating microkernel: measured FP32 SIMT peak (TFLOP/s) for the roofline */
 int ng_measure_ffma_peak(int iters, float* out_tflops);
+/* per-kernel-class CUDA-event timing of the contraction kernels on the compute stream
+ * (bench.py's roofline object).  total_ms / launches / algorithmic flops and bytes per class. */
+enum { NG_PROF_CONV_FPROP = 0, NG_PROF_CONV_DGRAD = 1, NG_PROF_CONV_WGRAD = 2, NG_PROF_GEMM = 3 };
+int ng_prof_enable(int on);
+int ng_prof_reset(void);
+int ng_prof_read(int kernel_class, double* total_ms, int64_t* launches, double* flops, double* bytes);
 
 /* --------------------------------------------------------------- elementwise ------- */
 /* unary op codes — replaces unary_op(), ops_gpu.py:79-85,127-131 */

@@ -43,6 +43,9 @@ _PROTOTYPES = {
     "ng_event_destroy": [u64],
     "ng_flush_l2": [],
     "ng_measure_ffma_peak": [i32, POINTER(c_float)],
+    "ng_prof_enable": [i32],
+    "ng_prof_reset": [],
+    "ng_prof_read": [i32, POINTER(ctypes.c_double), p_i64, POINTER(ctypes.c_double), POINTER(ctypes.c_double)],
     "ng_unary": [i32, u64, u64, i64],
     "ng_binary": [i32, u64, u64, u64, i32, p_i64, p_i64, p_i64],
     "ng_binary_scalar": [i32, u64, u64, f32, i32, i64],

@@ -506,7 +506,12 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
   p.relu = (flags & NG_F_RELU) ? 1 : 0;
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) { p.tap_dy[r * S + s] = (short)r; p.tap_dx[r * S + s] = (short)s; }
-  return launch_conv_gather(p, false);
+  const double flops = 2.0 * N * K * C * R * S * (double)OH * OW;
+  const double bytes = 4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW);
+  const int tok = prof_begin(NG_PROF_CONV_FPROP, flops, bytes);
+  const int rc = launch_conv_gather(p, false);
+  prof_end(tok);
+  return rc;
 }
 
 int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, int W, int K, int R, int S,
@@ -540,7 +545,12 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
   p.relu = 0;
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) { p.tap_dy[r * S + s] = (short)(-r); p.tap_dx[r * S + s] = (short)(-s); }
-  return launch_conv_gather(p, stride > 1);
+  const double flops = 2.0 * N * K * C * R * S * (double)OH * OW;
+  const double bytes = 4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW);
+  const int tok = prof_begin(NG_PROF_CONV_DGRAD, flops, bytes);
+  const int rc = launch_conv_gather(p, stride > 1);
+  prof_end(tok);
+  return rc;
 }
 
 int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, int W, int K, int R, int S,
@@ -580,6 +590,8 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
     p.out = dptr<float>(dw);
     p.vec_store = (p.CRS % 4 == 0) && ((dw & 15u) == 0);
   }
+  const int tok = prof_begin(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
+                             4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
   dim3 grid((unsigned)ceil_div(p.CRS, CT_BM), (unsigned)ceil_div(K, bn), (unsigned)splits);
   switch (tn) {
     case 1: NG_LAUNCH((conv_wgrad_kernel<1>), grid, CT_THREADS, 0, p); break;
@@ -596,6 +608,7 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
     NG_CHECK_LAUNCH();
     pool_free(ws);
   }
+  prof_end(tok);
   return 0;
 }
 
@@ -651,6 +664,8 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
     p.ws_stride = 0;
     p.vec_store = (N % 4 == 0) && ((c & 15u) == 0);
   }
+  const int tok = prof_begin(NG_PROF_GEMM, 2.0 * (double)M * N * K * batch,
+                             4.0 * batch * ((double)M * K + (double)K * N + (double)M * N));
   dim3 grid((unsigned)ceil_div(p.I, CT_BM), (unsigned)ceil_div(p.J, bn), (unsigned)(batch * splits));
   switch (tn) {
     case 1: NG_LAUNCH((gemm_kernel<1>), grid, CT_THREADS, 0, p); break;
@@ -667,6 +682,7 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
     NG_CHECK_LAUNCH();
     pool_free(ws);
   }
+  prof_end(tok);
   return 0;
 }
 

@@ -29,6 +29,9 @@ int ensure_init();
 // Workspace from the caching pool (freed with pool_free on the same stream → safe reuse).
 int pool_alloc(void** out, uint64_t bytes);
 int pool_free(void* p);
+// Optional per-class kernel timing (ng_prof_*): returns a token (< 0 when disabled).
+int prof_begin(int cls, double flops, double bytes);
+void prof_end(int token);
 
 template <typename T>
 static inline T* dptr(uint64_t p) { return reinterpret_cast<T*>(static_cast<uintptr_t>(p)); }

@@ -315,3 +315,85 @@ int ng_measure_ffma_peak(int iters, float* out_tflops) {
 }
 
 }  // extern "C"
+
+// ---- per-kernel-class timing (bench.py roofline) ---------------------------------------------
+// When enabled, the contraction launchers bracket each launch with a CUDA-event pair on the
+// compute stream; ng_prof_read sums elapsed times per class.  Recording a timestamp does not
+// serialise the stream.
+namespace ng {
+
+struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfRec>* g_prof = nullptr;
+static std::vector<cudaEvent_t>* g_prof_free = nullptr;
+static const size_t kProfMax = 1u << 16;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_free) g_prof_free = new std::vector<cudaEvent_t>();
+  if (!g_prof_free->empty()) {
+    cudaEvent_t e = g_prof_free->back();
+    g_prof_free->pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+int prof_begin(int cls, double flops, double bytes) {
+  if (!g_prof_on) return -1;
+  if (!g_prof) g_prof = new std::vector<ProfRec>();
+  if (g_prof->size() >= kProfMax) return -1;
+  ProfRec r;
+  r.e0 = prof_event();
+  r.e1 = prof_event();
+  r.cls = cls; r.flops = flops; r.bytes = bytes;
+  cudaEventRecord(r.e0, g_stream);
+  g_prof->push_back(r);
+  return (int)g_prof->size() - 1;
+}
+
+void prof_end(int token) {
+  if (token < 0 || !g_prof) return;
+  cudaEventRecord((*g_prof)[token].e1, g_stream);
+}
+
+}  // namespace ng
+
+extern "C" {
+
+int ng_prof_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int ng_prof_reset(void) {
+  if (g_prof) {
+    if (!g_prof_free) g_prof_free = new std::vector<cudaEvent_t>();
+    for (auto& r : *g_prof) { g_prof_free->push_back(r.e0); g_prof_free->push_back(r.e1); }
+    g_prof->clear();
+  }
+  return 0;
+}
+
+int ng_prof_read(int cls, double* total_ms, int64_t* launches, double* flops, double* bytes) {
+  NG_ENSURE_INIT();
+  NG_CHECK_CUDA(cudaStreamSynchronize(g_stream));
+  double ms = 0, fl = 0, by = 0;
+  int64_t n = 0;
+  if (g_prof) {
+    for (auto& r : *g_prof) {
+      if (r.cls != cls) continue;
+      float t = 0.f;
+      NG_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+      ms += t; fl += r.flops; by += r.bytes; n++;
+    }
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  if (flops) *flops = fl;
+  if (bytes) *bytes = by;
+  return 0;
+}
+
+}  // extern "C"
