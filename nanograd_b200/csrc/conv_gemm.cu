@@ -37,96 +37,150 @@ struct ConvGatherP {
   short tap_dy[64], tap_dx[64];
 };
 
-template <int TN, bool STRIDED>
+// Reduction order of the gather loaders:
+//   GATHER_GENERIC / GATHER_STRIDED  k = kc*RS + rs (any channel count; STRIDED = dgrad of a
+//                                    strided convolution, tap positions must divide by the stride)
+//   GATHER_TAPMAJOR                  k = rs*KC + kc, KC % 8 == 0: a K-tile is 8 channels of ONE
+//                                    filter tap, so bounds are checked once per pixel per K-tile
+//                                    (a precomputed tap-validity bit) and addresses step by the
+//                                    channel stride.
+enum { GATHER_GENERIC = 0, GATHER_STRIDED = 1, GATHER_TAPMAJOR = 2 };
+
+template <class T, int MODE>
 struct ConvGatherLoader {
+  using AM = CtAMapI<T>;
   const ConvGatherP& p;
-  // A: this thread stages rows k_local = khalf + 2q of column i_local
-  const float* a_img;
-  int y0, x0, i_local, khalf;
-  bool i_valid;
-  CtKPos apos[4];
-  float ra[4];
+  const float* a_pix[AM::NP];  // &a[img][0][y0][x0] (dereferenced only where the tap is in bounds)
+  int y0[AM::NP], x0[AM::NP], il[AM::NP];
+  unsigned long long tapmask[AM::NP];  // TAPMAJOR: bit rs = tap rs in bounds for this pixel (0 if the column is padding)
+  bool i_valid[AM::NP];
+  int krow0;
+  float ra[T::EA];
   // B: elements (klane, j_local + 32q)
-  const float* b_col[CtTile<TN>::NB];
-  bool b_valid[CtTile<TN>::NB];
+  const float* b_col[T::EB];
+  bool b_valid[T::EB];
   int klane, j_local;
-  CtKPos bpos;
-  float rb[CtTile<TN>::NB];
+  CtKPos bpos;   // GENERIC: position of row klane
+  CtKPos kbase;  // GENERIC: position of row 0 of the current K-tile
+  int cur_rs, cur_c0;  // TAPMAJOR
+  float rb[T::EB];
 
   __device__ __forceinline__ ConvGatherLoader(const ConvGatherP& pp, int tile_i0, int tile_j0, int tid) : p(pp) {
-    i_local = tid & 127;
-    khalf = tid >> 7;
-    const int i = tile_i0 + i_local;
-    i_valid = i < p.M;
-    const int ii = i_valid ? i : 0;
-    const int n_img = ii / p.opix, pix = ii - n_img * p.opix;
-    const int orow = pix / p.ow_out, ocol = pix - orow * p.ow_out;
-    y0 = orow * p.y_mul + p.y_add;
-    x0 = ocol * p.x_mul + p.x_add;
-    a_img = p.a + (long long)n_img * p.a_img_stride;
+    krow0 = AM::row0(tid);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) apos[q].set(khalf + 2 * q, p.RS);
+    for (int q = 0; q < AM::NP; ++q) {
+      il[q] = AM::col(tid, q);
+      const int i = tile_i0 + il[q];
+      i_valid[q] = i < p.M;
+      const int ii = i_valid[q] ? i : 0;
+      const int n_img = ii / p.opix, pix = ii - n_img * p.opix;
+      const int orow = pix / p.ow_out, ocol = pix - orow * p.ow_out;
+      y0[q] = orow * p.y_mul + p.y_add;
+      x0[q] = ocol * p.x_mul + p.x_add;
+      a_pix[q] = p.a + (long long)n_img * p.a_img_stride + (long long)y0[q] * p.a_w + x0[q];
+      tapmask[q] = 0ull;
+      if (MODE == GATHER_TAPMAJOR && i_valid[q]) {
+        for (int t = 0; t < p.RS; ++t) {
+          const int y = y0[q] + p.tap_dy[t], x = x0[q] + p.tap_dx[t];
+          if ((unsigned)y < (unsigned)p.a_h && (unsigned)x < (unsigned)p.a_w) tapmask[q] |= (1ull << t);
+        }
+      }
+    }
     klane = tid & 7;
     j_local = tid >> 3;
     bpos.set(klane, p.RS);
+    kbase.set(0, p.RS);
+    cur_rs = 0;
+    cur_c0 = 0;
 #pragma unroll
-    for (int q = 0; q < CtTile<TN>::NB; ++q) {
+    for (int q = 0; q < T::EB; ++q) {
       const int jl = j_local + 32 * q;
       const int j = tile_j0 + jl;
-      b_valid[q] = (jl < CtTile<TN>::BN) && (j < p.J);
+      b_valid[q] = (jl < T::BN) && (j < p.J);
       b_col[q] = p.b + (long long)(b_valid[q] ? j : 0) * p.b_sj;
     }
   }
 
   __device__ __forceinline__ void fetch() {
+    if (MODE == GATHER_TAPMAJOR) {
+      const int toff = p.tap_dy[cur_rs] * p.a_w + p.tap_dx[cur_rs];
+      const long long coff = (long long)(cur_c0 + krow0) * p.a_chan_stride + toff;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float v = 0.f;
-      if (i_valid && apos[q].slow < p.KC) {
-        int y = y0 + p.tap_dy[apos[q].fast];
-        int x = x0 + p.tap_dx[apos[q].fast];
-        bool ok = true;
-        if (STRIDED) {
-          ok = (y % p.dstride == 0) && (x % p.dstride == 0);
-          y /= p.dstride;
-          x /= p.dstride;
-        }
-        ok = ok && (unsigned)y < (unsigned)p.a_h && (unsigned)x < (unsigned)p.a_w;
-        if (ok) v = a_img[(long long)apos[q].slow * p.a_chan_stride + y * p.a_w + x];
+      for (int q = 0; q < AM::NP; ++q) {
+        const bool ok = (tapmask[q] >> cur_rs) & 1ull;
+        const float* src = a_pix[q] + coff;
+#pragma unroll
+        for (int r = 0; r < AM::KP; ++r)
+          ra[q * AM::KP + r] = ok ? src[(long long)(r * AM::KSTEP) * p.a_chan_stride] : 0.f;
       }
-      ra[q] = v;
-      apos[q].advance(CT_BK, p.RS);
-    }
+      const long long boff = (long long)(cur_c0 + klane) * p.b_sc + cur_rs;
 #pragma unroll
-    for (int q = 0; q < CtTile<TN>::NB; ++q) {
-      float v = 0.f;
-      if (b_valid[q] && bpos.slow < p.KC) v = b_col[q][(long long)bpos.slow * p.b_sc + bpos.fast];
-      rb[q] = v;
+      for (int q = 0; q < T::EB; ++q) rb[q] = b_valid[q] ? b_col[q][boff] : 0.f;
+      cur_c0 += CT_BK;
+      if (cur_c0 >= p.KC) { cur_c0 = 0; ++cur_rs; }
+    } else {
+      CtKPos kp = kbase;
+      kp.advance(krow0, p.RS);
+#pragma unroll
+      for (int r = 0; r < AM::KP; ++r) {
+        const bool k_ok = kp.slow < p.KC;
+        const int dy = p.tap_dy[kp.fast], dx = p.tap_dx[kp.fast];
+#pragma unroll
+        for (int q = 0; q < AM::NP; ++q) {
+          float v = 0.f;
+          if (i_valid[q] && k_ok) {
+            int y = y0[q] + dy, x = x0[q] + dx;
+            if (MODE == GATHER_STRIDED) {
+              const bool div_ok = (y % p.dstride == 0) && (x % p.dstride == 0);
+              y /= p.dstride;
+              x /= p.dstride;
+              if (div_ok && (unsigned)y < (unsigned)p.a_h && (unsigned)x < (unsigned)p.a_w)
+                v = (a_pix[q] - ((long long)y0[q] * p.a_w + x0[q]))[(long long)kp.slow * p.a_chan_stride + y * p.a_w + x];
+            } else {
+              if ((unsigned)y < (unsigned)p.a_h && (unsigned)x < (unsigned)p.a_w)
+                v = a_pix[q][(long long)kp.slow * p.a_chan_stride + dy * p.a_w + dx];
+            }
+          }
+          ra[q * AM::KP + r] = v;
+        }
+        kp.advance(AM::KSTEP, p.RS);
+      }
+      kbase.advance(CT_BK, p.RS);
+#pragma unroll
+      for (int q = 0; q < T::EB; ++q) {
+        float v = 0.f;
+        if (b_valid[q] && bpos.slow < p.KC) v = b_col[q][(long long)bpos.slow * p.b_sc + bpos.fast];
+        rb[q] = v;
+      }
+      bpos.advance(CT_BK, p.RS);
     }
-    bpos.advance(CT_BK, p.RS);
   }
 
-  __device__ __forceinline__ void commit(float (*As)[CT_LDA], float (*Bs)[CtTile<TN>::LDB]) {
+  __device__ __forceinline__ void commit(float* As, float* Bs) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) As[khalf + 2 * q][i_local] = ra[q];
+    for (int q = 0; q < AM::NP; ++q)
 #pragma unroll
-    for (int q = 0; q < CtTile<TN>::NB; ++q) {
+      for (int r = 0; r < AM::KP; ++r) As[(krow0 + r * AM::KSTEP) * T::LDA + il[q]] = ra[q * AM::KP + r];
+#pragma unroll
+    for (int q = 0; q < T::EB; ++q) {
       const int jl = j_local + 32 * q;
-      if (jl < CtTile<TN>::BN) Bs[klane][jl] = rb[q];
+      if (jl < T::BN) Bs[klane * T::LDB + jl] = rb[q];
     }
   }
 };
 
-template <int TN, bool STRIDED>
+template <class T, int MODE>
 __global__ void __launch_bounds__(CT_THREADS, 2) conv_gather_kernel(const __grid_constant__ ConvGatherP p) {
+  NG_SHARED16 float smem[T::TILE_FLOATS];
   const int tid = threadIdx.x;
-  const int tile_i0 = blockIdx.x * CT_BM, tile_j0 = blockIdx.y * CtTile<TN>::BN;
-  const CtCoord c = ct_coord<TN>(tid);
-  float acc[8][TN];
+  const int tile_i0 = blockIdx.x * T::BM, tile_j0 = blockIdx.y * T::BN;
+  const CtCoord c = ct_coord<T>(tid);
+  float acc[8][T::TN];
+  ct_zero<T>(acc);
   {
-    ConvGatherLoader<TN, STRIDED> ld(p, tile_i0, tile_j0, tid);
+    ConvGatherLoader<T, MODE> ld(p, tile_i0, tile_j0, tid);
     const int num_kt = (p.KC * p.RS + CT_BK - 1) / CT_BK;
-    ct_mainloop<TN>(ld, num_kt, c, acc);
+    ct_mainloop<T>(ld, num_kt, c, acc, smem);
   }
   // epilogue: out[(img*J + j)*opix + pix] (+ bias[j]) ; I = img*opix + pix is contiguous per (img, j)
 #pragma unroll
@@ -136,8 +190,8 @@ __global__ void __launch_bounds__(CT_THREADS, 2) conv_gather_kernel(const __grid
     if (p.vec_store) {
       const int n_img = i / p.opix, pix = i - n_img * p.opix;
 #pragma unroll
-      for (int n = 0; n < TN; ++n) {
-        const int j = tile_j0 + ct_jcol<TN>(c, n);
+      for (int n = 0; n < T::TN; ++n) {
+        const int j = tile_j0 + ct_jcol<T>(c, n);
         if (j >= p.J) continue;
         const float bv = p.bias ? p.bias[j] : 0.f;
         float4 v;
@@ -153,8 +207,8 @@ __global__ void __launch_bounds__(CT_THREADS, 2) conv_gather_kernel(const __grid
         if (im >= p.M) continue;
         const int n_img = im / p.opix, pix = im - n_img * p.opix;
 #pragma unroll
-        for (int n = 0; n < TN; ++n) {
-          const int j = tile_j0 + ct_jcol<TN>(c, n);
+        for (int n = 0; n < T::TN; ++n) {
+          const int j = tile_j0 + ct_jcol<T>(c, n);
           if (j >= p.J) continue;
           float v = acc[4 * f + m][n] + (p.bias ? p.bias[j] : 0.f);
           if (p.relu) v = fmaxf(v, 0.f);
@@ -168,17 +222,17 @@ __global__ void __launch_bounds__(CT_THREADS, 2) conv_gather_kernel(const __grid
 // =====================================================================================
 // dense epilogue shared by wgrad and GEMM: out[z][j*ldc + i]
 // =====================================================================================
-template <int TN>
+template <class T>
 __device__ __forceinline__ void dense_store(float* out, long long ldc, int I, int J, int tile_i0, int tile_j0,
-                                            const CtCoord& c, const float (&acc)[8][TN], const float* bias_i,
+                                            const CtCoord& c, const float (&acc)[8][T::TN], const float* bias_i,
                                             int relu, int vec_store) {
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
     const int i = tile_i0 + c.i0 + 32 * f;
     if (i >= I) continue;
 #pragma unroll
-    for (int n = 0; n < TN; ++n) {
-      const int j = tile_j0 + ct_jcol<TN>(c, n);
+    for (int n = 0; n < T::TN; ++n) {
+      const int j = tile_j0 + ct_jcol<T>(c, n);
       if (j >= J) continue;
       float* dst = out + (long long)j * ldc + i;
       if (vec_store && i + 3 < I) {
@@ -229,20 +283,20 @@ struct WgradP {
   int vec_store;
 };
 
-template <int TN>
+template <class T>
 struct WgradLoader {
   const WgradP& p;
   int klane, il;  // this thread stages (klane, il + 32q) of both tiles
   // A (x gather): per q the filter position of column i
-  int a_off[4], a_dy[4], a_dx[4];
-  bool a_valid[4];
+  int a_off[T::EA], a_dy[T::EA], a_dx[T::EA];
+  bool a_valid[T::EA];
   // B (dy): per q the output channel
-  long long b_off[CtTile<TN>::NB];
-  bool b_valid[CtTile<TN>::NB];
+  long long b_off[T::EB];
+  bool b_valid[T::EB];
   // reduction position (n, oh, ow) of row klane
   int n, oh, ow;
   long long kk, kk_end;
-  float ra[4], rb[CtTile<TN>::NB];
+  float ra[T::EA], rb[T::EB];
 
   __device__ __forceinline__ WgradLoader(const WgradP& pp, int tile_i0, int tile_j0, int tid, long long kk_begin,
                                          long long kk_stop)
@@ -251,7 +305,7 @@ struct WgradLoader {
     il = tid >> 3;
     const int RS = p.R * p.S;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < T::EA; ++q) {
       const int i = tile_i0 + il + 32 * q;
       a_valid[q] = i < p.CRS;
       const int ii = a_valid[q] ? i : 0;
@@ -262,10 +316,10 @@ struct WgradLoader {
       a_off[q] = cc * p.H * p.W;
     }
 #pragma unroll
-    for (int q = 0; q < CtTile<TN>::NB; ++q) {
+    for (int q = 0; q < T::EB; ++q) {
       const int jl = il + 32 * q;
       const int j = tile_j0 + jl;
-      b_valid[q] = (jl < CtTile<TN>::BN) && (j < p.K);
+      b_valid[q] = (jl < T::BN) && (j < p.K);
       b_off[q] = (long long)(b_valid[q] ? j : 0) * p.OH * p.OW;
     }
     kk = kk_begin + klane;
@@ -282,7 +336,7 @@ struct WgradLoader {
     const int yb = oh * p.stride, xb = ow * p.stride;
     const float* x_img = p.x + (long long)n * p.C * p.H * p.W;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < T::EA; ++q) {
       float v = 0.f;
       const int y = yb + a_dy[q], x = xb + a_dx[q];
       if (k_ok && a_valid[q] && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W)
@@ -291,7 +345,7 @@ struct WgradLoader {
     }
     const float* dy_img = p.dy + (long long)n * p.K * p.OH * p.OW + oh * p.OW + ow;
 #pragma unroll
-    for (int q = 0; q < CtTile<TN>::NB; ++q) {
+    for (int q = 0; q < T::EB; ++q) {
       float v = 0.f;
       if (k_ok && b_valid[q]) v = dy_img[b_off[q]];
       rb[q] = v;
@@ -302,33 +356,35 @@ struct WgradLoader {
     while (oh >= p.OH) { oh -= p.OH; ++n; }
   }
 
-  __device__ __forceinline__ void commit(float (*As)[CT_LDA], float (*Bs)[CtTile<TN>::LDB]) {
+  __device__ __forceinline__ void commit(float* As, float* Bs) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) As[klane][il + 32 * q] = ra[q];
+    for (int q = 0; q < T::EA; ++q) As[klane * T::LDA + il + 32 * q] = ra[q];
 #pragma unroll
-    for (int q = 0; q < CtTile<TN>::NB; ++q) {
+    for (int q = 0; q < T::EB; ++q) {
       const int jl = il + 32 * q;
-      if (jl < CtTile<TN>::BN) Bs[klane][jl] = rb[q];
+      if (jl < T::BN) Bs[klane * T::LDB + jl] = rb[q];
     }
   }
 };
 
-template <int TN>
+template <class T>
 __global__ void __launch_bounds__(CT_THREADS, 2) conv_wgrad_kernel(const __grid_constant__ WgradP p) {
+  NG_SHARED16 float smem[T::TILE_FLOATS];
   const int tid = threadIdx.x;
-  const int tile_i0 = blockIdx.x * CT_BM, tile_j0 = blockIdx.y * CtTile<TN>::BN;
-  const CtCoord c = ct_coord<TN>(tid);
+  const int tile_i0 = blockIdx.x * T::BM, tile_j0 = blockIdx.y * T::BN;
+  const CtCoord c = ct_coord<T>(tid);
   const long long kk_begin = (long long)blockIdx.z * p.kt_per_split * CT_BK;
   long long kk_stop = kk_begin + (long long)p.kt_per_split * CT_BK;
   if (kk_stop > p.total_kk) kk_stop = p.total_kk;
   const int num_kt = (int)((kk_stop - kk_begin + CT_BK - 1) / CT_BK);
-  float acc[8][TN];
+  float acc[8][T::TN];
+  ct_zero<T>(acc);
   {
-    WgradLoader<TN> ld(p, tile_i0, tile_j0, tid, kk_begin, kk_stop);
-    ct_mainloop<TN>(ld, num_kt, c, acc);
+    WgradLoader<T> ld(p, tile_i0, tile_j0, tid, kk_begin, kk_stop);
+    ct_mainloop<T>(ld, num_kt, c, acc, smem);
   }
   float* out = p.out + (long long)blockIdx.z * p.K * p.CRS;
-  dense_store<TN>(out, p.CRS, p.CRS, p.K, tile_i0, tile_j0, c, acc, nullptr, 0, p.vec_store);
+  dense_store<T>(out, p.CRS, p.CRS, p.K, tile_i0, tile_j0, c, acc, nullptr, 0, p.vec_store);
 }
 
 // =====================================================================================
@@ -349,15 +405,16 @@ struct GemmP {
   int vec_store, relu;
 };
 
-template <int TN>
+template <class T>
 struct GemmLoader {
+  using AM = CtAMapI<T>;
   const GemmP& p;
   const float* a;
   const float* b;
   int tile_i0, tile_j0, tid;
   int k0, k_end;
   bool a_icontig, b_jcontig;
-  float ra[4], rb[CtTile<TN>::NB];
+  float ra[T::EA], rb[T::EB];
 
   __device__ __forceinline__ GemmLoader(const GemmP& pp, const float* aa, const float* bb, int ti0, int tj0, int t,
                                         int kb, int ke)
@@ -365,95 +422,145 @@ struct GemmLoader {
     a_icontig = (p.sai == 1);
     b_jcontig = (p.sbj == 1);
   }
-  __device__ __forceinline__ void a_coord(int q, int& kl, int& il) const {
-    if (a_icontig) { il = tid & 127; kl = (tid >> 7) + 2 * q; }
-    else { kl = tid & 7; il = (tid >> 3) + 32 * q; }
+  __device__ __forceinline__ void a_coord(int e, int& kl, int& il) const {
+    if (a_icontig) { il = AM::col(tid, e / AM::KP); kl = AM::row0(tid) + (e % AM::KP) * AM::KSTEP; }
+    else ct_map_kcontig(tid, e, kl, il);
   }
-  __device__ __forceinline__ void b_coord(int q, int& kl, int& jl) const {
-    const int e = tid + CT_THREADS * q;
-    if (b_jcontig) { jl = e % CtTile<TN>::BN; kl = e / CtTile<TN>::BN; }
-    else { kl = e & 7; jl = e >> 3; }
+  __device__ __forceinline__ void b_coord(int e, int& kl, int& jl) const {
+    if (b_jcontig) { const int x = tid + CT_THREADS * e; jl = x % T::BN; kl = x / T::BN; }
+    else ct_map_kcontig(tid, e, kl, jl);
   }
   __device__ __forceinline__ void fetch() {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int e = 0; e < T::EA; ++e) {
       int kl, il;
-      a_coord(q, kl, il);
+      a_coord(e, kl, il);
       const int i = tile_i0 + il, k = k0 + kl;
-      ra[q] = (i < p.I && k < k_end) ? a[(long long)i * p.sai + (long long)k * p.sak] : 0.f;
+      ra[e] = (i < p.I && k < k_end) ? a[(long long)i * p.sai + (long long)k * p.sak] : 0.f;
     }
 #pragma unroll
-    for (int q = 0; q < CtTile<TN>::NB; ++q) {
+    for (int e = 0; e < T::EB; ++e) {
       int kl, jl;
-      b_coord(q, kl, jl);
+      b_coord(e, kl, jl);
       const int j = tile_j0 + jl, k = k0 + kl;
-      rb[q] = (kl < CT_BK && jl < CtTile<TN>::BN && j < p.J && k < k_end)
+      rb[e] = (kl < CT_BK && jl < T::BN && j < p.J && k < k_end)
                   ? b[(long long)j * p.sbj + (long long)k * p.sbk] : 0.f;
     }
     k0 += CT_BK;
   }
-  __device__ __forceinline__ void commit(float (*As)[CT_LDA], float (*Bs)[CtTile<TN>::LDB]) {
+  __device__ __forceinline__ void commit(float* As, float* Bs) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int e = 0; e < T::EA; ++e) {
       int kl, il;
-      a_coord(q, kl, il);
-      As[kl][il] = ra[q];
+      a_coord(e, kl, il);
+      As[kl * T::LDA + il] = ra[e];
     }
 #pragma unroll
-    for (int q = 0; q < CtTile<TN>::NB; ++q) {
+    for (int e = 0; e < T::EB; ++e) {
       int kl, jl;
-      b_coord(q, kl, jl);
-      if (kl < CT_BK && jl < CtTile<TN>::BN) Bs[kl][jl] = rb[q];
+      b_coord(e, kl, jl);
+      if (kl < CT_BK && jl < T::BN) Bs[kl * T::LDB + jl] = rb[e];
     }
   }
 };
 
-template <int TN>
+template <class T>
 __global__ void __launch_bounds__(CT_THREADS, 2) gemm_kernel(const __grid_constant__ GemmP p) {
+  NG_SHARED16 float smem[T::TILE_FLOATS];
   const int tid = threadIdx.x;
-  const int tile_i0 = blockIdx.x * CT_BM, tile_j0 = blockIdx.y * CtTile<TN>::BN;
+  const int tile_i0 = blockIdx.x * T::BM, tile_j0 = blockIdx.y * T::BN;
   const int batch = blockIdx.z / p.splits, split = blockIdx.z - batch * p.splits;
-  const CtCoord c = ct_coord<TN>(tid);
+  const CtCoord c = ct_coord<T>(tid);
   const int kb = split * p.kt_per_split * CT_BK;
   int ke = kb + p.kt_per_split * CT_BK;
   if (ke > p.K) ke = p.K;
   const int num_kt = (ke - kb + CT_BK - 1) / CT_BK;
-  float acc[8][TN];
+  float acc[8][T::TN];
+  ct_zero<T>(acc);
   {
-    GemmLoader<TN> ld(p, p.a + batch * p.batch_a, p.b + batch * p.batch_b, tile_i0, tile_j0, tid, kb, ke);
-    ct_mainloop<TN>(ld, num_kt, c, acc);
+    GemmLoader<T> ld(p, p.a + batch * p.batch_a, p.b + batch * p.batch_b, tile_i0, tile_j0, tid, kb, ke);
+    ct_mainloop<T>(ld, num_kt, c, acc, smem);
   }
   float* out = p.out + (long long)split * p.ws_stride + batch * p.batch_c;
   const bool final_pass = (p.splits == 1);
-  dense_store<TN>(out, p.ldc, p.I, p.J, tile_i0, tile_j0, c, acc, final_pass ? p.bias_i : nullptr,
-                  final_pass ? p.relu : 0, p.vec_store);
+  dense_store<T>(out, p.ldc, p.I, p.J, tile_i0, tile_j0, c, acc, final_pass ? p.bias_i : nullptr,
+                 final_pass ? p.relu : 0, p.vec_store);
 }
 
-static inline int pick_tn(int J) {
-  if (J <= 16) return 1;
-  if (J <= 32) return 2;
-  if (J <= 64) return 4;
-  return 8;
+// ---- tile selection ------------------------------------------------------------------------------
+// Tiles are BM (I) x BN (J); the 8 x 8 register micro-tile is kept whenever J > 16.
+using TileA = CtTile<2, 4, 8>;  // 128 x 128
+using TileB = CtTile<4, 2, 8>;  // 256 x  64
+using TileC = CtTile<8, 1, 8>;  // 512 x  32
+using TileD = CtTile<2, 4, 4>;  // 128 x  64
+using TileE = CtTile<2, 4, 2>;  // 128 x  32
+using TileF = CtTile<2, 4, 1>;  // 128 x  16
+enum { TILE_A = 0, TILE_B, TILE_C, TILE_D, TILE_E, TILE_F };
+
+struct TileShape { int bm, bn; };
+static inline TileShape tile_shape(int t) {
+  switch (t) {
+    case TILE_A: return {128, 128};
+    case TILE_B: return {256, 64};
+    case TILE_C: return {512, 32};
+    case TILE_D: return {128, 64};
+    case TILE_E: return {128, 32};
+    default: return {128, 16};
+  }
+}
+// `wide_ok`: the loader supports BM > 128 (gather and GEMM loaders do, wgrad's does not)
+static inline int pick_tile(long long I, int J, bool wide_ok) {
+  if (J > 64) return TILE_A;
+  if (J > 32) return (wide_ok && I >= 256) ? TILE_B : TILE_D;
+  if (J > 16) return (wide_ok && I >= 512) ? TILE_C : TILE_E;
+  return TILE_F;
+}
+
+#define NG_TILE_SWITCH(tile, EXPR)                      \
+  switch (tile) {                                       \
+    case TILE_A: { using TT = TileA; EXPR; } break;     \
+    case TILE_B: { using TT = TileB; EXPR; } break;     \
+    case TILE_C: { using TT = TileC; EXPR; } break;     \
+    case TILE_D: { using TT = TileD; EXPR; } break;     \
+    case TILE_E: { using TT = TileE; EXPR; } break;     \
+    default:     { using TT = TileF; EXPR; } break;     \
+  }
+#define NG_TILE_SWITCH_NARROW(tile, EXPR)               \
+  switch (tile) {                                       \
+    case TILE_A: { using TT = TileA; EXPR; } break;     \
+    case TILE_D: { using TT = TileD; EXPR; } break;     \
+    case TILE_E: { using TT = TileE; EXPR; } break;     \
+    default:     { using TT = TileF; EXPR; } break;     \
+  }
+
+// Number of reduction splits for `tiles` output tiles on `slots` concurrently resident CTAs:
+// the candidate floor(w*slots/tiles), w = 1..8 waves, with the best wave occupancy (ties: fewer splits).
+static inline long long pick_splits(long long tiles, long long slots, long long max_splits) {
+  if (max_splits < 1) max_splits = 1;
+  long long best = 1;
+  double best_eff = 0.0;
+  for (int w = 1; w <= 8; ++w) {
+    long long s = (w * slots) / tiles;
+    if (s < 1) s = 1;
+    if (s > max_splits) s = max_splits;
+    const long long ctas = tiles * s;
+    const double eff = (double)ctas / (double)(ceil_div(ctas, slots) * slots);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    if (s == max_splits) break;
+  }
+  return best;
 }
 
 static int launch_conv_gather(const ConvGatherP& p, bool strided) {
-  const int tn = pick_tn(p.J);
-  const int bn = 16 * tn;
-  dim3 grid((unsigned)ceil_div(p.M, CT_BM), (unsigned)ceil_div(p.J, bn), 1);
+  const int tile = pick_tile(p.M, p.J, true);
+  const TileShape ts = tile_shape(tile);
+  dim3 grid((unsigned)ceil_div(p.M, ts.bm), (unsigned)ceil_div(p.J, ts.bn), 1);
   if (strided) {
-    switch (tn) {
-      case 1: NG_LAUNCH((conv_gather_kernel<1, true>), grid, CT_THREADS, 0, p); break;
-      case 2: NG_LAUNCH((conv_gather_kernel<2, true>), grid, CT_THREADS, 0, p); break;
-      case 4: NG_LAUNCH((conv_gather_kernel<4, true>), grid, CT_THREADS, 0, p); break;
-      default: NG_LAUNCH((conv_gather_kernel<8, true>), grid, CT_THREADS, 0, p); break;
-    }
+    NG_TILE_SWITCH(tile, NG_LAUNCH((conv_gather_kernel<TT, GATHER_STRIDED>), grid, CT_THREADS, 0, p));
+  } else if (p.KC % CT_BK == 0) {
+    NG_TILE_SWITCH(tile, NG_LAUNCH((conv_gather_kernel<TT, GATHER_TAPMAJOR>), grid, CT_THREADS, 0, p));
   } else {
-    switch (tn) {
-      case 1: NG_LAUNCH((conv_gather_kernel<1, false>), grid, CT_THREADS, 0, p); break;
-      case 2: NG_LAUNCH((conv_gather_kernel<2, false>), grid, CT_THREADS, 0, p); break;
-      case 4: NG_LAUNCH((conv_gather_kernel<4, false>), grid, CT_THREADS, 0, p); break;
-      default: NG_LAUNCH((conv_gather_kernel<8, false>), grid, CT_THREADS, 0, p); break;
-    }
+    NG_TILE_SWITCH(tile, NG_LAUNCH((conv_gather_kernel<TT, GATHER_GENERIC>), grid, CT_THREADS, 0, p));
   }
   NG_CHECK_LAUNCH();
   return 0;
@@ -566,17 +673,15 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
   p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
   p.CRS = C * R * S;
   p.total_kk = (long long)N * OH * OW;
-  const int tn = pick_tn(K);
-  const int bn = 16 * tn;
-  const int tiles = (int)(ceil_div(p.CRS, CT_BM) * ceil_div(K, bn));
+  const int tile = pick_tile(p.CRS, K, false);
+  const TileShape ts = tile_shape(tile);
+  const int tiles = (int)(ceil_div(p.CRS, ts.bm) * ceil_div(K, ts.bn));
   const long long total_kt = ceil_div(p.total_kk, CT_BK);
   const int sms = g_sm_count > 0 ? g_sm_count : 148;
-  // enough splits for ~2 CTAs per SM over 2 waves, each split at least 64 K-tiles deep
-  long long splits = ceil_div((long long)sms * 4, tiles);
+  // split the reduction so that the grid fills whole waves of 2 CTAs per SM (a ragged last wave
+  // is the dominant loss for these small-output problems); every split at least 64 K-tiles deep
   const long long max_splits = total_kt / 64 > 0 ? total_kt / 64 : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits > 512) splits = 512;
-  if (splits < 1) splits = 1;
+  long long splits = pick_splits(tiles, 2 * sms, max_splits < 512 ? max_splits : 512);
   p.kt_per_split = (int)ceil_div(total_kt, splits);
   splits = ceil_div(total_kt, p.kt_per_split);
   const long long out_elems = (long long)K * p.CRS;
@@ -592,13 +697,8 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
   }
   const int tok = prof_begin(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
                              4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
-  dim3 grid((unsigned)ceil_div(p.CRS, CT_BM), (unsigned)ceil_div(K, bn), (unsigned)splits);
-  switch (tn) {
-    case 1: NG_LAUNCH((conv_wgrad_kernel<1>), grid, CT_THREADS, 0, p); break;
-    case 2: NG_LAUNCH((conv_wgrad_kernel<2>), grid, CT_THREADS, 0, p); break;
-    case 4: NG_LAUNCH((conv_wgrad_kernel<4>), grid, CT_THREADS, 0, p); break;
-    default: NG_LAUNCH((conv_wgrad_kernel<8>), grid, CT_THREADS, 0, p); break;
-  }
+  dim3 grid((unsigned)ceil_div(p.CRS, ts.bm), (unsigned)ceil_div(K, ts.bn), (unsigned)splits);
+  NG_TILE_SWITCH_NARROW(tile, NG_LAUNCH((conv_wgrad_kernel<TT>), grid, CT_THREADS, 0, p));
   NG_CHECK_LAUNCH();
   if (splits > 1) {
     int g = (int)ceil_div(out_elems, 256);
@@ -635,9 +735,9 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
   p.batch_b = M * K;
   p.batch_c = M * N;
   p.relu = (flags & NG_F_RELU) ? 1 : 0;
-  const int tn = pick_tn(p.J);
-  const int bn = 16 * tn;
-  const long long tiles = ceil_div(p.I, CT_BM) * ceil_div(p.J, bn) * batch;
+  const int tile = pick_tile(p.I, p.J, true);
+  const TileShape ts = tile_shape(tile);
+  const long long tiles = ceil_div(p.I, ts.bm) * ceil_div(p.J, ts.bn) * batch;
   const long long total_kt = ceil_div(K, CT_BK);
   const int sms = g_sm_count > 0 ? g_sm_count : 148;
   long long splits = 1;
@@ -666,13 +766,8 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
   }
   const int tok = prof_begin(NG_PROF_GEMM, 2.0 * (double)M * N * K * batch,
                              4.0 * batch * ((double)M * K + (double)K * N + (double)M * N));
-  dim3 grid((unsigned)ceil_div(p.I, CT_BM), (unsigned)ceil_div(p.J, bn), (unsigned)(batch * splits));
-  switch (tn) {
-    case 1: NG_LAUNCH((gemm_kernel<1>), grid, CT_THREADS, 0, p); break;
-    case 2: NG_LAUNCH((gemm_kernel<2>), grid, CT_THREADS, 0, p); break;
-    case 4: NG_LAUNCH((gemm_kernel<4>), grid, CT_THREADS, 0, p); break;
-    default: NG_LAUNCH((gemm_kernel<8>), grid, CT_THREADS, 0, p); break;
-  }
+  dim3 grid((unsigned)ceil_div(p.I, ts.bm), (unsigned)ceil_div(p.J, ts.bn), (unsigned)(batch * splits));
+  NG_TILE_SWITCH(tile, NG_LAUNCH((gemm_kernel<TT>), grid, CT_THREADS, 0, p));
   NG_CHECK_LAUNCH();
   if (splits > 1) {
     int g = (int)ceil_div(out_elems, 256);
