@@ -90,6 +90,30 @@ U_COPY, U_NEG, U_EXP, U_LOG, U_RELU, U_SIGMOID, U_TANH, U_SQRT, U_RECIP = range(
 R_SUM, R_MAX, R_MIN = range(3)
 F_RELU, F_TF32 = 1, 2
 
+# Math mode of the contraction kernels (Conv2d/Conv1d fprop, dgrad, wgrad):
+#   "fp32" (default)  FP32 SIMT FFMA kernels, parity bar rtol 1e-4
+#   "tf32" (opt-in)   tcgen05 tensor cores with TF32 inputs / FP32 accumulation where the shape
+#                     is supported (falls back to FP32 SIMT per call otherwise), parity bar rtol 1e-2
+# Selected with NANOGRAD_B200_MATH (or the reference-survey spelling NANOGRAD_TF32=1) or set_math_mode().
+_MATH_MODES = {"fp32": 0, "tf32": F_TF32}
+_math_flags = _MATH_MODES["tf32" if os.environ.get("NANOGRAD_TF32", "0") == "1"
+                          else os.environ.get("NANOGRAD_B200_MATH", "fp32").lower()]
+
+
+def set_math_mode(mode):
+    global _math_flags
+    if mode not in _MATH_MODES:
+        raise ValueError("math mode must be one of %s" % sorted(_MATH_MODES))
+    _math_flags = _MATH_MODES[mode]
+
+
+def math_mode():
+    return [k for k, v in _MATH_MODES.items() if v == _math_flags][0]
+
+
+def math_flags():
+    return _math_flags
+
 
 class DeviceLibraryError(Exception):
     """Raised when the device library is missing or a device call fails."""

@@ -10,6 +10,7 @@
 // Padding is applied by predicated loads (no padded copy: tensor.py:419-429 disappears) and the
 // bias add of module.py:434,476 rides in the epilogue.
 #include "contract.cuh"
+#include "umma_common.cuh"
 
 namespace ng {
 
@@ -616,7 +617,12 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
   const double flops = 2.0 * N * K * C * R * S * (double)OH * OW;
   const double bytes = 4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW);
   const int tok = prof_begin(NG_PROF_CONV_FPROP, flops, bytes);
-  const int rc = launch_conv_gather(p, false);
+  int rc = -1;
+#ifndef NG_EMU
+  if (flags & NG_F_TF32)
+    rc = umma::conv_fprop_tf32(p.out, p.a, p.b, p.bias, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW, p.relu);
+#endif
+  if (rc < 0) rc = launch_conv_gather(p, false);
   prof_end(tok);
   return rc;
 }
@@ -624,7 +630,6 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
 int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int flags) {
   NG_ENSURE_INIT();
-  (void)flags;
   if (check_conv_dims("ng_conv2d_dgrad", N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW)) return 1;
   // dx[n,c,ih,iw] = sum_{k,r,s} dy[n,k,(ih+pt-r)/st,(iw+pl-s)/st] * w[k,c,r,s]
   ConvGatherP p;
@@ -655,7 +660,12 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
   const double flops = 2.0 * N * K * C * R * S * (double)OH * OW;
   const double bytes = 4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW);
   const int tok = prof_begin(NG_PROF_CONV_DGRAD, flops, bytes);
-  const int rc = launch_conv_gather(p, stride > 1);
+  int rc = -1;
+#ifndef NG_EMU
+  if (flags & NG_F_TF32)
+    rc = umma::conv_dgrad_tf32(p.out, p.a, p.b, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW);
+#endif
+  if (rc < 0) rc = launch_conv_gather(p, stride > 1);
   prof_end(tok);
   return rc;
 }

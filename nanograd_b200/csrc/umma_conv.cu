@@ -1,0 +1,428 @@
+// Tensor-core (tcgen05, TF32 inputs / FP32 accumulate) implicit-GEMM convolution for sm_100a.
+//
+// Opt-in path (flag NG_F_TF32) behind the same C-ABI entry points as the FP32 SIMT kernels of
+// conv_gemm.cu; stated tolerance rtol 1e-2 (scale-relative) against the reference's NumPy path
+// (nanograd/nn/ops_cpu.py:345-400).  The C ABI keeps the reference's layouts (NCHW activations,
+// KCRS filters, NCHW results).
+//
+// Measured on B200 (tools/umma_probe*.cu): a TMA box must start at a 16-byte aligned innermost
+// coordinate, so the +-1 pixel tap shifts cannot be expressed on the W axis of an NCHW tensor.
+// Each call therefore stages a channels-last (NHWC) copy of the gathered activation tensor
+// (one bandwidth-bound transpose), after which every filter tap is a TMA box shifted along the
+// non-innermost W/H axes, with zero padding supplied by TMA out-of-bounds fill.
+//
+// fprop / dgrad ("gather" kernel), stride 1:
+//   GEMM view  D[pixel, j] = sum_{tap, kc} A[pixel shifted by tap, kc] * B[tap][j][kc]
+//   A  activations NHWC, per (tap, 32-channel chunk) ONE 4-D TMA box {32 c, w, rows, imgs} ->
+//      shared memory [128 pixels][32 c] = canonical K-major UMMA operand, 128B swizzle.
+//   B  filters, re-laid once per call as [tap][j][kc] (K-major, 128B swizzle), 3-D TMA box.
+//   D  128 pixels x N_TILE output channels, FP32 in TMEM, double buffered so the epilogue of tile
+//      t (TMEM -> registers -> +bias/ReLU -> coalesced NCHW stores) overlaps the MMAs of tile t+1.
+//   Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer
+//   (single elected thread), warps 2-5 epilogue.
+#include "umma_common.cuh"
+
+#ifndef NG_EMU
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+namespace ng {
+namespace umma {
+
+// ------------------------------------------------------------------ driver entry point
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return set_error("cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
+  if (load_encode()) return 1;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle == SWZ_128B) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else if (swizzle == SWZ_64B) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle == SWZ_32B) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                        bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// ------------------------------------------------------------------ filter re-layout
+// dst[(rs*J + j)*KC + kc] = w[j*sj + kc*sc + rs]
+__global__ void __launch_bounds__(256) filter_relayout_kernel(float* __restrict__ dst, const float* __restrict__ w,
+                                                              int J, int KC, int RS, long long sj, long long sc) {
+  const long long n = (long long)J * KC * RS;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int kc = (int)(e % KC);
+    const long long t = e / KC;
+    const int j = (int)(t % J);
+    const int rs = (int)(t / J);
+    dst[e] = w[(long long)j * sj + (long long)kc * sc + rs];
+  }
+}
+
+// ------------------------------------------------------------------ NCHW -> NHWC staging copy
+// out[n][p][c] = in[n][c][p], p = h*W + w.  32 x 32 tiles through shared memory, coalesced both ways.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(float* __restrict__ out, const float* __restrict__ in, int C,
+                                                           int HW) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const long long img = (long long)blockIdx.z * C * HW;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, p = p0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && p < HW) ? in[img + (long long)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty + 8 * i, c = c0 + tx;
+    if (p < HW && c < C) out[img + (long long)p * C + c] = tile[tx][ty + 8 * i];
+  }
+}
+
+int to_nhwc(float* out, const float* in, int N, int C, int HW) {
+  dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N);
+  NG_LAUNCH(nchw_to_nhwc_kernel, grid, 256, 0, out, in, C, HW);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ gather kernel (fprop / dgrad)
+constexpr int G_THREADS = 192;
+constexpr int G_CCHUNK = 32;        // channels per pipeline stage (4 MMAs of K = 8)
+constexpr int G_MAX_STAGES = 8;
+
+struct GatherP {
+  CUtensorMap tm_a;  // activations NHWC, dims (C, W, H, N)
+  CUtensorMap tm_b;  // filters [tap][j][kc], dims (KC, J, RS)
+  float* out;
+  const float* bias;
+  int n_img, J, KC, RS, OH, OW;
+  int w_tile, rows_tile, imgs_tile;   // w_tile * rows_tile * imgs_tile == 128
+  int tiles_w, tiles_h, tiles_img;
+  int n_tile, n_tiles;                // MMA N and the number of output-channel tiles
+  int c_chunks;
+  uint32_t idesc;
+  uint32_t stage_a_bytes, stage_b_bytes;
+  int stages;
+  uint32_t tmem_cols;
+  int relu;
+  uint32_t* dbg;  // host-mapped progress words (NG_UMMA_DEBUG=1), else null
+  short tap_dx[64], tap_dy[64];
+};
+
+#define NG_DBG(i, v)                                   \
+  do {                                                 \
+    if (p.dbg) { ((volatile uint32_t*)p.dbg)[i] = (v); __threadfence_system(); } \
+  } while (0)
+
+__global__ void __launch_bounds__(G_THREADS, 1) umma_conv_gather_kernel(const __grid_constant__ GatherP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + G_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + G_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_a);
+    tma_prefetch_desc(&p.tm_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0 && blockIdx.x == 0) { NG_DBG(4, tmem_base); NG_DBG(5, 0x1111u); }
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int k_iters = p.RS * p.c_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_t = tile % p.n_tiles;
+        int m_t = tile / p.n_tiles;
+        const int tw = m_t % p.tiles_w; m_t /= p.tiles_w;
+        const int th = m_t % p.tiles_h;
+        const int ti = m_t / p.tiles_h;
+        const int col0 = tw * p.w_tile, row0 = th * p.rows_tile, img0 = ti * p.imgs_tile;
+        for (int rs = 0; rs < p.RS; ++rs) {
+          const int cx = col0 + p.tap_dx[rs], cy = row0 + p.tap_dy[rs];
+          for (int cc = 0; cc < p.c_chunks; ++cc) {
+            mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+            tma_load_4d(sa, &p.tm_a, &full_bar[s], cc * G_CCHUNK, cx, cy, img0);
+            tma_load_3d(sa + p.stage_a_bytes, &p.tm_b, &full_bar[s], cc * G_CCHUNK, n_t * p.n_tile, rs);
+            if (blockIdx.x == 0) NG_DBG(8, (uint32_t)(rs * 256 + cc + 1));
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aph ^ 1u, p.dbg, 0x200u + as);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.n_tile);
+        uint32_t accumulate = 0;
+        for (int it = 0; it < k_iters; ++it) {
+          const int cc = it % p.c_chunks;
+          int ksteps = (p.KC - cc * G_CCHUNK + 7) >> 3;
+          if (ksteps > 4) ksteps = 4;
+          mbar_wait(&full_bar[s], ph, p.dbg, 0x300u + s);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + p.stage_a_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
+            const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
+            mma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+            accumulate = 1;
+          }
+          mma_commit(&empty_bar[s]);
+          if (blockIdx.x == 0) NG_DBG(9, (uint32_t)(it + 1));
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        mma_commit(&tmem_full[as]);
+        as ^= 1;
+        if (as == 0) aph ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int g = m / p.w_tile, wcol = m - g * p.w_tile;
+    const int gi = g / p.rows_tile, gr = g - gi * p.rows_tile;
+    const long long opix = (long long)p.OH * p.OW;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % p.n_tiles;
+      int m_t = tile / p.n_tiles;
+      const int tw = m_t % p.tiles_w; m_t /= p.tiles_w;
+      const int th = m_t % p.tiles_h;
+      const int ti = m_t / p.tiles_h;
+      const int col = tw * p.w_tile + wcol, row = th * p.rows_tile + gr, img = ti * p.imgs_tile + gi;
+      const bool valid = (col < p.OW) && (row < p.OH) && (img < p.n_img);
+      float* out_pix = p.out + ((long long)img * p.J) * opix + (long long)row * p.OW + col;
+      mbar_wait(&tmem_full[as], aph, p.dbg, 0x400u + as);
+      tc_fence_after();
+      if (blockIdx.x == 0 && threadIdx.x == 64) NG_DBG(10, (uint32_t)(tile + 1));
+      for (int j0 = 0; j0 < p.n_tile; j0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.n_tile + j0);
+        tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        const int jbase = n_t * p.n_tile + j0;
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = jbase + i;
+            if (j < p.J) {
+              float v = __uint_as_float(r[i]);
+              if (p.bias) v += __ldg(p.bias + j);
+              if (p.relu) v = fmaxf(v, 0.f);
+              out_pix[(long long)j * opix] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      as ^= 1;
+      if (as == 0) aph ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static inline int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+// Launches the gather kernel.  `act` is the gathered activation tensor [n_img, KC, AH, AW] (NCHW);
+// `filt` the KCRS filters addressed as filt[j*sj + kc*sc + rs]; the output is [n_img, J, OH, OW].
+// Returns 0 on success, -1 when the shape is not supported by this path (caller falls back to
+// the SIMT kernel), > 0 on error.
+static int launch_gather(float* out, const float* act, const float* filt, const float* bias, int n_img, int KC, int AH,
+                         int AW, int J, int R, int S, long long sj, long long sc, int OH, int OW, const int* tap_dy,
+                         const int* tap_dx, int relu) {
+  const int RS = R * S;
+  if (KC % 4 != 0 || KC < 8 || RS > 64 || J < 8) return -1;
+  GatherP p;
+  memset(&p, 0, sizeof(p));
+  p.out = out;
+  p.bias = bias;
+  p.n_img = n_img; p.J = J; p.KC = KC; p.RS = RS; p.OH = OH; p.OW = OW;
+  int w_tile = pow2_ceil(OW);
+  if (w_tile > 32) w_tile = 32;
+  int rows = 128 / w_tile;
+  const int oh2 = pow2_ceil(OH);
+  if (rows > oh2) rows = oh2;
+  p.w_tile = w_tile;
+  p.rows_tile = rows;
+  p.imgs_tile = 128 / (w_tile * rows);
+  p.tiles_w = (int)ceil_div(OW, p.w_tile);
+  p.tiles_h = (int)ceil_div(OH, rows);
+  p.tiles_img = (int)ceil_div(n_img, p.imgs_tile);
+  int n_tile = (int)ceil_div(J, 32) * 32;
+  if (n_tile > 256) n_tile = 256;
+  p.n_tile = n_tile;
+  p.n_tiles = (int)ceil_div(J, n_tile);
+  p.c_chunks = (int)ceil_div(KC, G_CCHUNK);
+  p.idesc = make_idesc_tf32(128, n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
+  p.stage_a_bytes = 128u * G_CCHUNK * 4u;
+  p.stage_b_bytes = (uint32_t)n_tile * 128u;
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  const uint32_t budget = 227u * 1024u - 2048u;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
+  if (stages < 2) return -1;
+  p.stages = stages;
+  p.tmem_cols = (uint32_t)pow2_ceil(2 * n_tile < 32 ? 32 : 2 * n_tile);
+  p.relu = relu;
+  for (int t = 0; t < RS; ++t) { p.tap_dx[t] = (short)tap_dx[t]; p.tap_dy[t] = (short)tap_dy[t]; }
+
+  // staging: activations -> NHWC, filters -> [tap][j][kc]
+  float* act_t = nullptr;
+  float* wt = nullptr;
+  if (pool_alloc((void**)&act_t, (uint64_t)n_img * KC * AH * AW * sizeof(float))) return 1;
+  if (pool_alloc((void**)&wt, (uint64_t)RS * J * KC * sizeof(float))) { pool_free(act_t); return 1; }
+  int rc = to_nhwc(act_t, act, n_img, KC, AH * AW);
+  if (rc == 0) {
+    const long long n = (long long)RS * J * KC;
+    int g = (int)ceil_div(n, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    NG_LAUNCH(filter_relayout_kernel, g, 256, 0, wt, filt, J, KC, RS, sj, sc);
+    const uint64_t dims[4] = {(uint64_t)KC, (uint64_t)AW, (uint64_t)AH, (uint64_t)n_img};
+    const uint64_t strides[3] = {(uint64_t)KC * 4u, (uint64_t)AW * KC * 4u, (uint64_t)AH * AW * KC * 4u};
+    const uint32_t box[4] = {(uint32_t)G_CCHUNK, (uint32_t)p.w_tile, (uint32_t)p.rows_tile, (uint32_t)p.imgs_tile};
+    if (encode_tensor_map(&p.tm_a, act_t, 4, dims, strides, box, SWZ_128B)) rc = -1;
+  }
+  if (rc == 0) {
+    const uint64_t dims[3] = {(uint64_t)KC, (uint64_t)J, (uint64_t)RS};
+    const uint64_t strides[2] = {(uint64_t)KC * 4u, (uint64_t)J * KC * 4u};
+    const uint32_t box[3] = {(uint32_t)G_CCHUNK, (uint32_t)n_tile, 1u};
+    if (encode_tensor_map(&p.tm_b, wt, 3, dims, strides, box, SWZ_128B)) rc = -1;
+  }
+  if (rc == 0) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(umma_conv_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(227 * 1024));
+      if (e != cudaSuccess) rc = set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      configured = (e == cudaSuccess);
+    }
+  }
+  if (rc == 0) {
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_img * p.n_tiles;
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    const int grid = total_tiles < sms ? total_tiles : sms;
+    static uint32_t* dbg_host = nullptr;
+    const bool debug = getenv("NG_UMMA_DEBUG") != nullptr;
+    if (debug) {
+      if (!dbg_host) cudaHostAlloc((void**)&dbg_host, 64 * sizeof(uint32_t), cudaHostAllocMapped);
+      memset(dbg_host, 0, 64 * sizeof(uint32_t));
+      p.dbg = dbg_host;
+      fprintf(stderr, "[umma] gather: tiles %d grid %d n_tile %d stages %d w_tile %d rows %d imgs %d idesc %08x tmem %u\n",
+              total_tiles, grid, p.n_tile, p.stages, p.w_tile, p.rows_tile, p.imgs_tile, p.idesc, p.tmem_cols);
+    }
+    NG_LAUNCH(umma_conv_gather_kernel, grid, G_THREADS, smem_bytes, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = set_error("umma_conv_gather_kernel launch failed: %s", cudaGetErrorString(e));
+    if (debug) {
+      cudaError_t e2 = cudaStreamSynchronize(g_stream);
+      fprintf(stderr, "[umma] sync: %s ; dbg:", cudaGetErrorString(e2));
+      for (int i = 0; i < 12; ++i) fprintf(stderr, " %08x", dbg_host[i]);
+      fprintf(stderr, "\n");
+    }
+  }
+  pool_free(wt);
+  pool_free(act_t);
+  return rc;
+}
+
+int conv_fprop_tf32(float* y, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int K,
+                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu) {
+  if (stride != 1) return -1;
+  int dy[64], dx[64];
+  if (R * S > 64) return -1;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) { dy[r * S + s] = r - pad_t; dx[r * S + s] = s - pad_l; }
+  return launch_gather(y, x, w, bias, N, C, H, W, K, R, S, (long long)C * R * S, (long long)R * S, OH, OW, dy, dx,
+                       relu);
+}
+
+int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int C, int H, int W, int K, int R, int S,
+                    int stride, int pad_t, int pad_l, int OH, int OW) {
+  if (stride != 1) return -1;
+  int dy[64], dx[64];
+  if (R * S > 64) return -1;
+  // dx[n,c,y,x] = sum_{k,r,s} dy[n,k,y+pt-r,x+pl-s] * w[k,c,r,s]
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) { dy[r * S + s] = pad_t - r; dx[r * S + s] = pad_l - s; }
+  return launch_gather(dx_out, dyv, w, nullptr, N, K, OH, OW, C, R, S, (long long)R * S, (long long)C * R * S, H, W,
+                       dy, dx, 0);
+}
+
+}  // namespace umma
+}  // namespace ng
+#endif  // NG_EMU

@@ -544,21 +544,21 @@ def _conv2d_forward(x, w, bias, stride, padding, flags=0):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x.shape, w.shape, stride, padding)
     y = DeviceBuffer((n, k, oh, ow))
     _lib().ng_conv2d_fprop(y.ptr, x.ptr, w.ptr, bias.ptr if bias is not None else 0,
-                           n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, flags)
+                           n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, flags | B.math_flags())
     return y
 
 
 def _conv2d_dgrad(dy, w, x_shape, stride, padding):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x_shape, w.shape, stride, padding)
     dx = DeviceBuffer(x_shape)
-    _lib().ng_conv2d_dgrad(dx.ptr, dy.ptr, w.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, 0)
+    _lib().ng_conv2d_dgrad(dx.ptr, dy.ptr, w.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, B.math_flags())
     return dx
 
 
 def _conv2d_wgrad(dy, x, w_shape, stride, padding):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x.shape, w_shape, stride, padding)
     dw = DeviceBuffer(w_shape)
-    _lib().ng_conv2d_wgrad(dw.ptr, dy.ptr, x.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, 0)
+    _lib().ng_conv2d_wgrad(dw.ptr, dy.ptr, x.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, B.math_flags())
     return dw
 
 
