@@ -673,8 +673,17 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
 int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int flags) {
   NG_ENSURE_INIT();
-  (void)flags;
   if (check_conv_dims("ng_conv2d_wgrad", N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW)) return 1;
+#ifndef NG_EMU
+  if (flags & NG_F_TF32) {
+    const int tok = prof_begin(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
+                               4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
+    const int rc = umma::conv_wgrad_tf32(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R,
+                                         S, stride, pad_t, pad_l, OH, OW);
+    prof_end(tok);
+    if (rc >= 0) return rc;
+  }
+#endif
   WgradP p;
   memset(&p, 0, sizeof(p));
   p.x = dptr<const float>(x);

@@ -86,6 +86,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM allocation
 // Executed by one full warp.  The base address (lane 0, first column) lands in *smem_dst.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -142,7 +151,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [ 0,14) start address >> 4      [16,30) leading-dimension byte offset >> 4
 //   [32,46) stride-dimension byte offset >> 4      [46,48) version = 1 (Blackwell)
 //   [49,52) base offset = 0         [61,64) swizzle: 0 none, 2 = 128B, 4 = 64B, 6 = 32B
-enum { SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };
+//   1 = 128B rows swizzled in 32B atoms: the only layout for MN-major 32-bit (TF32) operands
+enum { SWZ_NONE = 0, SWZ_128B_ATOM32 = 1, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };
 __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
                                                             uint32_t sbo_bytes, uint32_t swizzle) {
   uint64_t d = 0;
@@ -181,6 +191,8 @@ int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64
 int conv_fprop_tf32(float* y, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int K,
                     int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu);
 int conv_dgrad_tf32(float* dx, const float* dy, const float* w, int N, int C, int H, int W, int K, int R, int S,
+                    int stride, int pad_t, int pad_l, int OH, int OW);
+int conv_wgrad_tf32(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW);
 
 }  // namespace umma

@@ -61,6 +61,7 @@ int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64
   if (swizzle == SWZ_128B) sw = CU_TENSOR_MAP_SWIZZLE_128B;
   else if (swizzle == SWZ_64B) sw = CU_TENSOR_MAP_SWIZZLE_64B;
   else if (swizzle == SWZ_32B) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle == SWZ_128B_ATOM32) sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
                         bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -421,6 +422,277 @@ int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int 
     for (int s = 0; s < S; ++s) { dy[r * S + s] = pad_t - r; dx[r * S + s] = pad_l - s; }
   return launch_gather(dx_out, dyv, w, nullptr, N, K, OH, OW, C, R, S, (long long)R * S, (long long)C * R * S, H, W,
                        dy, dx, 0);
+}
+
+
+// ------------------------------------------------------------------ wgrad kernel
+//   per filter tap t = (r, s):   D_t[c][k] = sum_{n,oh,ow} x[n, oh+r-pt, ow+s-pl, c] * dy[n, oh, ow, k]
+// Both operands come from the NHWC staging copies, so both are MN-major (channel-contiguous) UMMA
+// operands: shared memory [pixel][32 channels] rows of 128 B in the 128B/32B-atom swizzle, the
+// only layout the tensor core accepts for MN-major 32-bit data.  The reduction runs over pixels
+// (8 per MMA, 32 per pipeline stage).
+//   M = 128 rows = (128 / Cm) taps x Cm input channels  (Cm = min(C, 128)): narrow layers put
+//       several taps of the same channel tile side by side so the MMA is always 128 rows tall;
+//   N = up to 256 output channels;  one 5-D TMA box per tap for x, one for dy, per stage.
+// CTA = (tap group, c tile, k tile, split of the pixel range); partial sums go to a workspace
+// [split][tap][c][k] and a second pass reduces the splits in a fixed order (deterministic) and
+// writes KCRS.
+constexpr int W_THREADS = 192;
+constexpr int W_MAX_STAGES = 6;
+
+struct WgradUP {
+  CUtensorMap tm_x;   // x NHWC as (32, W, H, C/32, N)
+  CUtensorMap tm_dy;  // dy NHWC as (32, OW, OH, K/32, N)
+  float* ws;          // [splits][RS][C][K]
+  int C, K, RS, S;
+  int Cm, taps_per_cta, tap_groups, c_tiles, n_tile, n_tiles;
+  int w_c, rows_c, chunks_w, chunks_h, total_chunks, chunks_per_split, splits;
+  int pad_t, pad_l;
+  uint32_t idesc, stage_a_bytes, stage_b_bytes, tmem_cols;
+  int stages;
+  uint32_t* dbg;
+};
+
+__global__ void __launch_bounds__(W_THREADS, 1) umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + W_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + W_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_x);
+    tma_prefetch_desc(&p.tm_dy);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item
+  int item = blockIdx.x;
+  const int split = item % p.splits; item /= p.splits;
+  const int n_t = item % p.n_tiles; item /= p.n_tiles;
+  const int c_t = item % p.c_tiles;
+  const int tg = item / p.c_tiles;
+  const int chunk_begin = split * p.chunks_per_split;
+  int chunk_end = chunk_begin + p.chunks_per_split;
+  if (chunk_end > p.total_chunks) chunk_end = p.total_chunks;
+  const int n_chunks = chunk_end > chunk_begin ? chunk_end - chunk_begin : 0;
+  const int tap0 = tg * p.taps_per_cta;
+  int n_taps = p.RS - tap0;
+  if (n_taps > p.taps_per_cta) n_taps = p.taps_per_cta;
+  const int groups_per_tap = p.Cm >> 5;
+  const uint32_t tap_bytes = (uint32_t)groups_per_tap * 4096u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ch = chunk_begin; ch < chunk_end; ++ch) {
+        int t = ch;
+        const int cw = t % p.chunks_w; t /= p.chunks_w;
+        const int chh = t % p.chunks_h;
+        const int img = t / p.chunks_h;
+        const int ow0 = cw * p.w_c, oh0 = chh * p.rows_c;
+        mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)n_taps * tap_bytes + p.stage_b_bytes);
+        for (int tl = 0; tl < n_taps; ++tl) {
+          const int tap = tap0 + tl;
+          const int r = tap / p.S, sx = tap - r * p.S;
+          tma_load_5d(sa + (size_t)tl * tap_bytes, &p.tm_x, &full_bar[s], 0, ow0 + sx - p.pad_l, oh0 + r - p.pad_t,
+                      c_t * groups_per_tap, img);
+        }
+        tma_load_5d(sa + p.stage_a_bytes, &p.tm_dy, &full_bar[s], 0, ow0, oh0, n_t * (p.n_tile >> 5), img);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t accumulate = 0;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(&full_bar[s], ph, p.dbg, 0x300u + s);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + p.stage_a_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
+          const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
+          mma_tf32(tmem_base, adesc, bdesc, p.idesc, accumulate);
+          accumulate = 1;
+        }
+        mma_commit(&empty_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int tl = m / p.Cm, cl = m - tl * p.Cm;
+    const int tap = tap0 + tl;
+    const int c = c_t * p.Cm + cl;
+    mbar_wait(tmem_full, 0, p.dbg, 0x400u);
+    tc_fence_after();
+    float* dst_row = p.ws + (((long long)split * p.RS + tap) * p.C + c) * p.K + (long long)n_t * p.n_tile;
+    const bool row_ok = (tl < n_taps);
+    for (int j0 = 0; j0 < p.n_tile; j0 += 32) {
+      uint32_t r[32];
+      if (n_chunks > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (row_ok && n_t * p.n_tile + j0 < p.K) {
+        float4* d4 = reinterpret_cast<float4*>(dst_row + j0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                              __uint_as_float(r[4 * i + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// dw[k][c][rs] = sum_split ws[split][rs][c][k]   (fixed summation order)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ dw, const float* __restrict__ ws, int splits,
+                                                           int RS, int C, int K) {
+  const long long n = (long long)RS * C * K;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * n + e];
+    const int k = (int)(e % K);
+    const long long t = e / K;
+    const int c = (int)(t % C);
+    const int rs = (int)(t / C);
+    dw[((long long)k * C + c) * RS + rs] = acc;
+  }
+}
+
+int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, int H, int W, int K, int R, int S,
+                    int stride, int pad_t, int pad_l, int OH, int OW) {
+  const int RS = R * S;
+  if (stride != 1 || C % 32 != 0 || K % 32 != 0 || RS > 64) return -1;
+  WgradUP p;
+  memset(&p, 0, sizeof(p));
+  p.C = C; p.K = K; p.RS = RS; p.S = S;
+  p.pad_t = pad_t; p.pad_l = pad_l;
+  p.Cm = (C % 128 == 0) ? 128 : ((C % 64 == 0) ? 64 : 32);
+  p.taps_per_cta = 128 / p.Cm;
+  p.tap_groups = (int)ceil_div(RS, p.taps_per_cta);
+  p.c_tiles = C / p.Cm;
+  p.n_tile = K < 256 ? K : 256;
+  p.n_tiles = (int)ceil_div(K, p.n_tile);
+  int w_c = pow2_ceil(OW);
+  if (w_c > 32) w_c = 32;
+  p.w_c = w_c;
+  p.rows_c = 32 / w_c;
+  p.chunks_w = (int)ceil_div(OW, w_c);
+  p.chunks_h = (int)ceil_div(OH, p.rows_c);
+  p.total_chunks = N * p.chunks_h * p.chunks_w;
+  const int items = p.tap_groups * p.c_tiles * p.n_tiles;
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  int splits = sms / items;
+  if (splits < 1) splits = 1;
+  if (splits > p.total_chunks) splits = p.total_chunks;
+  p.chunks_per_split = (int)ceil_div(p.total_chunks, splits);
+  splits = (int)ceil_div(p.total_chunks, p.chunks_per_split);
+  p.splits = splits;
+  p.idesc = make_idesc_tf32(128, p.n_tile, /*a MN-major*/ 1, /*b MN-major*/ 1);
+  p.stage_a_bytes = 128u * 128u;
+  p.stage_b_bytes = (uint32_t)p.n_tile * 128u;
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  int stages = (int)((227u * 1024u - 2048u) / stage_bytes);
+  if (stages > W_MAX_STAGES) stages = W_MAX_STAGES;
+  p.stages = stages;
+  p.tmem_cols = (uint32_t)pow2_ceil(p.n_tile < 32 ? 32 : p.n_tile);
+
+  float *x_t = nullptr, *dy_t = nullptr, *ws = nullptr;
+  if (pool_alloc((void**)&x_t, (uint64_t)N * C * H * W * sizeof(float))) return 1;
+  if (pool_alloc((void**)&dy_t, (uint64_t)N * K * OH * OW * sizeof(float))) { pool_free(x_t); return 1; }
+  if (pool_alloc((void**)&ws, (uint64_t)splits * RS * C * K * sizeof(float))) { pool_free(x_t); pool_free(dy_t); return 1; }
+  p.ws = ws;
+  int rc = to_nhwc(x_t, x, N, C, H * W);
+  if (rc == 0) rc = to_nhwc(dy_t, dyv, N, K, OH * OW);
+  if (rc == 0) {
+    const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)(C / 32), (uint64_t)N};
+    const uint64_t strides[4] = {(uint64_t)C * 4u, (uint64_t)W * C * 4u, 128u, (uint64_t)H * W * C * 4u};
+    const uint32_t box[5] = {32u, (uint32_t)w_c, (uint32_t)p.rows_c, (uint32_t)(p.Cm / 32), 1u};
+    if (encode_tensor_map(&p.tm_x, x_t, 5, dims, strides, box, SWZ_128B_ATOM32)) rc = -1;
+  }
+  if (rc == 0) {
+    const uint64_t dims[5] = {32u, (uint64_t)OW, (uint64_t)OH, (uint64_t)(K / 32), (uint64_t)N};
+    const uint64_t strides[4] = {(uint64_t)K * 4u, (uint64_t)OW * K * 4u, 128u, (uint64_t)OH * OW * K * 4u};
+    const uint32_t box[5] = {32u, (uint32_t)w_c, (uint32_t)p.rows_c, (uint32_t)(p.n_tile / 32), 1u};
+    if (encode_tensor_map(&p.tm_dy, dy_t, 5, dims, strides, box, SWZ_128B_ATOM32)) rc = -1;
+  }
+  if (rc == 0) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(umma_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(227 * 1024));
+      if (e != cudaSuccess) rc = set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      configured = (e == cudaSuccess);
+    }
+  }
+  if (rc == 0) {
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+    const int grid = items * splits;
+    static uint32_t* dbg_host = nullptr;
+    const bool debug = getenv("NG_UMMA_DEBUG") != nullptr;
+    if (debug) {
+      if (!dbg_host) cudaHostAlloc((void**)&dbg_host, 64 * sizeof(uint32_t), cudaHostAllocMapped);
+      memset(dbg_host, 0, 64 * sizeof(uint32_t));
+      p.dbg = dbg_host;
+      fprintf(stderr, "[umma] wgrad: grid %d items %d splits %d chunks %d/split Cm %d taps/cta %d n_tile %d stages %d w_c %d rows_c %d\n",
+              grid, items, splits, p.chunks_per_split, p.Cm, p.taps_per_cta, p.n_tile, stages, w_c, p.rows_c);
+    }
+    NG_LAUNCH(umma_conv_wgrad_kernel, grid, W_THREADS, smem_bytes, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = set_error("umma_conv_wgrad_kernel launch failed: %s", cudaGetErrorString(e));
+    if (debug) {
+      cudaError_t e2 = cudaStreamSynchronize(g_stream);
+      fprintf(stderr, "[umma] wgrad sync: %s ; dbg: %08x %08x %08x\n", cudaGetErrorString(e2), dbg_host[0], dbg_host[1],
+              dbg_host[2]);
+    }
+  }
+  if (rc == 0) {
+    const long long n = (long long)RS * C * K;
+    int g = (int)ceil_div(n, 256);
+    if (g > sms * 8) g = sms * 8;
+    NG_LAUNCH(wgrad_reduce_kernel, g, 256, 0, dw, (const float*)ws, splits, RS, C, K);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = set_error("wgrad_reduce_kernel launch failed: %s", cudaGetErrorString(e));
+  }
+  pool_free(ws);
+  pool_free(dy_t);
+  pool_free(x_t);
+  return rc;
 }
 
 }  // namespace umma
