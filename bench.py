@@ -215,6 +215,8 @@ def ncu_traffic(kernel_class):
 
 
 def conv2d_sweep(B, lib, ffma_peak):
+    """BASELINE config 1: per-pass TFLOP/s of the FP32 SIMT kernels (fraction of the measured FFMA
+    peak) and of the opt-in TF32 tensor-core kernels (staging transposes included in the time)."""
     from nanograd_b200.nn.buffer import DeviceBuffer
     rows = []
     rng = np.random.RandomState(0)
@@ -226,25 +228,27 @@ def conv2d_sweep(B, lib, ffma_peak):
         w = DeviceBuffer((K, C, R, S), hostbuf=(rng.randn(K, C, R, S) / np.sqrt(9 * C)).astype(np.float32))
         dy = DeviceBuffer((N, K, OH, OW), hostbuf=rng.randn(N, K, OH, OW).astype(np.float32))
         y, dx, dw = DeviceBuffer((N, K, OH, OW)), DeviceBuffer((N, C, H, W)), DeviceBuffer((K, C, R, S))
-        dims = (N, C, H, W, K, R, S, 1, 0, 0, OH, OW, 0)
-        calls = {"fprop": lambda: lib.ng_conv2d_fprop(y.ptr, x.ptr, w.ptr, 0, *dims),
-                 "dgrad": lambda: lib.ng_conv2d_dgrad(dx.ptr, dy.ptr, w.ptr, *dims),
-                 "wgrad": lambda: lib.ng_conv2d_wgrad(dw.ptr, dy.ptr, x.ptr, *dims)}
+        dims = (N, C, H, W, K, R, S, 1, 0, 0, OH, OW)
+        calls = {"fprop": lambda f: lib.ng_conv2d_fprop(y.ptr, x.ptr, w.ptr, 0, *dims, f),
+                 "dgrad": lambda f: lib.ng_conv2d_dgrad(dx.ptr, dy.ptr, w.ptr, *dims, f),
+                 "wgrad": lambda f: lib.ng_conv2d_wgrad(dw.ptr, dy.ptr, x.ptr, *dims, f)}
         flops = 2.0 * N * K * C * R * S * OH * OW
-        row, total = {"C=K": ch}, 0.0
+        row = {"C=K": ch}
         iters = 20 if ch <= 64 else 5
-        for name, fn in calls.items():
-            for _ in range(3):
-                fn()
-            e0, e1 = B.Event().record(), B.Event()
-            for _ in range(iters):
-                fn()
-            e1.record()
-            e1.synchronize()
-            ms = e0.elapsed_ms(e1) / iters
-            total += ms
-            row[f"{name}_tflops"] = round(flops / (ms * 1e-3) / 1e12, 2)
-        row["fwd_bwd_tflops"] = round(3 * flops / (total * 1e-3) / 1e12, 2)
+        for mode, flag in (("", 0), ("tf32_", B.F_TF32)):
+            total = 0.0
+            for name, fn in calls.items():
+                for _ in range(3):
+                    fn(flag)
+                e0, e1 = B.Event().record(), B.Event()
+                for _ in range(iters):
+                    fn(flag)
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_ms(e1) / iters
+                total += ms
+                row[f"{mode}{name}_tflops"] = round(flops / (ms * 1e-3) / 1e12, 2)
+            row[f"{mode}fwd_bwd_tflops"] = round(3 * flops / (total * 1e-3) / 1e12, 2)
         row["frac_of_ffma_peak"] = round(row["fwd_bwd_tflops"] / ffma_peak, 3) if ffma_peak else None
         rows.append(row)
         del x, w, dy, y, dx, dw
@@ -286,24 +290,17 @@ def mnist_cnn_images_per_sec(B, steps=30, warmup=5):
             "ms_per_step": round(ms, 4), "loss": float(loss.numpy()[0])}
 
 
-def run_device_arm(args):
-    from nanograd_b200 import backend as B
-    from nanograd_b200 import dist
+def measure_training(args, B, dist, lib, math_mode, with_clocks):
+    """W warm-up + K timed training steps of the workload in one math mode ("fp32" | "tf32").
+    Returns the device-resident throughput, the end-to-end throughput through the public API with
+    host batches, the per-class kernel timings and (fp32 only) the measured FFMA peak."""
     import nanograd_b200.nn.module as nn
     import nanograd_b200.optim.optimizer as optim
     from nanograd_b200.device import Device
     from nanograd_b200.tensor import Tensor
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nnodes=1 "
-                             f"--nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus}")
-    dist.init(use_device=True)
+    B.set_math_mode(math_mode)
     rank, world = dist.rank(), dist.world_size()
-    lib = B.lib()
-    B.init(dist.local_rank())
-
     # identical parameters on every rank: host-side NumPy init under the same seed
     np.random.seed(0)
     model = build_model(nn)
@@ -332,13 +329,17 @@ def run_device_arm(args):
     dist.barrier()
     B.sync()
     launches0 = B.launch_count()
-    with ClockSampler(dist.local_rank()) as clocks:
-        e0, e1 = B.Event().record(), B.Event()
-        for _ in range(K):
-            loss = train_step(model, opt, crit, x_res, y_res)
-        e1.record()
-        e1.synchronize()
-        B.sync()
+    clocks = ClockSampler(dist.local_rank()) if with_clocks else None
+    if clocks:
+        clocks.__enter__()
+    e0, e1 = B.Event().record(), B.Event()
+    for _ in range(K):
+        loss = train_step(model, opt, crit, x_res, y_res)
+    e1.record()
+    e1.synchronize()
+    B.sync()
+    if clocks:
+        clocks.__exit__(None, None, None)
     dist.barrier()
     lib.ng_prof_enable(0)
     ms_total = dist.all_reduce_max(e0.elapsed_ms(e1))
@@ -369,56 +370,116 @@ def run_device_arm(args):
     dist.barrier()
     e2e_ms = dist.all_reduce_max(max(e0.elapsed_ms(e1), wall_ms)) / K
     e2e_value = PER_GPU_BATCH * world / (e2e_ms * 1e-3)
+    del loss, x_res, y_res, model, opt
+    B.set_math_mode("fp32")
+    return {"value": value, "ms_per_step": ms_per_step, "e2e_value": e2e_value, "e2e_ms": e2e_ms,
+            "h2d": int(Xh.nbytes + Yh.nbytes), "launches": int(launches), "loss": loss_value, "prof": prof,
+            "ffma_peak": float(ffma_peak.value), "clocks": clocks.summary() if clocks else None,
+            "n_params": n_params, "K": K, "W": W}
 
-    if rank != 0:
-        dist.shutdown()
-        return
 
-    # ---- roofline of the dominant kernel class -----------------------------------------------
-    peaks, peak_src = measured_peaks()
+KERNEL_NAMES = {
+    "fp32": {"conv_fprop": "conv_gather_kernel<CtTile<2,4,8>,TAPMAJOR> (fprop)",
+             "conv_dgrad": "conv_gather_kernel<CtTile<2,4,8>,TAPMAJOR> (dgrad)",
+             "conv_wgrad": "conv_wgrad_kernel<CtTile<2,4,8>> + splitk_reduce_kernel", "gemm": "gemm_kernel"},
+    "tf32": {"conv_fprop": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05, fprop)",
+             "conv_dgrad": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05, dgrad)",
+             "conv_wgrad": "2x nchw_to_nhwc + umma_conv_wgrad_kernel (tcgen05) + wgrad_reduce_kernel",
+             "gemm": "gemm_kernel (FP32 SIMT)"},
+}
+
+
+def roofline_object(m, math_mode, peaks, peak_src):
+    """Roofline of the dominant contraction class.  FP32 mode: the FFMA pipe bounds it (peak =
+    FFMA-saturating microkernel measured in this run).  TF32 mode: the tensor pipe bounds it; the
+    dense TF32 peak is half the measured dense BF16 GEMM rate of MEASURED_PEAKS.json (sustained
+    figure: the kernels are timed inside a long step)."""
+    prof, K = m["prof"], m["K"]
     dominant = max(prof, key=lambda k: prof[k]["ms"])
     d = prof[dominant]
     achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
     kernel_ms = sum(v["ms"] for v in prof.values())
-    roofline = {
-        "kernel": {"conv_fprop": "conv_gather_kernel<8,false> (fprop)", "conv_dgrad": "conv_gather_kernel<8,false> (dgrad)",
-                   "conv_wgrad": "conv_wgrad_kernel<8> + splitk_reduce_kernel", "gemm": "gemm_kernel"}[dominant],
-        "bound": "fp32_ffma", "achieved": round(achieved, 2), "peak": round(float(ffma_peak.value), 2),
-        "unit": "TFLOP/s", "frac": round(achieved / ffma_peak.value, 4) if ffma_peak.value else None,
-        "traffic": ncu_traffic(dominant),
-        "peak_source": "FFMA-saturating microkernel measured in this run (nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4); "
-                       "the default path is FP32 SIMT, so the tensor peak of %s (bf16 %.0f TFLOP/s) does not bound it"
-                       % (peak_src, peaks.get("bf16_tflops", 0.0)),
+    if math_mode == "fp32":
+        bound, peak = "fp32_ffma", m["ffma_peak"]
+        src = ("FFMA-saturating microkernel measured in this run (nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4); "
+               "the default path is FP32 SIMT, so the tensor peak of %s (bf16 %.0f TFLOP/s) does not bound it"
+               % (peak_src, peaks.get("bf16_tflops", 0.0)))
+    else:
+        bound = "tensor"
+        peak = 0.5 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)))
+        src = ("dense TF32 = 1/2 of the measured sustained dense bf16 GEMM rate in %s (%.1f TFLOP/s)"
+               % (peak_src, peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0))))
+    return {
+        "kernel": KERNEL_NAMES[math_mode][dominant], "bound": bound, "achieved": round(achieved, 2),
+        "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(achieved / peak, 4) if peak else None,
+        "traffic": ncu_traffic(math_mode + ":" + dominant), "peak_source": src,
         "avg_launch_ms": round(d["ms"] / max(d["launches"], 1), 4), "launches": d["launches"],
-        "share_of_step": round(d["ms"] / (ms_per_step * K), 4),
-        "contraction_share_of_step": round(kernel_ms / (ms_per_step * K), 4),
+        "share_of_step": round(d["ms"] / (m["ms_per_step"] * K), 4),
+        "contraction_share_of_step": round(kernel_ms / (m["ms_per_step"] * K), 4),
         "per_class": {k: {"ms_per_step": round(v["ms"] / K, 4), "launches_per_step": v["launches"] / K,
                           "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None}
                       for k, v in prof.items()},
         "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_src,
     }
 
+
+def run_device_arm(args):
+    from nanograd_b200 import backend as B
+    from nanograd_b200 import dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nnodes=1 "
+                             f"--nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus}")
+    dist.init(use_device=True)
+    rank, world = dist.rank(), dist.world_size()
+    lib = B.lib()
+    B.init(dist.local_rank())
+    peaks, peak_src = measured_peaks()
+
+    main_mode = args.math
+    m = measure_training(args, B, dist, lib, main_mode, with_clocks=True)
+    other = None
+    if args.math == "fp32" and not args.no_tf32:
+        other = measure_training(args, B, dist, lib, "tf32", with_clocks=False)
+
+    if rank != 0:
+        dist.shutdown()
+        return
+
+    K, W = m["K"], m["W"]
+    math_text = {"fp32": "FP32 SIMT (FFMA) implicit-GEMM conv / GEMM",
+                 "tf32": "TF32 tcgen05 tensor-core conv (FP32 accumulate), FP32 SIMT elsewhere"}
     line = {
-        "metric": "train_images_per_sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "metric": "train_images_per_sec", "value": round(m["value"], 1), "unit": "images/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": round(m["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if main_mode == "fp32" else "tf32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": PER_GPU_BATCH * world, "per_gpu_batch": PER_GPU_BATCH,
                    "image": "3x32x32", "optimizer": "Adam(lr=1e-3)", "loss": "log_softmax + NLLLoss",
-                   "params": n_params, "parallelism": f"dp{world}" if world > 1 else "single",
+                   "params": m["n_params"], "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "no flush: one step touches ~1.9 GB of activations, far larger than the 126 MB L2",
-                   "math": "FP32 SIMT (FFMA) implicit-GEMM conv / GEMM"},
-        "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(e2e_ms, 4),
-                "h2d_bytes_per_step": int(Xh.nbytes + Yh.nbytes), "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "launches_per_step": launches / K, "loss": loss_value,
-        "clocks": clocks.summary(), "roofline": roofline,
+                   "math": math_text[main_mode]},
+        "e2e": {"value": round(m["e2e_value"], 1), "unit": "images/s", "ms_per_step": round(m["e2e_ms"], 4),
+                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4},
+        "gpu_launches": m["launches"], "launches_per_step": m["launches"] / K, "loss": m["loss"],
+        "clocks": m["clocks"], "roofline": roofline_object(m, main_mode, peaks, peak_src),
     }
+    if other is not None:
+        line["tf32_mode"] = {
+            "note": "same workload with the opt-in TF32 tensor-core convolutions (NANOGRAD_B200_MATH=tf32; parity bar "
+                    "rtol 1e-2); not the headline value, which is the default FP32 path",
+            "value": round(other["value"], 1), "unit": "images/s", "ms_per_step": round(other["ms_per_step"], 4),
+            "e2e": {"value": round(other["e2e_value"], 1), "unit": "images/s", "ms_per_step": round(other["e2e_ms"], 4),
+                    "h2d_bytes_per_step": other["h2d"], "d2h_bytes_per_step": 4},
+            "gpu_launches": other["launches"], "loss": other["loss"],
+            "roofline": roofline_object(other, "tf32", peaks, peak_src)}
 
     if world == 1 and not args.no_extras:
-        # free the training graph before the side measurements
-        del loss, x_res, y_res
+        ffma = m["ffma_peak"]
         line["conv2d_sweep"] = {"workload": "Conv2d 3x3 s1 p0, x(256,C,32,32), BASELINE configs[1]",
-                                "ffma_peak_tflops": round(float(ffma_peak.value), 2),
-                                "rows": conv2d_sweep(B, lib, float(ffma_peak.value))}
+                                "ffma_peak_tflops": round(ffma, 2),
+                                "rows": conv2d_sweep(B, lib, ffma)}
         line["mnist_cnn"] = mnist_cnn_images_per_sec(B)
         t0 = time.perf_counter()
         cpu_ips, cpu_sec = cpu_oracle_images_per_sec(steps=2, warmup=1)
@@ -436,6 +497,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="device", choices=["device", "reference"])
+    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"],
+                    help="math mode of the headline measurement (default: the FP32 SIMT path)")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the secondary TF32-mode measurement")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the conv2d sweep / MNIST CNN / CPU baseline side measurements (profiling runs)")
     args = ap.parse_args()

@@ -69,6 +69,14 @@ int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64
   return 0;
 }
 
+// Round-to-nearest (ties away) FP32 -> TF32.  The tensor core would otherwise truncate the 13 low
+// mantissa bits (a biased, twice larger error); the staging copies round once, for free.
+__device__ __forceinline__ float tf32_round(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
 // ------------------------------------------------------------------ filter re-layout
 // dst[(rs*J + j)*KC + kc] = w[j*sj + kc*sc + rs]
 __global__ void __launch_bounds__(256) filter_relayout_kernel(float* __restrict__ dst, const float* __restrict__ w,
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(256) filter_relayout_kernel(float* __restrict_
     const long long t = e / KC;
     const int j = (int)(t % J);
     const int rs = (int)(t / J);
-    dst[e] = w[(long long)j * sj + (long long)kc * sc + rs];
+    dst[e] = tf32_round(w[(long long)j * sj + (long long)kc * sc + rs]);
   }
 }
 
@@ -100,7 +108,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(float* __restrict__ o
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int p = p0 + ty + 8 * i, c = c0 + tx;
-    if (p < HW && c < C) out[img + (long long)p * C + c] = tile[tx][ty + 8 * i];
+    if (p < HW && c < C) out[img + (long long)p * C + c] = tf32_round(tile[tx][ty + 8 * i]);
   }
 }
 

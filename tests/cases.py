@@ -54,6 +54,24 @@ def case_conv2d(fw, k, s, seed=0, loc=0.0):
     return {"y": fw.numpy(y), "dx": _grad(fw, x), "dw": _grad(fw, w)}
 
 
+def case_conv2d_wide(fw, c=32, k=64, hw=16, n=4, pad=0, seed=0):
+    """Conv2d shapes the tensor-core (TF32) path accepts: channels multiple of 32, stride 1.
+    pad > 0 goes through nn.Conv2d (pad2d + conv2d + bias, module.py:437-476)."""
+    rng = np.random.RandomState(seed + c + k + hw)
+    np.random.seed(seed + 1)
+    x = fw.tensor(rng.normal(0, 1, (n, c, hw, hw)).astype(np.float32), True)
+    if pad:
+        conv = fw.nn.Conv2d(c, k, 3, 1, pad)
+        fw.place(conv)
+        y = conv(x)
+        w = conv.weight
+    else:
+        w = fw.tensor((rng.normal(0, 1, (k, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32), True)
+        y = x.conv2d(w, 1)
+    _weighted_sum(fw, y, rng).backward()
+    return {"y": fw.numpy(y), "dx": _grad(fw, x), "dw": _grad(fw, w)}
+
+
 def case_conv1d(fw, k, s, seed=0, loc=0.0):
     rng = np.random.RandomState(seed + 100 + 10 * k + s)
     x = fw.tensor(rng.normal(loc, 1, (5, 3, 40)).astype(np.float32), True)
@@ -239,16 +257,16 @@ def case_mnist_cnn(fw, opt_name, batch=16, steps=2, seed=0):
     return _train(fw, model, opt_name, X, Y, steps, fw.nn.NLLLoss())
 
 
-def case_vgg_bn(fw, opt_name="adam", batch=8, steps=2, seed=0):
+def case_vgg_bn(fw, opt_name="adam", batch=8, steps=2, seed=0, widths=(8, 16), hw=8):
     """BASELINE config 2 (VGG-style conv-BN-ReLU stages + FC, log_softmax + NLLLoss) shrunk."""
     nn = fw.nn
     np.random.seed(seed)
     layers, c = [], 3
-    for w in (8, 16):
+    for w in widths:
         layers += [nn.Conv2d(c, w, 3, 1, 1), nn.BatchNorm2d(w), nn.ReLU(),
                    nn.Conv2d(w, w, 3, 1, 1), nn.BatchNorm2d(w), nn.ReLU(), nn.MaxPool2d(2)]
         c = w
-    layers += [nn.Flatten(), nn.Linear(16 * 2 * 2, 32), nn.ReLU(), nn.Linear(32, 10)]
+    layers += [nn.Flatten(), nn.Linear(widths[-1] * (hw // 4) ** 2, 32), nn.ReLU(), nn.Linear(32, 10)]
     body = nn.Sequential(*layers)
 
     class Net(nn.Module):
@@ -259,7 +277,7 @@ def case_vgg_bn(fw, opt_name="adam", batch=8, steps=2, seed=0):
         def forward(self, x):
             return self.body(x).log_softmax()
 
-    X = np.random.randn(batch, 3, 8, 8).astype(np.float32)
+    X = np.random.randn(batch, 3, hw, hw).astype(np.float32)
     Y = np.random.randint(0, 10, batch).astype(np.float32)
     return _train(fw, Net(), opt_name, X, Y, steps, nn.NLLLoss())
 
@@ -358,6 +376,14 @@ def all_cases():
         cases[f"mnist_cnn_{o}"] = (case_mnist_cnn, dict(opt_name=o))
     cases["vgg_bn_adam"] = (case_vgg_bn, dict(opt_name="adam"))
     cases["vgg_bn_sgd"] = (case_vgg_bn, dict(opt_name="sgd"))
+    # shapes that the tcgen05 TF32 path accepts (channel counts multiple of 32)
+    # (16x16 images, batch 16: BatchNorm statistics over >= 256 values, so the comparison measures the
+    # kernels and not the conditioning of a 32-sample variance estimate)
+    cases["vgg_wide_adam"] = (case_vgg_bn, dict(opt_name="adam", widths=(32, 64), hw=16, batch=16))
+    cases["vgg_wide_sgd"] = (case_vgg_bn, dict(opt_name="sgd", widths=(32, 64), hw=16, batch=16))
+    cases["conv2d_wide_c32_k64"] = (case_conv2d_wide, dict(c=32, k=64, hw=16, n=4, pad=0))
+    cases["conv2d_wide_c64_k32_p1"] = (case_conv2d_wide, dict(c=64, k=32, hw=8, n=3, pad=1))
+    cases["conv2d_wide_c128_k128_p1"] = (case_conv2d_wide, dict(c=128, k=128, hw=12, n=2, pad=1))
     cases["attention_adamw"] = (case_attention, {})
     for o in ("sgd", "sgdm", "adam", "adamw1", "adamw2", "adamw3"):
         cases[f"tinynet_{o}"] = (case_tinynet_step, dict(opt_name=o))
