@@ -216,7 +216,8 @@ def ncu_traffic(kernel_class):
 
 def conv2d_sweep(B, lib, ffma_peak):
     """BASELINE config 1: per-pass TFLOP/s of the FP32 SIMT kernels (fraction of the measured FFMA
-    peak) and of the opt-in TF32 tensor-core kernels (staging transposes included in the time)."""
+    peak), of the FP32-accurate 3xTF32 tensor-core kernels (useful FLOPs: one per FP32 MAC) and of the
+    opt-in TF32 tensor-core kernels (staging transposes included in the time)."""
     from nanograd_b200.nn.buffer import DeviceBuffer
     rows = []
     rng = np.random.RandomState(0)
@@ -235,7 +236,7 @@ def conv2d_sweep(B, lib, ffma_peak):
         flops = 2.0 * N * K * C * R * S * OH * OW
         row = {"C=K": ch}
         iters = 20 if ch <= 64 else 5
-        for mode, flag in (("", 0), ("tf32_", B.F_TF32)):
+        for mode, flag in (("", 0), ("tf32x3_", B.F_TF32X3 | B.F_TC_FORCE), ("tf32_", B.F_TF32)):
             total = 0.0
             for name, fn in calls.items():
                 for _ in range(3):
@@ -255,7 +256,7 @@ def conv2d_sweep(B, lib, ffma_peak):
     return rows
 
 
-def mnist_cnn_images_per_sec(B, steps=30, warmup=5):
+def mnist_cnn_images_per_sec(B, steps=100, warmup=10):
     import helpers
     import nanograd_b200.nn.module as nn
     import nanograd_b200.optim.optimizer as optim
@@ -280,18 +281,25 @@ def mnist_cnn_images_per_sec(B, steps=30, warmup=5):
     for _ in range(warmup):
         step()
     B.sync()
+    import gc
+    gc.collect()  # garbage of the previous measurements would otherwise be collected inside the timed loop
     e0, e1 = B.Event().record(), B.Event()
+    walls = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         loss = step()
+        walls.append((time.perf_counter() - t0) * 1e3)
     e1.record()
     e1.synchronize()
     ms = e0.elapsed_ms(e1) / steps
+    if os.environ.get("NG_BENCH_DEBUG"):
+        print("mnist host ms per step:", " ".join("%.2f" % w for w in walls), "mem", B.mem_stats(), file=sys.stderr)
     return {"workload": "README MNIST CNN, BS 128, SGD (BASELINE configs[0])", "images_per_sec": round(128 / (ms * 1e-3), 1),
             "ms_per_step": round(ms, 4), "loss": float(loss.numpy()[0])}
 
 
 def measure_training(args, B, dist, lib, math_mode, with_clocks):
-    """W warm-up + K timed training steps of the workload in one math mode ("fp32" | "tf32").
+    """W warm-up + K timed training steps of the workload in one math mode (backend.set_math_mode).
     Returns the device-resident throughput, the end-to-end throughput through the public API with
     host batches, the per-class kernel timings and (fp32 only) the measured FFMA peak."""
     import nanograd_b200.nn.module as nn
@@ -379,36 +387,46 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
 
 
 KERNEL_NAMES = {
-    "fp32": {"conv_fprop": "conv_gather_kernel<CtTile<2,4,8>,TAPMAJOR> (fprop)",
+    "simt": {"conv_fprop": "conv_gather_kernel<CtTile<2,4,8>,TAPMAJOR> (fprop)",
              "conv_dgrad": "conv_gather_kernel<CtTile<2,4,8>,TAPMAJOR> (dgrad)",
              "conv_wgrad": "conv_wgrad_kernel<CtTile<2,4,8>> + splitk_reduce_kernel", "gemm": "gemm_kernel"},
     "tf32": {"conv_fprop": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05, fprop)",
              "conv_dgrad": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05, dgrad)",
-             "conv_wgrad": "2x nchw_to_nhwc + umma_conv_wgrad_kernel (tcgen05) + wgrad_reduce_kernel",
+             "conv_wgrad": "2x nchw_to_nhwc + umma_conv_wgrad_kernel<false> (tcgen05) + wgrad_reduce_kernel",
+             "gemm": "gemm_kernel (FP32 SIMT)"},
+    "fp32": {"conv_fprop": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05 3xTF32, fprop)",
+             "conv_dgrad": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05 3xTF32, dgrad)",
+             "conv_wgrad": "2x nchw_to_nhwc + umma_conv_wgrad_kernel<true> (tcgen05 3xTF32) + wgrad_reduce_kernel",
              "gemm": "gemm_kernel (FP32 SIMT)"},
 }
+KERNEL_NAMES["tf32x3"] = KERNEL_NAMES["fp32"]
 
 
 def roofline_object(m, math_mode, peaks, peak_src):
-    """Roofline of the dominant contraction class.  FP32 mode: the FFMA pipe bounds it (peak =
-    FFMA-saturating microkernel measured in this run).  TF32 mode: the tensor pipe bounds it; the
-    dense TF32 peak is half the measured dense BF16 GEMM rate of MEASURED_PEAKS.json (sustained
-    figure: the kernels are timed inside a long step)."""
+    """Roofline of the dominant contraction class.
+    simt: the FFMA pipe bounds it (peak = FFMA-saturating microkernel measured in this run).
+    tf32: the tensor pipe bounds it; dense TF32 peak = 1/2 of the measured dense BF16 GEMM rate of
+          MEASURED_PEAKS.json (sustained figure: the kernels are timed inside a long step).
+    fp32 / tf32x3 (FP32-accurate 3xTF32 on tensor cores): three TF32 MMAs per useful FP32 MAC, so the
+          peak for useful FLOPs is the TF32 peak / 3."""
     prof, K = m["prof"], m["K"]
     dominant = max(prof, key=lambda k: prof[k]["ms"])
     d = prof[dominant]
     achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
     kernel_ms = sum(v["ms"] for v in prof.values())
-    if math_mode == "fp32":
+    bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)))
+    if math_mode == "simt":
         bound, peak = "fp32_ffma", m["ffma_peak"]
         src = ("FFMA-saturating microkernel measured in this run (nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4); "
-               "the default path is FP32 SIMT, so the tensor peak of %s (bf16 %.0f TFLOP/s) does not bound it"
-               % (peak_src, peaks.get("bf16_tflops", 0.0)))
+               "no FP32 tensor-core MMA exists, so the tensor peak of %s does not bound this mode" % peak_src)
+    elif math_mode == "tf32":
+        bound, peak = "tensor", 0.5 * bf16
+        src = "dense TF32 = 1/2 of the measured sustained dense bf16 GEMM rate in %s (%.1f TFLOP/s)" % (peak_src, bf16)
     else:
-        bound = "tensor"
-        peak = 0.5 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)))
-        src = ("dense TF32 = 1/2 of the measured sustained dense bf16 GEMM rate in %s (%.1f TFLOP/s)"
-               % (peak_src, peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0))))
+        bound, peak = "tensor", 0.5 * bf16 / 3.0
+        src = ("useful-FLOP peak of the FP32-accurate 3xTF32 scheme = dense TF32 (1/2 of the measured sustained bf16 "
+               "rate in %s, %.1f TFLOP/s) / 3 MMAs per FP32 MAC; for scale, the measured FFMA peak of the SIMT "
+               "alternative is %.1f TFLOP/s" % (peak_src, bf16, m["ffma_peak"]))
     return {
         "kernel": KERNEL_NAMES[math_mode][dominant], "bound": bound, "achieved": round(achieved, 2),
         "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(achieved / peak, 4) if peak else None,
@@ -440,21 +458,28 @@ def run_device_arm(args):
 
     main_mode = args.math
     m = measure_training(args, B, dist, lib, main_mode, with_clocks=True)
-    other = None
+    others = {}
     if args.math == "fp32" and not args.no_tf32:
-        other = measure_training(args, B, dist, lib, "tf32", with_clocks=False)
+        others["simt_mode"] = ("simt", measure_training(args, B, dist, lib, "simt", with_clocks=False))
+        others["tf32_mode"] = ("tf32", measure_training(args, B, dist, lib, "tf32", with_clocks=False))
 
     if rank != 0:
         dist.shutdown()
         return
 
     K, W = m["K"], m["W"]
-    math_text = {"fp32": "FP32 SIMT (FFMA) implicit-GEMM conv / GEMM",
+    math_text = {"fp32": "FP32-accurate: tcgen05 tensor-core conv with 3xTF32 error compensation where the shape is "
+                         "supported, FP32 SIMT (FFMA) elsewhere (first conv layer, GEMMs)",
+                 "tf32x3": "FP32-accurate 3xTF32 tcgen05 conv forced for every supported shape",
+                 "simt": "FP32 SIMT (FFMA) implicit-GEMM conv / GEMM only",
                  "tf32": "TF32 tcgen05 tensor-core conv (FP32 accumulate), FP32 SIMT elsewhere"}
+    notes = {"simt_mode": "same workload restricted to the FP32 SIMT (FFMA) kernels (NANOGRAD_B200_MATH=simt)",
+             "tf32_mode": "same workload with the opt-in plain-TF32 tensor-core convolutions (NANOGRAD_B200_MATH=tf32; "
+                          "parity bar rtol 1e-2); reduced precision, hence not the headline value"}
     line = {
         "metric": "train_images_per_sec", "value": round(m["value"], 1), "unit": "images/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": round(m["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if main_mode == "fp32" else "tf32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "tf32" if main_mode == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": PER_GPU_BATCH * world, "per_gpu_batch": PER_GPU_BATCH,
                    "image": "3x32x32", "optimizer": "Adam(lr=1e-3)", "loss": "log_softmax + NLLLoss",
                    "params": m["n_params"], "parallelism": f"dp{world}" if world > 1 else "single",
@@ -465,15 +490,12 @@ def run_device_arm(args):
         "gpu_launches": m["launches"], "launches_per_step": m["launches"] / K, "loss": m["loss"],
         "clocks": m["clocks"], "roofline": roofline_object(m, main_mode, peaks, peak_src),
     }
-    if other is not None:
-        line["tf32_mode"] = {
-            "note": "same workload with the opt-in TF32 tensor-core convolutions (NANOGRAD_B200_MATH=tf32; parity bar "
-                    "rtol 1e-2); not the headline value, which is the default FP32 path",
-            "value": round(other["value"], 1), "unit": "images/s", "ms_per_step": round(other["ms_per_step"], 4),
-            "e2e": {"value": round(other["e2e_value"], 1), "unit": "images/s", "ms_per_step": round(other["e2e_ms"], 4),
-                    "h2d_bytes_per_step": other["h2d"], "d2h_bytes_per_step": 4},
-            "gpu_launches": other["launches"], "loss": other["loss"],
-            "roofline": roofline_object(other, "tf32", peaks, peak_src)}
+    for key, (mode, o) in others.items():
+        line[key] = {
+            "note": notes[key], "value": round(o["value"], 1), "unit": "images/s", "ms_per_step": round(o["ms_per_step"], 4),
+            "e2e": {"value": round(o["e2e_value"], 1), "unit": "images/s", "ms_per_step": round(o["e2e_ms"], 4),
+                    "h2d_bytes_per_step": o["h2d"], "d2h_bytes_per_step": 4},
+            "gpu_launches": o["launches"], "loss": o["loss"], "roofline": roofline_object(o, mode, peaks, peak_src)}
 
     if world == 1 and not args.no_extras:
         ffma = m["ffma_peak"]
@@ -497,9 +519,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="device", choices=["device", "reference"])
-    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"],
-                    help="math mode of the headline measurement (default: the FP32 SIMT path)")
-    ap.add_argument("--no-tf32", action="store_true", help="skip the secondary TF32-mode measurement")
+    ap.add_argument("--math", default="fp32", choices=["fp32", "simt", "tf32x3", "tf32"],
+                    help="math mode of the headline measurement (default fp32: FP32-accurate, engine picked per call)")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the secondary simt-mode and tf32-mode measurements")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the conv2d sweep / MNIST CNN / CPU baseline side measurements (profiling runs)")
     args = ap.parse_args()

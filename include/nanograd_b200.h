@@ -118,7 +118,14 @@ int ng_onehot(uint64_t out, uint64_t labels, int64_t rows, int64_t classes);
 
 /* ------------------------------------------------------------ GEMM / convolution --- */
 /* flags for the contraction kernels */
-enum { NG_F_RELU = 1, NG_F_TF32 = 2 };
+/*   NG_F_TF32    convolutions on tcgen05 tensor cores with TF32 inputs (opt-in, rtol 1e-2)
+ *   NG_F_TF32X3  convolutions on tcgen05 with the error-compensated 3xTF32 split: FP32-accurate
+ *                (meets the FP32 parity bar rtol 1e-4).  Shapes a tensor-core kernel does not take
+ *                run on the FP32 SIMT kernel. */
+/*   NG_F_TC_FORCE  take the tensor-core kernel whenever the shape allows; without it NG_F_TF32X3 keeps
+ *                problems below ~0.2 GFLOP on the SIMT kernel (staging + extra launches cost more
+ *                than they save there). */
+enum { NG_F_RELU = 1, NG_F_TF32 = 2, NG_F_TF32X3 = 4, NG_F_TC_FORCE = 8 };
 /* C[M,N] = op(A) @ op(B) (+ bias[N]) ; row-major; op = transpose when the flag is set.
  * replaces matmul_op, ops_gpu.py:214-232, and the perm+matmul chain in MatMul.backward,
  * ops_gpu.py:452-459.  batch > 1: equally strided batches of A, B and C. */

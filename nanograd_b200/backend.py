@@ -88,14 +88,20 @@ U_COPY, U_NEG, U_EXP, U_LOG, U_RELU, U_SIGMOID, U_TANH, U_SQRT, U_RECIP = range(
 (B_ADD, B_MUL, B_POW, B_DIV, B_SUB, B_EQ, B_RELU_BWD, B_EXP_BWD, B_LOG_BWD, B_SIGMOID_BWD,
  B_TANH_BWD, B_POW_DBASE, B_POW_DEXP) = range(13)
 R_SUM, R_MAX, R_MIN = range(3)
-F_RELU, F_TF32 = 1, 2
+F_RELU, F_TF32, F_TF32X3 = 1, 2, 4
 
-# Math mode of the contraction kernels (Conv2d/Conv1d fprop, dgrad, wgrad):
-#   "fp32" (default)  FP32 SIMT FFMA kernels, parity bar rtol 1e-4
-#   "tf32" (opt-in)   tcgen05 tensor cores with TF32 inputs / FP32 accumulation where the shape
-#                     is supported (falls back to FP32 SIMT per call otherwise), parity bar rtol 1e-2
+# Math mode of the convolution kernels (fprop, dgrad, wgrad):
+#   "fp32" (default)  FP32-accurate results (parity bar rtol 1e-4).  Per call the library picks the
+#                     faster FP32-accurate engine: the tcgen05 tensor-core kernel with the
+#                     error-compensated 3xTF32 operand split (measured 2e-6 .. 1.4e-5 from a float64
+#                     reference) when the shape is supported and the problem is large enough to pay
+#                     for staging, else the FP32 SIMT (FFMA) kernel.
+#   "simt"            FP32 SIMT kernels only.
+#   "tf32x3"          like "fp32" but tensor cores for every supported shape, whatever its size.
+#   "tf32"  (opt-in)  tensor cores with plain TF32 inputs / FP32 accumulation (parity bar rtol 1e-2).
 # Selected with NANOGRAD_B200_MATH (or the reference-survey spelling NANOGRAD_TF32=1) or set_math_mode().
-_MATH_MODES = {"fp32": 0, "tf32": F_TF32}
+F_TC_FORCE = 8
+_MATH_MODES = {"fp32": F_TF32X3, "simt": 0, "tf32x3": F_TF32X3 | F_TC_FORCE, "tf32": F_TF32}
 _math_flags = _MATH_MODES["tf32" if os.environ.get("NANOGRAD_TF32", "0") == "1"
                           else os.environ.get("NANOGRAD_B200_MATH", "fp32").lower()]
 

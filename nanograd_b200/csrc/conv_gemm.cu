@@ -567,6 +567,13 @@ static int launch_conv_gather(const ConvGatherP& p, bool strided) {
   return 0;
 }
 
+// Engine selection for one convolution pass: 0 = FP32 SIMT, else the tensor-core kernel.
+static inline bool want_tensor_core(int flags, double flops) {
+  if (flags & NG_F_TF32) return true;
+  if (!(flags & NG_F_TF32X3)) return false;
+  return (flags & NG_F_TC_FORCE) || flops >= 2.0e8;
+}
+
 static int check_conv_dims(const char* who, int N, int C, int H, int W, int K, int R, int S, int stride, int pad_t,
                            int pad_l, int OH, int OW) {
   NG_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && K > 0 && R > 0 && S > 0, "%s: non-positive dimension", who);
@@ -619,8 +626,9 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
   const int tok = prof_begin(NG_PROF_CONV_FPROP, flops, bytes);
   int rc = -1;
 #ifndef NG_EMU
-  if (flags & NG_F_TF32)
-    rc = umma::conv_fprop_tf32(p.out, p.a, p.b, p.bias, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW, p.relu);
+  if (want_tensor_core(flags, flops))
+    rc = umma::conv_fprop_tf32(p.out, p.a, p.b, p.bias, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW, p.relu,
+                               (flags & NG_F_TF32) ? 0 : 1);
 #endif
   if (rc < 0) rc = launch_conv_gather(p, false);
   prof_end(tok);
@@ -662,8 +670,9 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
   const int tok = prof_begin(NG_PROF_CONV_DGRAD, flops, bytes);
   int rc = -1;
 #ifndef NG_EMU
-  if (flags & NG_F_TF32)
-    rc = umma::conv_dgrad_tf32(p.out, p.a, p.b, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW);
+  if (want_tensor_core(flags, flops))
+    rc = umma::conv_dgrad_tf32(p.out, p.a, p.b, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW,
+                               (flags & NG_F_TF32) ? 0 : 1);
 #endif
   if (rc < 0) rc = launch_conv_gather(p, stride > 1);
   prof_end(tok);
@@ -675,11 +684,11 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
   NG_ENSURE_INIT();
   if (check_conv_dims("ng_conv2d_wgrad", N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW)) return 1;
 #ifndef NG_EMU
-  if (flags & NG_F_TF32) {
+  if (want_tensor_core(flags, 2.0 * N * K * C * R * S * (double)OH * OW)) {
     const int tok = prof_begin(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
                                4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
     const int rc = umma::conv_wgrad_tf32(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R,
-                                         S, stride, pad_t, pad_l, OH, OW);
+                                         S, stride, pad_t, pad_l, OH, OW, (flags & NG_F_TF32) ? 0 : 1);
     prof_end(tok);
     if (rc >= 0) return rc;
   }

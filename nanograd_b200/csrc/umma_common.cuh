@@ -185,15 +185,16 @@ int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
 
-// ---------------------------------------------------------------- host: TF32 convolution
+// ---------------------------------------------------------------- host: tensor-core convolution
+// x3 = 0: TF32 inputs (rtol 1e-2 mode).  x3 = 1: error-compensated 3xTF32 (FP32-accurate).
 // Return 0 = done, -1 = shape not supported by the tensor-core path (use the SIMT kernel),
 // > 0 = error (ng_last_error is set).
 int conv_fprop_tf32(float* y, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int K,
-                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu);
+                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x3);
 int conv_dgrad_tf32(float* dx, const float* dy, const float* w, int N, int C, int H, int W, int K, int R, int S,
-                    int stride, int pad_t, int pad_l, int OH, int OW);
+                    int stride, int pad_t, int pad_l, int OH, int OW, int x3);
 int conv_wgrad_tf32(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
-                    int stride, int pad_t, int pad_l, int OH, int OW);
+                    int stride, int pad_t, int pad_l, int OH, int OW, int x3);
 
 }  // namespace umma
 }  // namespace ng

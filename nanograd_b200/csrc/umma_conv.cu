@@ -80,21 +80,23 @@ __device__ __forceinline__ float tf32_round(float v) {
 // ------------------------------------------------------------------ filter re-layout
 // dst[(rs*J + j)*KC + kc] = w[j*sj + kc*sc + rs]
 __global__ void __launch_bounds__(256) filter_relayout_kernel(float* __restrict__ dst, const float* __restrict__ w,
-                                                              int J, int KC, int RS, long long sj, long long sc) {
+                                                              int J, int KC, int RS, long long sj, long long sc,
+                                                              int round) {
   const long long n = (long long)J * KC * RS;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const int kc = (int)(e % KC);
     const long long t = e / KC;
     const int j = (int)(t % J);
     const int rs = (int)(t / J);
-    dst[e] = tf32_round(w[(long long)j * sj + (long long)kc * sc + rs]);
+    const float v = w[(long long)j * sj + (long long)kc * sc + rs];
+    dst[e] = round ? tf32_round(v) : v;
   }
 }
 
 // ------------------------------------------------------------------ NCHW -> NHWC staging copy
 // out[n][p][c] = in[n][c][p], p = h*W + w.  32 x 32 tiles through shared memory, coalesced both ways.
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(float* __restrict__ out, const float* __restrict__ in, int C,
-                                                           int HW) {
+                                                           int HW, int round) {
   __shared__ float tile[32][33];
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const long long img = (long long)blockIdx.z * C * HW;
@@ -108,19 +110,45 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(float* __restrict__ o
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int p = p0 + ty + 8 * i, c = c0 + tx;
-    if (p < HW && c < C) out[img + (long long)p * C + c] = tf32_round(tile[tx][ty + 8 * i]);
+    if (p < HW && c < C) {
+      const float v = tile[tx][ty + 8 * i];
+      out[img + (long long)p * C + c] = round ? tf32_round(v) : v;
+    }
   }
 }
 
-int to_nhwc(float* out, const float* in, int N, int C, int HW) {
+int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
   dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N);
-  NG_LAUNCH(nchw_to_nhwc_kernel, grid, 256, 0, out, in, C, HW);
+  NG_LAUNCH(nchw_to_nhwc_kernel, grid, 256, 0, out, in, C, HW, round);
   NG_CHECK_LAUNCH();
   return 0;
 }
 
+// ------------------------------------------------------------------ 3xTF32 operand split
+// FP32-accurate mode: a freshly landed stage (FP32 words written by TMA) is split in place into
+//   hi = tf32(v)  (round to nearest)  and  lo = tf32(v - hi)  (second half of the stage),
+// and the MMA warp issues  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is
+// ~2^-22 relative).  128 threads, conflict-free 16-byte accesses; the generic-proxy writes are
+// published to the tensor core's async proxy with fence.proxy.async before the barrier arrive.
+__device__ __forceinline__ void split_stage_hi_lo(uint8_t* stage_hi, uint8_t* stage_lo, uint32_t bytes, int t) {
+  float4* hi = reinterpret_cast<float4*>(stage_hi);
+  float4* lo = reinterpret_cast<float4*>(stage_lo);
+  const int n4 = (int)(bytes >> 4);
+#pragma unroll 4
+  for (int i = t; i < n4; i += 128) {
+    const float4 v = hi[i];
+    float4 h, l;
+    h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+    l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
+  fence_proxy_async();
+}
+
 // ------------------------------------------------------------------ gather kernel (fprop / dgrad)
-constexpr int G_THREADS = 192;
+constexpr int G_THREADS = 192;       // TF32 mode: producer, MMA, 4 epilogue warps
+constexpr int G_THREADS_X3 = 320;    // 3xTF32 mode: + 4 operand-split warps
 constexpr int G_CCHUNK = 32;        // channels per pipeline stage (4 MMAs of K = 8)
 constexpr int G_MAX_STAGES = 8;
 
@@ -139,6 +167,7 @@ struct GatherP {
   int stages;
   uint32_t tmem_cols;
   int relu;
+  int x3;         // 3xTF32 (FP32-accurate) mode: stages hold hi and lo halves
   uint32_t* dbg;  // host-mapped progress words (NG_UMMA_DEBUG=1), else null
   short tap_dx[64], tap_dy[64];
 };
@@ -148,13 +177,15 @@ struct GatherP {
     if (p.dbg) { ((volatile uint32_t*)p.dbg)[i] = (v); __threadfence_system(); } \
   } while (0)
 
-__global__ void __launch_bounds__(G_THREADS, 1) umma_conv_gather_kernel(const __grid_constant__ GatherP p) {
+__global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const __grid_constant__ GatherP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  const uint32_t half_bytes = p.stage_a_bytes + p.stage_b_bytes;          // one operand set (A tile + B tile)
+  const uint32_t stage_bytes = p.x3 ? 2u * half_bytes : half_bytes;       // x3: [hi A|B][lo A|B]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + G_MAX_STAGES;
-  uint64_t* tmem_full = empty_bar + G_MAX_STAGES;
+  uint64_t* split_bar = empty_bar + G_MAX_STAGES;
+  uint64_t* tmem_full = split_bar + G_MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -165,6 +196,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_conv_gather_kernel(const __
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 4);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -202,7 +234,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_conv_gather_kernel(const __
           for (int cc = 0; cc < p.c_chunks; ++cc) {
             mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
             uint8_t* sa = smem + (size_t)s * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+            mbar_arrive_expect_tx(&full_bar[s], half_bytes);
             tma_load_4d(sa, &p.tm_a, &full_bar[s], cc * G_CCHUNK, cx, cy, img0);
             tma_load_3d(sa + p.stage_a_bytes, &p.tm_b, &full_bar[s], cc * G_CCHUNK, n_t * p.n_tile, rs);
             if (blockIdx.x == 0) NG_DBG(8, (uint32_t)(rs * 256 + cc + 1));
@@ -226,14 +258,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_conv_gather_kernel(const __
           const int cc = it % p.c_chunks;
           int ksteps = (p.KC - cc * G_CCHUNK + 7) >> 3;
           if (ksteps > 4) ksteps = 4;
-          mbar_wait(&full_bar[s], ph, p.dbg, 0x300u + s);
+          mbar_wait(p.x3 ? &split_bar[s] : &full_bar[s], ph, p.dbg, 0x300u + s);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + p.stage_a_bytes;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
             const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
-            mma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+            if (p.x3) {
+              const uint64_t adesc_lo = make_smem_desc(sa + half_bytes + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
+              const uint64_t bdesc_lo = make_smem_desc(sb + half_bytes + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
+              mma_tf32(d_tmem, adesc_lo, bdesc, p.idesc, accumulate);
+              mma_tf32(d_tmem, adesc, bdesc_lo, p.idesc, 1u);
+              mma_tf32(d_tmem, adesc, bdesc, p.idesc, 1u);
+            } else {
+              mma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+            }
             accumulate = 1;
           }
           mma_commit(&empty_bar[s]);
@@ -243,6 +283,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_conv_gather_kernel(const __
         mma_commit(&tmem_full[as]);
         as ^= 1;
         if (as == 0) aph ^= 1u;
+      }
+    }
+  } else if (warp >= 6) {
+    // 3xTF32 operand split (these warps exist only in x3 launches)
+    const int t = threadIdx.x - 192;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        split_stage_hi_lo(st, st + half_bytes, half_bytes, t);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
@@ -312,7 +367,7 @@ static inline int pow2_ceil(int v) {
 // the SIMT kernel), > 0 on error.
 static int launch_gather(float* out, const float* act, const float* filt, const float* bias, int n_img, int KC, int AH,
                          int AW, int J, int R, int S, long long sj, long long sc, int OH, int OW, const int* tap_dy,
-                         const int* tap_dx, int relu) {
+                         const int* tap_dx, int relu, int x3) {
   const int RS = R * S;
   if (KC % 4 != 0 || KC < 8 || RS > 64 || J < 8) return -1;
   GatherP p;
@@ -332,14 +387,16 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   p.tiles_h = (int)ceil_div(OH, rows);
   p.tiles_img = (int)ceil_div(n_img, p.imgs_tile);
   int n_tile = (int)ceil_div(J, 32) * 32;
-  if (n_tile > 256) n_tile = 256;
+  const int n_cap = x3 ? 128 : 256;  // x3 stages hold hi and lo halves: keep >= 3 stages in 227 KB
+  if (n_tile > n_cap) n_tile = n_cap;
   p.n_tile = n_tile;
+  p.x3 = x3 ? 1 : 0;
   p.n_tiles = (int)ceil_div(J, n_tile);
   p.c_chunks = (int)ceil_div(KC, G_CCHUNK);
   p.idesc = make_idesc_tf32(128, n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
   p.stage_a_bytes = 128u * G_CCHUNK * 4u;
   p.stage_b_bytes = (uint32_t)n_tile * 128u;
-  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  const uint32_t stage_bytes = (x3 ? 2u : 1u) * (p.stage_a_bytes + p.stage_b_bytes);
   const uint32_t budget = 227u * 1024u - 2048u;
   int stages = (int)(budget / stage_bytes);
   if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
@@ -354,12 +411,12 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   float* wt = nullptr;
   if (pool_alloc((void**)&act_t, (uint64_t)n_img * KC * AH * AW * sizeof(float))) return 1;
   if (pool_alloc((void**)&wt, (uint64_t)RS * J * KC * sizeof(float))) { pool_free(act_t); return 1; }
-  int rc = to_nhwc(act_t, act, n_img, KC, AH * AW);
+  int rc = to_nhwc(act_t, act, n_img, KC, AH * AW, /*round=*/x3 ? 0 : 1);
   if (rc == 0) {
     const long long n = (long long)RS * J * KC;
     int g = (int)ceil_div(n, 256);
     if (g > 148 * 8) g = 148 * 8;
-    NG_LAUNCH(filter_relayout_kernel, g, 256, 0, wt, filt, J, KC, RS, sj, sc);
+    NG_LAUNCH(filter_relayout_kernel, g, 256, 0, wt, filt, J, KC, RS, sj, sc, x3 ? 0 : 1);
     const uint64_t dims[4] = {(uint64_t)KC, (uint64_t)AW, (uint64_t)AH, (uint64_t)n_img};
     const uint64_t strides[3] = {(uint64_t)KC * 4u, (uint64_t)AW * KC * 4u, (uint64_t)AH * AW * KC * 4u};
     const uint32_t box[4] = {(uint32_t)G_CCHUNK, (uint32_t)p.w_tile, (uint32_t)p.rows_tile, (uint32_t)p.imgs_tile};
@@ -394,7 +451,7 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
       fprintf(stderr, "[umma] gather: tiles %d grid %d n_tile %d stages %d w_tile %d rows %d imgs %d idesc %08x tmem %u\n",
               total_tiles, grid, p.n_tile, p.stages, p.w_tile, p.rows_tile, p.imgs_tile, p.idesc, p.tmem_cols);
     }
-    NG_LAUNCH(umma_conv_gather_kernel, grid, G_THREADS, smem_bytes, p);
+    NG_LAUNCH(umma_conv_gather_kernel, grid, x3 ? G_THREADS_X3 : G_THREADS, smem_bytes, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = set_error("umma_conv_gather_kernel launch failed: %s", cudaGetErrorString(e));
     if (debug) {
@@ -410,18 +467,18 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
 }
 
 int conv_fprop_tf32(float* y, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int K,
-                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu) {
+                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x3) {
   if (stride != 1) return -1;
   int dy[64], dx[64];
   if (R * S > 64) return -1;
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) { dy[r * S + s] = r - pad_t; dx[r * S + s] = s - pad_l; }
   return launch_gather(y, x, w, bias, N, C, H, W, K, R, S, (long long)C * R * S, (long long)R * S, OH, OW, dy, dx,
-                       relu);
+                       relu, x3);
 }
 
 int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int C, int H, int W, int K, int R, int S,
-                    int stride, int pad_t, int pad_l, int OH, int OW) {
+                    int stride, int pad_t, int pad_l, int OH, int OW, int x3) {
   if (stride != 1) return -1;
   int dy[64], dx[64];
   if (R * S > 64) return -1;
@@ -429,7 +486,7 @@ int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int 
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) { dy[r * S + s] = pad_t - r; dx[r * S + s] = pad_l - s; }
   return launch_gather(dx_out, dyv, w, nullptr, N, K, OH, OW, C, R, S, (long long)R * S, (long long)C * R * S, H, W,
-                       dy, dx, 0);
+                       dy, dx, 0, x3);
 }
 
 
@@ -446,6 +503,7 @@ int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int 
 // [split][tap][c][k] and a second pass reduces the splits in a fixed order (deterministic) and
 // writes KCRS.
 constexpr int W_THREADS = 192;
+constexpr int W_THREADS_X3 = 320;
 constexpr int W_MAX_STAGES = 6;
 
 struct WgradUP {
@@ -458,17 +516,32 @@ struct WgradUP {
   int pad_t, pad_l;
   uint32_t idesc, stage_a_bytes, stage_b_bytes, tmem_cols;
   int stages;
+  int x3;
   uint32_t* dbg;
 };
 
-__global__ void __launch_bounds__(W_THREADS, 1) umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
+// X3 = false: TF32 mode, one TMEM accumulator for the whole pixel range of the CTA.
+// X3 = true : 3xTF32 mode.  The tensor core's FP32 accumulation is not round-to-nearest, so a long
+//   accumulation chain drifts (measured 1.3e-4 relative after 17k pixels); the reduction is
+//   therefore cut into groups of W_PROMOTE chunks that ping-pong between two TMEM accumulators,
+//   and the epilogue warps add each finished group into FP32 registers (round-to-nearest) while
+//   the next group is being multiplied.
+constexpr int W_PROMOTE = 8;       // chunks (of 32 pixels) per TMEM accumulation group in X3 mode
+constexpr int W_X3_MAX_N = 128;    // output channels per CTA in X3 mode (register accumulator row)
+
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? W_THREADS_X3 : W_THREADS, 1)
+umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  const uint32_t half_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  const uint32_t stage_bytes = X3 ? 2u * half_bytes : half_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + W_MAX_STAGES;
-  uint64_t* tmem_full = empty_bar + W_MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* split_bar = empty_bar + W_MAX_STAGES;
+  uint64_t* acc_full = split_bar + W_MAX_STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -477,8 +550,12 @@ __global__ void __launch_bounds__(W_THREADS, 1) umma_conv_wgrad_kernel(const __g
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 4);
     }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -500,6 +577,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) umma_conv_wgrad_kernel(const __g
   int chunk_end = chunk_begin + p.chunks_per_split;
   if (chunk_end > p.total_chunks) chunk_end = p.total_chunks;
   const int n_chunks = chunk_end > chunk_begin ? chunk_end - chunk_begin : 0;
+  const int n_groups = X3 ? (n_chunks + W_PROMOTE - 1) / W_PROMOTE : (n_chunks > 0 ? 1 : 0);
   const int tap0 = tg * p.taps_per_cta;
   int n_taps = p.RS - tap0;
   if (n_taps > p.taps_per_cta) n_taps = p.taps_per_cta;
@@ -533,23 +611,57 @@ __global__ void __launch_bounds__(W_THREADS, 1) umma_conv_wgrad_kernel(const __g
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      uint32_t accumulate = 0;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(&full_bar[s], ph, p.dbg, 0x300u + s);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + p.stage_a_bytes;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
-          const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
-          mma_tf32(tmem_base, adesc, bdesc, p.idesc, accumulate);
-          accumulate = 1;
+      int ch = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        const int b = X3 ? (g & 1) : 0;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * p.n_tile);
+        if (X3) {
+          mbar_wait(&acc_empty[b], (uint32_t)(((g >> 1) & 1) ^ 1), p.dbg, 0x200u + b);
+          tc_fence_after();
         }
-        mma_commit(&empty_bar[s]);
+        const int g_end = X3 ? (ch + W_PROMOTE < n_chunks ? ch + W_PROMOTE : n_chunks) : n_chunks;
+        uint32_t accumulate = 0;
+        for (; ch < g_end; ++ch) {
+          mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph, p.dbg, 0x300u + s);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + p.stage_a_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
+            const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
+            if (X3) {
+              const uint64_t adesc_lo = make_smem_desc(sa + half_bytes + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
+              const uint64_t bdesc_lo = make_smem_desc(sb + half_bytes + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
+              mma_tf32(d_tmem, adesc_lo, bdesc, p.idesc, accumulate);
+              mma_tf32(d_tmem, adesc, bdesc_lo, p.idesc, 1u);
+              mma_tf32(d_tmem, adesc, bdesc, p.idesc, 1u);
+            } else {
+              mma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+            }
+            accumulate = 1;
+          }
+          mma_commit(&empty_bar[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        mma_commit(&acc_full[b]);
+      }
+    }
+  } else if (warp >= 6) {
+    // 3xTF32 operand split (X3 launches only).  A last tap group with fewer taps leaves part of
+    // the A region unwritten by TMA: splitting that garbage is harmless (those D rows are never stored).
+    if (X3) {
+      const int t = threadIdx.x - 192;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        split_stage_hi_lo(st, st + half_bytes, half_bytes, t);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      mma_commit(tmem_full);
     }
   } else {
     const int q = warp & 3;
@@ -557,25 +669,60 @@ __global__ void __launch_bounds__(W_THREADS, 1) umma_conv_wgrad_kernel(const __g
     const int tl = m / p.Cm, cl = m - tl * p.Cm;
     const int tap = tap0 + tl;
     const int c = c_t * p.Cm + cl;
-    mbar_wait(tmem_full, 0, p.dbg, 0x400u);
-    tc_fence_after();
     float* dst_row = p.ws + (((long long)split * p.RS + tap) * p.C + c) * p.K + (long long)n_t * p.n_tile;
     const bool row_ok = (tl < n_taps);
-    for (int j0 = 0; j0 < p.n_tile; j0 += 32) {
-      uint32_t r[32];
-      if (n_chunks > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j0, r);
-        tmem_ld_wait();
-      } else {
+    if (X3) {
+      float acc[W_X3_MAX_N];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      for (int i = 0; i < W_X3_MAX_N; ++i) acc[i] = 0.f;
+      for (int g = 0; g < n_groups; ++g) {
+        const int b = g & 1;
+        mbar_wait(&acc_full[b], (uint32_t)((g >> 1) & 1), p.dbg, 0x400u + b);
+        tc_fence_after();
+#pragma unroll
+        for (int j0 = 0; j0 < W_X3_MAX_N; j0 += 32) {
+          if (j0 < p.n_tile) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.n_tile + j0), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[j0 + i] += __uint_as_float(r[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
       }
-      if (row_ok && n_t * p.n_tile + j0 < p.K) {
-        float4* d4 = reinterpret_cast<float4*>(dst_row + j0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                              __uint_as_float(r[4 * i + 3]));
+      for (int j0 = 0; j0 < W_X3_MAX_N; j0 += 32) {
+        if (j0 < p.n_tile && row_ok && n_t * p.n_tile + j0 < p.K) {
+          float4* d4 = reinterpret_cast<float4*>(dst_row + j0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            d4[i] = make_float4(acc[j0 + 4 * i], acc[j0 + 4 * i + 1], acc[j0 + 4 * i + 2], acc[j0 + 4 * i + 3]);
+        }
+      }
+    } else {
+      if (n_chunks > 0) {
+        mbar_wait(&acc_full[0], 0, p.dbg, 0x400u);
+        tc_fence_after();
+      }
+      for (int j0 = 0; j0 < p.n_tile; j0 += 32) {
+        uint32_t r[32];
+        if (n_chunks > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+        if (row_ok && n_t * p.n_tile + j0 < p.K) {
+          float4* d4 = reinterpret_cast<float4*>(dst_row + j0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                __uint_as_float(r[4 * i + 3]));
+        }
       }
     }
   }
@@ -603,7 +750,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ d
 }
 
 int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, int H, int W, int K, int R, int S,
-                    int stride, int pad_t, int pad_l, int OH, int OW) {
+                    int stride, int pad_t, int pad_l, int OH, int OW, int x3) {
   const int RS = R * S;
   if (stride != 1 || C % 32 != 0 || K % 32 != 0 || RS > 64) return -1;
   WgradUP p;
@@ -614,8 +761,10 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
   p.taps_per_cta = 128 / p.Cm;
   p.tap_groups = (int)ceil_div(RS, p.taps_per_cta);
   p.c_tiles = C / p.Cm;
-  p.n_tile = K < 256 ? K : 256;
+  const int n_cap = x3 ? W_X3_MAX_N : 256;
+  p.n_tile = K < n_cap ? K : n_cap;
   p.n_tiles = (int)ceil_div(K, p.n_tile);
+  p.x3 = x3 ? 1 : 0;
   int w_c = pow2_ceil(OW);
   if (w_c > 32) w_c = 32;
   p.w_c = w_c;
@@ -634,19 +783,19 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
   p.idesc = make_idesc_tf32(128, p.n_tile, /*a MN-major*/ 1, /*b MN-major*/ 1);
   p.stage_a_bytes = 128u * 128u;
   p.stage_b_bytes = (uint32_t)p.n_tile * 128u;
-  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  const uint32_t stage_bytes = (x3 ? 2u : 1u) * (p.stage_a_bytes + p.stage_b_bytes);
   int stages = (int)((227u * 1024u - 2048u) / stage_bytes);
   if (stages > W_MAX_STAGES) stages = W_MAX_STAGES;
   p.stages = stages;
-  p.tmem_cols = (uint32_t)pow2_ceil(p.n_tile < 32 ? 32 : p.n_tile);
+  p.tmem_cols = (uint32_t)pow2_ceil((x3 ? 2 : 1) * (p.n_tile < 32 ? 32 : p.n_tile));
 
   float *x_t = nullptr, *dy_t = nullptr, *ws = nullptr;
   if (pool_alloc((void**)&x_t, (uint64_t)N * C * H * W * sizeof(float))) return 1;
   if (pool_alloc((void**)&dy_t, (uint64_t)N * K * OH * OW * sizeof(float))) { pool_free(x_t); return 1; }
   if (pool_alloc((void**)&ws, (uint64_t)splits * RS * C * K * sizeof(float))) { pool_free(x_t); pool_free(dy_t); return 1; }
   p.ws = ws;
-  int rc = to_nhwc(x_t, x, N, C, H * W);
-  if (rc == 0) rc = to_nhwc(dy_t, dyv, N, K, OH * OW);
+  int rc = to_nhwc(x_t, x, N, C, H * W, x3 ? 0 : 1);
+  if (rc == 0) rc = to_nhwc(dy_t, dyv, N, K, OH * OW, x3 ? 0 : 1);
   if (rc == 0) {
     const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)(C / 32), (uint64_t)N};
     const uint64_t strides[4] = {(uint64_t)C * 4u, (uint64_t)W * C * 4u, 128u, (uint64_t)H * W * C * 4u};
@@ -662,8 +811,11 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
   if (rc == 0) {
     static bool configured = false;
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(umma_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(umma_conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(227 * 1024));
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(umma_conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(227 * 1024));
       if (e != cudaSuccess) rc = set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       configured = (e == cudaSuccess);
     }
@@ -680,7 +832,8 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
       fprintf(stderr, "[umma] wgrad: grid %d items %d splits %d chunks %d/split Cm %d taps/cta %d n_tile %d stages %d w_c %d rows_c %d\n",
               grid, items, splits, p.chunks_per_split, p.Cm, p.taps_per_cta, p.n_tile, stages, w_c, p.rows_c);
     }
-    NG_LAUNCH(umma_conv_wgrad_kernel, grid, W_THREADS, smem_bytes, p);
+    if (x3) NG_LAUNCH(umma_conv_wgrad_kernel<true>, grid, W_THREADS_X3, smem_bytes, p);
+    else NG_LAUNCH(umma_conv_wgrad_kernel<false>, grid, W_THREADS, smem_bytes, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = set_error("umma_conv_wgrad_kernel launch failed: %s", cudaGetErrorString(e));
     if (debug) {

@@ -46,6 +46,39 @@ def test_case_matches_reference_golden_on_b200(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["simt", "tf32x3"])
+@pytest.mark.parametrize("name", TF32_CASES)
+def test_case_matches_reference_golden_on_b200_fp32_engines(name, mode):
+    """Both FP32-accurate engines at the FP32 bar (rtol 1e-4): the SIMT FFMA kernels alone, and the
+    tensor-core 3xTF32 kernels forced on for every shape they accept."""
+    from nanograd_b200 import backend
+    H.use_cuda_library()
+    backend.set_math_mode(mode)
+    try:
+        fn, kwargs = CASES[name]
+        fw = H.device_framework(Device.GPU)
+        with np.errstate(all="ignore"):
+            got = fn(fw, **kwargs)
+    finally:
+        backend.set_math_mode("fp32")
+    want = H.golden(name)
+    keys = _keys_for_tensor_core_modes(name, want)
+    H.compare_case(name, {k: got[k] for k in keys}, {k: want[k] for k in keys}, H.RTOL_FP32,
+                   cases.EXACT_KEYS.get(name, ()))
+
+
+def _keys_for_tensor_core_modes(name, want):
+    """Adam moves a parameter by ~lr * sign(g) wherever |g| is at the noise level, so post-step weights
+    amplify rounding differences without bound (1e-6 -> 1e-4, 3e-4 -> 1); they are pinned through the
+    SGD twin of the case (and, for the SIMT engine, in the default-mode test).  Outputs, loss and
+    gradients of the Adam case stay in."""
+    keys = list(want.files)
+    if name.endswith("_adam"):
+        keys = [k for k in keys if not k.startswith("param") and k != "loss_last"]
+    return keys
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", TF32_CASES)
 def test_case_matches_reference_golden_on_b200_tf32_mode(name):
     """Opt-in TF32 math (tcgen05 tensor cores): rtol 1e-2 against the reference's vectors."""
@@ -60,12 +93,7 @@ def test_case_matches_reference_golden_on_b200_tf32_mode(name):
     finally:
         backend.set_math_mode("fp32")
     want = H.golden(name)
-    keys = list(want.files)
-    if name.endswith("_adam"):
-        # Adam moves a parameter by ~lr * sign(g) wherever |g| is at the noise level, so post-step
-        # weights amplify TF32 rounding without bound; they are pinned at the FP32 bar in the default
-        # mode and, in TF32 mode, through the SGD twin of the case.  Outputs, loss and gradients stay.
-        keys = [k for k in keys if not k.startswith("param") and k != "loss_last"]
+    keys = _keys_for_tensor_core_modes(name, want)
     H.compare_case(name, {k: got[k] for k in keys}, {k: want[k] for k in keys}, H.RTOL_TF32,
                    cases.EXACT_KEYS.get(name, ()), params_on_model_scale=True)
 

@@ -72,7 +72,11 @@ def main():
     ap.add_argument("--perf", action="store_true")
     ap.add_argument("--passes", default="fprop,dgrad,wgrad")
     ap.add_argument("--set", default="small")
+    ap.add_argument("--x3", action="store_true", help="check the FP32-accurate 3xTF32 mode instead of TF32")
     args = ap.parse_args()
+    global TF32
+    if args.x3:
+        TF32 = B.F_TF32X3 | B.F_TC_FORCE
     B.init()
     passes = args.passes.split(",")
     small = [(2, 32, 32, 32, 32, 3, 3, 1), (2, 64, 32, 32, 64, 3, 3, 1), (4, 64, 16, 16, 128, 3, 3, 1),
