@@ -125,23 +125,24 @@ int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
 }
 
 // ------------------------------------------------------------------ 3xTF32 operand split
-// FP32-accurate mode: a freshly landed stage (FP32 words written by TMA) is split in place into
-//   hi = tf32(v)  (round to nearest)  and  lo = tf32(v - hi)  (second half of the stage),
-// and the MMA warp issues  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is
-// ~2^-22 relative).  128 threads, conflict-free 16-byte accesses; the generic-proxy writes are
-// published to the tensor core's async proxy with fence.proxy.async before the barrier arrive.
-__device__ __forceinline__ void split_stage_hi_lo(uint8_t* stage_hi, uint8_t* stage_lo, uint32_t bytes, int t) {
-  float4* hi = reinterpret_cast<float4*>(stage_hi);
+// FP32-accurate mode.  The tensor core reads an FP32 word as TF32 by ignoring its 13 low mantissa
+// bits, so the stage as TMA wrote it already IS the "hi" operand: hi = trunc13(v).  The split warps
+// only produce  lo = tf32(v - hi)  (exact difference, then rounded) into a separate "lo" operand
+// set, and the MMA warp issues  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is
+// ~2^-20 relative to one product).  128 threads, conflict-free 16-byte accesses; the generic-proxy
+// writes are published to the tensor core's async proxy with fence.proxy.async before the arrive.
+__device__ __forceinline__ float tf32_lo(float v) {
+  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  return tf32_round(v - hi);
+}
+__device__ __forceinline__ void split_stage_hi_lo(const uint8_t* stage_raw, uint8_t* stage_lo, uint32_t bytes, int t) {
+  const float4* raw = reinterpret_cast<const float4*>(stage_raw);
   float4* lo = reinterpret_cast<float4*>(stage_lo);
   const int n4 = (int)(bytes >> 4);
-#pragma unroll 4
+#pragma unroll 8
   for (int i = t; i < n4; i += 128) {
-    const float4 v = hi[i];
-    float4 h, l;
-    h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-    l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
-    hi[i] = h;
-    lo[i] = l;
+    const float4 v = raw[i];
+    lo[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
   }
   fence_proxy_async();
 }
@@ -180,12 +181,16 @@ struct GatherP {
 __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const __grid_constant__ GatherP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t half_bytes = p.stage_a_bytes + p.stage_b_bytes;          // one operand set (A tile + B tile)
-  const uint32_t stage_bytes = p.x3 ? 2u * half_bytes : half_bytes;       // x3: [hi A|B][lo A|B]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  // Shared memory: `stages` operand sets (A tile + B tile) filled by TMA, then — 3xTF32 mode only — a
+  // ring of 2 "lo" sets.  A lo set lives only from the split to the end of its MMAs, an operand set
+  // from the TMA issue on, so most of the capacity stays available for loads in flight.
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (p.x3 ? 2u * stage_bytes : 0u));
   uint64_t* empty_bar = full_bar + G_MAX_STAGES;
   uint64_t* split_bar = empty_bar + G_MAX_STAGES;
-  uint64_t* tmem_full = split_bar + G_MAX_STAGES;
+  uint64_t* lo_empty = split_bar + G_MAX_STAGES;   // [2]
+  uint64_t* tmem_full = lo_empty + 2;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -201,6 +206,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);
+      mbar_init(&lo_empty[s], 1);
     }
     fence_barrier_init();
   }
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
           for (int cc = 0; cc < p.c_chunks; ++cc) {
             mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
             uint8_t* sa = smem + (size_t)s * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[s], half_bytes);
+            mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
             tma_load_4d(sa, &p.tm_a, &full_bar[s], cc * G_CCHUNK, cx, cy, img0);
             tma_load_3d(sa + p.stage_a_bytes, &p.tm_b, &full_bar[s], cc * G_CCHUNK, n_t * p.n_tile, rs);
             if (blockIdx.x == 0) NG_DBG(8, (uint32_t)(rs * 256 + cc + 1));
@@ -249,6 +255,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
+      uint32_t lo_i = 0;  // running stage counter: lo set = lo_i & 1
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[as], aph ^ 1u, p.dbg, 0x200u + as);
         tc_fence_after();
@@ -266,8 +273,9 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
             const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
             const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
             if (p.x3) {
-              const uint64_t adesc_lo = make_smem_desc(sa + half_bytes + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
-              const uint64_t bdesc_lo = make_smem_desc(sb + half_bytes + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
+              const uint32_t la = smem_u32(lo_ring + (size_t)(lo_i & 1u) * stage_bytes);
+              const uint64_t adesc_lo = make_smem_desc(la + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
+              const uint64_t bdesc_lo = make_smem_desc(la + p.stage_a_bytes + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
               mma_tf32(d_tmem, adesc_lo, bdesc, p.idesc, accumulate);
               mma_tf32(d_tmem, adesc, bdesc_lo, p.idesc, 1u);
               mma_tf32(d_tmem, adesc, bdesc, p.idesc, 1u);
@@ -277,6 +285,8 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
             accumulate = 1;
           }
           mma_commit(&empty_bar[s]);
+          if (p.x3) mma_commit(&lo_empty[lo_i & 1u]);
+          ++lo_i;
           if (blockIdx.x == 0) NG_DBG(9, (uint32_t)(it + 1));
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -290,13 +300,15 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
     const int t = threadIdx.x - 192;
     int s = 0;
     uint32_t ph = 0;
+    uint32_t lo_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&lo_empty[lo_i & 1u], ((lo_i >> 1) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i & 1u));
         mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        split_stage_hi_lo(st, st + half_bytes, half_bytes, t);
+        split_stage_hi_lo(smem + (size_t)s * stage_bytes, lo_ring + (size_t)(lo_i & 1u) * stage_bytes, stage_bytes, t);
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[s]);
+        ++lo_i;
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -396,9 +408,9 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   p.idesc = make_idesc_tf32(128, n_tile, /*a K-major*/ 0, /*b K-major*/ 0);
   p.stage_a_bytes = 128u * G_CCHUNK * 4u;
   p.stage_b_bytes = (uint32_t)n_tile * 128u;
-  const uint32_t stage_bytes = (x3 ? 2u : 1u) * (p.stage_a_bytes + p.stage_b_bytes);
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
   const uint32_t budget = 227u * 1024u - 2048u;
-  int stages = (int)(budget / stage_bytes);
+  int stages = (int)(budget / stage_bytes) - (x3 ? 2 : 0);  // x3: two lo sets share the capacity
   if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
   if (stages < 2) return -1;
   p.stages = stages;
@@ -438,7 +450,7 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
     }
   }
   if (rc == 0) {
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+    const size_t smem_bytes = (size_t)(stages + (x3 ? 2 : 0)) * stage_bytes + 1024 + 512;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_img * p.n_tiles;
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int grid = total_tiles < sms ? total_tiles : sms;
@@ -534,12 +546,13 @@ __global__ void __launch_bounds__(X3 ? W_THREADS_X3 : W_THREADS, 1)
 umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t half_bytes = p.stage_a_bytes + p.stage_b_bytes;
-  const uint32_t stage_bytes = X3 ? 2u * half_bytes : half_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;   // X3: two "lo" operand sets
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? 2u * stage_bytes : 0u));
   uint64_t* empty_bar = full_bar + W_MAX_STAGES;
   uint64_t* split_bar = empty_bar + W_MAX_STAGES;
-  uint64_t* acc_full = split_bar + W_MAX_STAGES;   // [2]
+  uint64_t* lo_empty = split_bar + W_MAX_STAGES;   // [2]
+  uint64_t* acc_full = lo_empty + 2;               // [2]
   uint64_t* acc_empty = acc_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -555,6 +568,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 4);
+      mbar_init(&lo_empty[b], 1);
     }
     fence_barrier_init();
   }
@@ -631,8 +645,9 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
             const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
             const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
             if (X3) {
-              const uint64_t adesc_lo = make_smem_desc(sa + half_bytes + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
-              const uint64_t bdesc_lo = make_smem_desc(sb + half_bytes + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
+              const uint32_t la = smem_u32(lo_ring + (size_t)(ch & 1) * stage_bytes);
+              const uint64_t adesc_lo = make_smem_desc(la + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
+              const uint64_t bdesc_lo = make_smem_desc(la + p.stage_a_bytes + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
               mma_tf32(d_tmem, adesc_lo, bdesc, p.idesc, accumulate);
               mma_tf32(d_tmem, adesc, bdesc_lo, p.idesc, 1u);
               mma_tf32(d_tmem, adesc, bdesc, p.idesc, 1u);
@@ -642,6 +657,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
             accumulate = 1;
           }
           mma_commit(&empty_bar[s]);
+          if (X3) mma_commit(&lo_empty[ch & 1]);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         mma_commit(&acc_full[b]);
@@ -655,9 +671,9 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
       int s = 0;
       uint32_t ph = 0;
       for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(&lo_empty[ch & 1], (uint32_t)(((ch >> 1) & 1) ^ 1), p.dbg, 0x600u + (ch & 1));
         mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        split_stage_hi_lo(st, st + half_bytes, half_bytes, t);
+        split_stage_hi_lo(smem + (size_t)s * stage_bytes, lo_ring + (size_t)(ch & 1) * stage_bytes, stage_bytes, t);
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[s]);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -783,9 +799,10 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
   p.idesc = make_idesc_tf32(128, p.n_tile, /*a MN-major*/ 1, /*b MN-major*/ 1);
   p.stage_a_bytes = 128u * 128u;
   p.stage_b_bytes = (uint32_t)p.n_tile * 128u;
-  const uint32_t stage_bytes = (x3 ? 2u : 1u) * (p.stage_a_bytes + p.stage_b_bytes);
-  int stages = (int)((227u * 1024u - 2048u) / stage_bytes);
+  const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
+  int stages = (int)((227u * 1024u - 2048u) / stage_bytes) - (x3 ? 2 : 0);
   if (stages > W_MAX_STAGES) stages = W_MAX_STAGES;
+  if (stages < 2) return -1;
   p.stages = stages;
   p.tmem_cols = (uint32_t)pow2_ceil((x3 ? 2 : 1) * (p.n_tile < 32 ? 32 : p.n_tile));
 
@@ -821,7 +838,7 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
     }
   }
   if (rc == 0) {
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+    const size_t smem_bytes = (size_t)(stages + (x3 ? 2 : 0)) * stage_bytes + 1024 + 512;
     const int grid = items * splits;
     static uint32_t* dbg_host = nullptr;
     const bool debug = getenv("NG_UMMA_DEBUG") != nullptr;
