@@ -87,7 +87,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -327,6 +327,11 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     W, K = max(args.warmup, 3), max(args.steps, 1)
 
     # ---- value: inputs resident in HBM -------------------------------------------------------
+    # the clock sampler starts before the warm-up steps (nvidia-smi needs ~0.1 s to produce its first
+    # line; the timed region of a short run would be over by then) and stops after the timed steps
+    clocks = ClockSampler(dist.local_rank()) if with_clocks else None
+    if clocks:
+        clocks.__enter__()
     for _ in range(W):
         loss = train_step(model, opt, crit, x_res, y_res)
     float(loss.numpy()[0])
@@ -334,12 +339,12 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     lib.ng_measure_ffma_peak(4096, ctypes.byref(ffma_peak))
     lib.ng_prof_reset()
     lib.ng_prof_enable(1)
+    import gc
+    gc.collect()
+    gc.disable()  # a generation-2 collection inside a 10-step timed loop costs more than a step
     dist.barrier()
     B.sync()
     launches0 = B.launch_count()
-    clocks = ClockSampler(dist.local_rank()) if with_clocks else None
-    if clocks:
-        clocks.__enter__()
     e0, e1 = B.Event().record(), B.Event()
     for _ in range(K):
         loss = train_step(model, opt, crit, x_res, y_res)
@@ -376,6 +381,7 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     e1.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     dist.barrier()
+    gc.enable()
     e2e_ms = dist.all_reduce_max(max(e0.elapsed_ms(e1), wall_ms)) / K
     e2e_value = PER_GPU_BATCH * world / (e2e_ms * 1e-3)
     del loss, x_res, y_res, model, opt

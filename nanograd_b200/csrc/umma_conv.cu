@@ -131,20 +131,40 @@ int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
 // set, and the MMA warp issues  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is
 // ~2^-20 relative to one product).  128 threads, conflict-free 16-byte accesses; the generic-proxy
 // writes are published to the tensor core's async proxy with fence.proxy.async before the arrive.
+// lo = v - trunc13(v): exact in FP32 and two instructions.  The tensor core truncates lo itself when
+// it reads it (|error| < 2^-10 |lo| < 2^-20 |v|); rounding it here with cvt.rna would cost ~6 more ALU
+// instructions per element and made the split warps, not the tensor pipe, the critical path.
 __device__ __forceinline__ float tf32_lo(float v) {
   const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-  return tf32_round(v - hi);
+  return v - hi;
 }
-__device__ __forceinline__ void split_stage_hi_lo(const uint8_t* stage_raw, uint8_t* stage_lo, uint32_t bytes, int t) {
-  const float4* raw = reinterpret_cast<const float4*>(stage_raw);
-  float4* lo = reinterpret_cast<float4*>(stage_lo);
-  const int n4 = (int)(bytes >> 4);
-#pragma unroll 8
-  for (int i = t; i < n4; i += 128) {
-    const float4 v = raw[i];
-    lo[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Explicit shared-space accesses in batches of 8 independent 16-byte loads per thread: with generic
+// pointers the compiler serialised load -> convert -> store per element (one load in flight).
+__device__ __forceinline__ void split_stage_hi_lo(const uint8_t* stage_raw, uint8_t* stage_lo, uint32_t bytes, int t,
+                                                  int exp_flags = 0) {
+  const uint32_t raw = smem_u32(stage_raw), lo = smem_u32(stage_lo);
+  int n4 = (int)(bytes >> 4);
+  if (exp_flags & 16) n4 = 0;
+  for (int base = t; base < n4; base += 128 * 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (base + 128 * u < n4) v[u] = lds128(raw + (uint32_t)(base + 128 * u) * 16u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (base + 128 * u < n4)
+        sts128(lo + (uint32_t)(base + 128 * u) * 16u,
+               make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w)));
   }
-  fence_proxy_async();
+  if (!(exp_flags & 8)) fence_proxy_async();
 }
 
 // ------------------------------------------------------------------ gather kernel (fprop / dgrad)
@@ -169,6 +189,7 @@ struct GatherP {
   uint32_t tmem_cols;
   int relu;
   int x3;         // 3xTF32 (FP32-accurate) mode: stages hold hi and lo halves
+  int exp_flags;  // experiments (NG_UMMA_EXP): 1 = skip the split arithmetic, 2 = skip the MMAs, 4 = skip the epilogue stores
   uint32_t* dbg;  // host-mapped progress words (NG_UMMA_DEBUG=1), else null
   short tap_dx[64], tap_dy[64];
 };
@@ -269,6 +290,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + p.stage_a_bytes;
+          if (p.exp_flags & 2) ksteps = 0;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
             const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
@@ -305,7 +327,9 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&lo_empty[lo_i & 1u], ((lo_i >> 1) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i & 1u));
         mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
-        split_stage_hi_lo(smem + (size_t)s * stage_bytes, lo_ring + (size_t)(lo_i & 1u) * stage_bytes, stage_bytes, t);
+        if (!(p.exp_flags & 1))
+          split_stage_hi_lo(smem + (size_t)s * stage_bytes, lo_ring + (size_t)(lo_i & 1u) * stage_bytes, stage_bytes, t,
+                            p.exp_flags);
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[s]);
         ++lo_i;
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
         const int jbase = n_t * p.n_tile + j0;
-        if (valid) {
+        if (valid && !(p.exp_flags & 4)) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int j = jbase + i;
@@ -416,6 +440,7 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   p.stages = stages;
   p.tmem_cols = (uint32_t)pow2_ceil(2 * n_tile < 32 ? 32 : 2 * n_tile);
   p.relu = relu;
+  { const char* e = getenv("NG_UMMA_EXP"); p.exp_flags = e ? atoi(e) : 0; }
   for (int t = 0; t < RS; ++t) { p.tap_dx[t] = (short)tap_dx[t]; p.tap_dy[t] = (short)tap_dy[t]; }
 
   // staging: activations -> NHWC, filters -> [tap][j][kc]
