@@ -110,6 +110,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp (the same one every time for a full mask).  The MMA warp runs its
+// loops warp-uniformly and only the instruction issue sits under this predicate, so descriptors
+// and addresses stay in uniform registers (a single-lane branch made every operand take the
+// R2UR path: ~150 cycles of issue per tcgen05.mma, more than the MMA itself).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- MMA
 // D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs (the FP32 words in shared memory are
 // read with their 13 low mantissa bits ignored), FP32 accumulation.  One thread issues.
@@ -153,6 +169,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [49,52) base offset = 0         [61,64) swizzle: 0 none, 2 = 128B, 4 = 64B, 6 = 32B
 //   1 = 128B rows swizzled in 32B atoms: the only layout for MN-major 32-bit (TF32) operands
 enum { SWZ_NONE = 0, SWZ_128B_ATOM32 = 1, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };
+// High word of a descriptor (constant per operand kind) and low word for a given address: the MMA
+// loops advance only the low word.
+__host__ __device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t swizzle) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((swizzle & 7u) << 29);
+}
+__host__ __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
                                                             uint32_t sbo_bytes, uint32_t swizzle) {
   uint64_t d = 0;

@@ -271,51 +271,62 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      int as = 0;
-      uint32_t aph = 0;
-      uint32_t lo_i = 0;  // running stage counter: lo set = lo_i & 1
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[as], aph ^ 1u, p.dbg, 0x200u + as);
+    // MMA issuer: the whole warp walks the pipeline (uniform control flow), one elected lane issues.
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    uint32_t lo_i = 0;  // running stage counter: lo set = lo_i & 1
+    const uint32_t dhi = smem_desc_hi(1024u, SWZ_128B);
+    const uint32_t smem0 = smem_u32(smem), lo0 = smem_u32(lo_ring);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[as], aph ^ 1u, p.dbg, 0x200u + as);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.n_tile);
+      uint32_t accumulate = 0;
+      int cc = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        int ksteps = (p.KC - cc * G_CCHUNK + 7) >> 3;
+        if (ksteps > 4) ksteps = 4;
+        if (p.exp_flags & 2) ksteps = 0;
+        mbar_wait(p.x3 ? &split_bar[s] : &full_bar[s], ph, p.dbg, 0x300u + s);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.n_tile);
-        uint32_t accumulate = 0;
-        for (int it = 0; it < k_iters; ++it) {
-          const int cc = it % p.c_chunks;
-          int ksteps = (p.KC - cc * G_CCHUNK + 7) >> 3;
-          if (ksteps > 4) ksteps = 4;
-          mbar_wait(p.x3 ? &split_bar[s] : &full_bar[s], ph, p.dbg, 0x300u + s);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + p.stage_a_bytes;
-          if (p.exp_flags & 2) ksteps = 0;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
-            const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
-            if (p.x3) {
-              const uint32_t la = smem_u32(lo_ring + (size_t)(lo_i & 1u) * stage_bytes);
-              const uint64_t adesc_lo = make_smem_desc(la + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
-              const uint64_t bdesc_lo = make_smem_desc(la + p.stage_a_bytes + (uint32_t)k * 32u, 16u, 1024u, SWZ_128B);
-              mma_tf32(d_tmem, adesc_lo, bdesc, p.idesc, accumulate);
-              mma_tf32(d_tmem, adesc, bdesc_lo, p.idesc, 1u);
-              mma_tf32(d_tmem, adesc, bdesc, p.idesc, 1u);
-            } else {
-              mma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
+        const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+        uint32_t a_lo = smem_desc_lo(sa, 16u), b_lo = smem_desc_lo(sa + p.stage_a_bytes, 16u);
+        if (p.x3) {
+          const uint32_t la = lo0 + (lo_i & 1u) * stage_bytes;
+          uint32_t al_lo = smem_desc_lo(la, 16u), bl_lo = smem_desc_lo(la + p.stage_a_bytes, 16u);
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k) {
+              mma_tf32(d_tmem, desc64(al_lo, dhi), desc64(b_lo, dhi), p.idesc, accumulate);
+              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(bl_lo, dhi), p.idesc, 1u);
+              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(b_lo, dhi), p.idesc, 1u);
+              accumulate = 1;
+              a_lo += 2; b_lo += 2; al_lo += 2; bl_lo += 2;   // 32 bytes along K
             }
-            accumulate = 1;
+            mma_commit(&empty_bar[s]);
+            mma_commit(&lo_empty[lo_i & 1u]);
           }
-          mma_commit(&empty_bar[s]);
-          if (p.x3) mma_commit(&lo_empty[lo_i & 1u]);
-          ++lo_i;
-          if (blockIdx.x == 0) NG_DBG(9, (uint32_t)(it + 1));
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        } else {
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k) {
+              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(b_lo, dhi), p.idesc, accumulate);
+              accumulate = 1;
+              a_lo += 2; b_lo += 2;
+            }
+            mma_commit(&empty_bar[s]);
+          }
         }
-        mma_commit(&tmem_full[as]);
-        as ^= 1;
-        if (as == 0) aph ^= 1u;
+        accumulate = ksteps > 0 ? 1u : accumulate;
+        __syncwarp();
+        ++lo_i;
+        if (++cc == p.c_chunks) cc = 0;
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
+      if (elect_one()) mma_commit(&tmem_full[as]);
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aph ^= 1u;
     }
   } else if (warp >= 6) {
     // 3xTF32 operand split (these warps exist only in x3 launches)
@@ -647,46 +658,58 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      int ch = 0;
-      for (int g = 0; g < n_groups; ++g) {
-        const int b = X3 ? (g & 1) : 0;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(b * p.n_tile);
-        if (X3) {
-          mbar_wait(&acc_empty[b], (uint32_t)(((g >> 1) & 1) ^ 1), p.dbg, 0x200u + b);
-          tc_fence_after();
-        }
-        const int g_end = X3 ? (ch + W_PROMOTE < n_chunks ? ch + W_PROMOTE : n_chunks) : n_chunks;
-        uint32_t accumulate = 0;
-        for (; ch < g_end; ++ch) {
-          mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph, p.dbg, 0x300u + s);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + p.stage_a_bytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
-            const uint64_t bdesc = make_smem_desc(sb + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
-            if (X3) {
-              const uint32_t la = smem_u32(lo_ring + (size_t)(ch & 1) * stage_bytes);
-              const uint64_t adesc_lo = make_smem_desc(la + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
-              const uint64_t bdesc_lo = make_smem_desc(la + p.stage_a_bytes + (uint32_t)k * 1024u, 4096u, 512u, SWZ_128B_ATOM32);
-              mma_tf32(d_tmem, adesc_lo, bdesc, p.idesc, accumulate);
-              mma_tf32(d_tmem, adesc, bdesc_lo, p.idesc, 1u);
-              mma_tf32(d_tmem, adesc, bdesc, p.idesc, 1u);
-            } else {
-              mma_tf32(d_tmem, adesc, bdesc, p.idesc, accumulate);
-            }
-            accumulate = 1;
-          }
-          mma_commit(&empty_bar[s]);
-          if (X3) mma_commit(&lo_empty[ch & 1]);
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
-        }
-        mma_commit(&acc_full[b]);
+    // MMA issuer: warp-uniform control flow, one elected lane issues (see elect_one()).
+    int s = 0;
+    uint32_t ph = 0;
+    int ch = 0;
+    const uint32_t dhi = smem_desc_hi(512u, SWZ_128B_ATOM32);
+    const uint32_t smem0 = smem_u32(smem), lo0 = smem_u32(lo_ring);
+    for (int g = 0; g < n_groups; ++g) {
+      const int b = X3 ? (g & 1) : 0;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(b * p.n_tile);
+      if (X3) {
+        mbar_wait(&acc_empty[b], (uint32_t)(((g >> 1) & 1) ^ 1), p.dbg, 0x200u + b);
+        tc_fence_after();
       }
+      const int g_end = X3 ? (ch + W_PROMOTE < n_chunks ? ch + W_PROMOTE : n_chunks) : n_chunks;
+      uint32_t accumulate = 0;
+      for (; ch < g_end; ++ch) {
+        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph, p.dbg, 0x300u + s);
+        tc_fence_after();
+        const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+        uint32_t a_lo = smem_desc_lo(sa, 4096u), b_lo = smem_desc_lo(sa + p.stage_a_bytes, 4096u);
+        if (X3) {
+          const uint32_t la = lo0 + (uint32_t)(ch & 1) * stage_bytes;
+          uint32_t al_lo = smem_desc_lo(la, 4096u), bl_lo = smem_desc_lo(la + p.stage_a_bytes, 4096u);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              mma_tf32(d_tmem, desc64(al_lo, dhi), desc64(b_lo, dhi), p.idesc, accumulate);
+              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(bl_lo, dhi), p.idesc, 1u);
+              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(b_lo, dhi), p.idesc, 1u);
+              accumulate = 1;
+              a_lo += 64; b_lo += 64; al_lo += 64; bl_lo += 64;   // 1024 bytes = 8 pixel rows
+            }
+            mma_commit(&empty_bar[s]);
+            mma_commit(&lo_empty[ch & 1]);
+          }
+        } else {
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(b_lo, dhi), p.idesc, accumulate);
+              accumulate = 1;
+              a_lo += 64; b_lo += 64;
+            }
+            mma_commit(&empty_bar[s]);
+          }
+        }
+        accumulate = 1;
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) mma_commit(&acc_full[b]);
+      __syncwarp();
     }
   } else if (warp >= 6) {
     // 3xTF32 operand split (X3 launches only).  A last tap group with fewer taps leaves part of
