@@ -125,7 +125,11 @@ int ng_onehot(uint64_t out, uint64_t labels, int64_t rows, int64_t classes);
 /*   NG_F_TC_FORCE  take the tensor-core kernel whenever the shape allows; without it NG_F_TF32X3 keeps
  *                problems below ~0.2 GFLOP on the SIMT kernel (staging + extra launches cost more
  *                than they save there). */
-enum { NG_F_RELU = 1, NG_F_TF32 = 2, NG_F_TF32X3 = 4, NG_F_TC_FORCE = 8 };
+/*   NG_F_X_NHWC / NG_F_DY_NHWC  the x (fprop, wgrad) / dy (dgrad, wgrad) argument is already the staged
+ *                channels-last copy made by ng_conv2d_stage_nhwc with the same flags: forward and
+ *                backward of one layer then share two staging passes instead of running four.  Only
+ *                legal when ng_conv2d_tc_plan says that pass takes the tensor-core kernel. */
+enum { NG_F_RELU = 1, NG_F_TF32 = 2, NG_F_TF32X3 = 4, NG_F_TC_FORCE = 8, NG_F_X_NHWC = 16, NG_F_DY_NHWC = 32 };
 /* C[M,N] = op(A) @ op(B) (+ bias[N]) ; row-major; op = transpose when the flag is set.
  * replaces matmul_op, ops_gpu.py:214-232, and the perm+matmul chain in MatMul.backward,
  * ops_gpu.py:452-459.  batch > 1: equally strided batches of A, B and C. */
@@ -147,6 +151,13 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w,
 int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x,
                     int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int flags);
+
+/* Which of fprop / dgrad / wgrad (out[0..2]) will run on the tensor-core kernels for this geometry
+ * and these flags (so a caller knows whether staging an NHWC copy pays off). */
+int ng_conv2d_tc_plan(int N, int C, int H, int W, int K, int R, int S, int stride, int OH, int OW,
+                      int flags, int* out_fprop_dgrad_wgrad);
+/* dst[n][p][c] = src[n][c][p] (p = h*W + w); rounds to TF32 when flags has NG_F_TF32. */
+int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64_t HW, int flags);
 
 /* -------------------------------------------------------------------- pooling ------ */
 /* fused replacements for Tensor._pool2d → Slice, Reshape, Max/Sum(axis=(3,5)), Mul
@@ -179,6 +190,21 @@ int ng_bn2d_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
 int ng_bn2d_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x,
                 uint64_t gamma, uint64_t save_mean, uint64_t save_invstd,
                 int64_t N, int64_t C, int64_t HW);
+
+/* BatchNorm2d followed by an activation in one pass (act: 0 = none, 1 = ReLU): the pair
+ * BatchNorm2d -> ReLU of module.py:356-391 + ops_cpu.py:254-263.  The backward recomputes
+ * z = (x - mean) * gamma * invstd + beta with the forward's exact expression and masks dy with
+ * (z >= 0), the reference's ReLU subgradient (relu'(0) = 1). */
+int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
+                          uint64_t running_mean, uint64_t running_var,
+                          uint64_t save_mean, uint64_t save_invstd,
+                          int64_t N, int64_t C, int64_t HW, float eps, float momentum, int act);
+int ng_bn2d_act_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
+                         uint64_t running_mean, uint64_t running_var,
+                         int64_t N, int64_t C, int64_t HW, float eps, int act);
+int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x,
+                    uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd,
+                    int64_t N, int64_t C, int64_t HW, int act);
 
 /* ------------------------------------------------------------------- optimizers ---- */
 /* one multi-tensor launch per step for the whole parameter list.

@@ -60,6 +60,8 @@ _PROTOTYPES = {
     "ng_conv2d_fprop": [u64, u64, u64, u64] + [i32] * 13,
     "ng_conv2d_dgrad": [u64, u64, u64] + [i32] * 13,
     "ng_conv2d_wgrad": [u64, u64, u64] + [i32] * 13,
+    "ng_conv2d_tc_plan": [i32] * 11 + [POINTER(c_int)],
+    "ng_conv2d_stage_nhwc": [u64, u64, i64, i64, i64, i32],
     "ng_maxpool2d_fwd": [u64, u64, i64, i32, i32, i32, i32],
     "ng_maxpool2d_bwd": [u64, u64, u64, u64, i64, i32, i32, i32, i32],
     "ng_avgpool2d_fwd": [u64, u64, i64, i32, i32, i32, i32],
@@ -71,6 +73,9 @@ _PROTOTYPES = {
     "ng_bn2d_fwd_train": [u64] * 8 + [i64, i64, i64, f32, f32],
     "ng_bn2d_fwd_eval": [u64] * 6 + [i64, i64, i64, f32],
     "ng_bn2d_bwd": [u64] * 8 + [i64, i64, i64],
+    "ng_bn2d_act_fwd_train": [u64] * 8 + [i64, i64, i64, f32, f32, i32],
+    "ng_bn2d_act_fwd_eval": [u64] * 6 + [i64, i64, i64, f32, i32],
+    "ng_bn2d_act_bwd": [u64] * 9 + [i64, i64, i64, i32],
     "ng_multi_sgd": [i32, p_u64, p_u64, p_u64, p_i64, f32, f32, f32],
     "ng_multi_adam": [i32, p_u64, p_u64, p_u64, p_u64, p_i64, f32, f32, f32, f32, f32, f32, f32, i32, f32],
     "ng_multi_pack": [i32, p_u64, p_i64, u64],
@@ -100,7 +105,7 @@ F_RELU, F_TF32, F_TF32X3 = 1, 2, 4
 #   "tf32x3"          like "fp32" but tensor cores for every supported shape, whatever its size.
 #   "tf32"  (opt-in)  tensor cores with plain TF32 inputs / FP32 accumulation (parity bar rtol 1e-2).
 # Selected with NANOGRAD_B200_MATH (or the reference-survey spelling NANOGRAD_TF32=1) or set_math_mode().
-F_TC_FORCE = 8
+F_TC_FORCE, F_X_NHWC, F_DY_NHWC = 8, 16, 32
 _MATH_MODES = {"fp32": F_TF32X3, "simt": 0, "tf32x3": F_TF32X3 | F_TC_FORCE, "tf32": F_TF32}
 _math_flags = _MATH_MODES["tf32" if os.environ.get("NANOGRAD_TF32", "0") == "1"
                           else os.environ.get("NANOGRAD_B200_MATH", "fp32").lower()]

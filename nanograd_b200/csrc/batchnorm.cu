@@ -13,16 +13,25 @@
 
 namespace ng {
 
+// z = (x - mean) * (gamma * invstd) + beta, written ONE way so the forward kernel and the backward
+// kernels that recompute z for the fused-ReLU mask produce bit-identical values.
+__device__ __forceinline__ float bn_affine(float x, float mu, float a, float b) { return fmaf(x - mu, a, b); }
+
 // MODE 0: a = x - shift[c], b = a*a          (forward statistics)
 // MODE 1: a = dy,           b = dy*(x-mean)  (backward reductions)
+// MODE 2: like MODE 1 with dy masked by the fused ReLU: dy * (z >= 0), z recomputed from x
 // partial layout: [S][C][2]; grid = (C, S)
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ partial, const float* __restrict__ x,
                                                         const float* __restrict__ dy, const float* __restrict__ mean,
                                                         int64_t N, int64_t C, int64_t P, int64_t n_per_split,
-                                                        int vec_ok) {
+                                                        int vec_ok, const float* __restrict__ gamma = nullptr,
+                                                        const float* __restrict__ beta = nullptr,
+                                                        const float* __restrict__ invstd = nullptr) {
   __shared__ float scratch[32];
   const int64_t c = blockIdx.x, s = blockIdx.y;
+  float za = 0.f, zb = 0.f;
+  if (MODE == 2) { za = gamma[c] * invstd[c]; zb = beta[c]; }
   const int64_t n0 = s * n_per_split;
   int64_t n1 = n0 + n_per_split;
   if (n1 > N) n1 = N;
@@ -40,7 +49,13 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
         sa += (a0 + a1) + (a2 + a3);
         sb += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
       } else {
-        const float4 g = *reinterpret_cast<const float4*>(dy + off);
+        float4 g = *reinterpret_cast<const float4*>(dy + off);
+        if (MODE == 2) {
+          if (!(bn_affine(xv.x, ref, za, zb) >= 0.f)) g.x = 0.f;
+          if (!(bn_affine(xv.y, ref, za, zb) >= 0.f)) g.y = 0.f;
+          if (!(bn_affine(xv.z, ref, za, zb) >= 0.f)) g.z = 0.f;
+          if (!(bn_affine(xv.w, ref, za, zb) >= 0.f)) g.w = 0.f;
+        }
         sa += (g.x + g.y) + (g.z + g.w);
         sb += (g.x * (xv.x - ref) + g.y * (xv.y - ref)) + (g.z * (xv.z - ref) + g.w * (xv.w - ref));
       }
@@ -55,7 +70,8 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
         sa += a;
         sb += a * a;
       } else {
-        const float g = dy[off];
+        float g = dy[off];
+        if (MODE == 2 && !(bn_affine(x[off], ref, za, zb) >= 0.f)) g = 0.f;
         sa += g;
         sb += g * (x[off] - ref);
       }
@@ -102,7 +118,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, co
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ mean, const float* __restrict__ inv_or_var,
                                                        int64_t total, int64_t C, int64_t P, float eps, int use_var,
-                                                       int vec_ok) {
+                                                       int vec_ok, int relu) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
@@ -112,14 +128,17 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, co
       const float inv = use_var ? 1.f / sqrtf(inv_or_var[c] + eps) : inv_or_var[c];
       const float a = gamma[c] * inv, mu = mean[c], b = beta[c];
       float4 v = reinterpret_cast<const float4*>(x)[i];
-      v.x = (v.x - mu) * a + b; v.y = (v.y - mu) * a + b; v.z = (v.z - mu) * a + b; v.w = (v.w - mu) * a + b;
+      v.x = bn_affine(v.x, mu, a, b); v.y = bn_affine(v.y, mu, a, b);
+      v.z = bn_affine(v.z, mu, a, b); v.w = bn_affine(v.w, mu, a, b);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       reinterpret_cast<float4*>(y)[i] = v;
     }
   } else {
     for (int64_t i = tid; i < total; i += nth) {
       const int64_t c = (i / P) % C;
       const float inv = use_var ? 1.f / sqrtf(inv_or_var[c] + eps) : inv_or_var[c];
-      y[i] = (x[i] - mean[c]) * (gamma[c] * inv) + beta[c];
+      const float z = bn_affine(x[i], mean[c], gamma[c] * inv, beta[c]);
+      y[i] = relu ? fmaxf(z, 0.f) : z;
     }
   }
 }
@@ -146,7 +165,8 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(float* __restrict__ dx, 
                                                         const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ sums, int64_t total, int64_t C, int64_t P,
-                                                        float inv_count, int vec_ok) {
+                                                        float inv_count, int vec_ok, const float* __restrict__ beta) {
+  // beta != nullptr: fused ReLU, dy is masked by (z >= 0) with z recomputed from x
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
@@ -155,8 +175,15 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(float* __restrict__ dx, 
       const int64_t c = ((i << 2) / P) % C;
       const float inv = invstd[c], mu = mean[c];
       const float k0 = gamma[c] * inv, k1 = sums[c * 2] * inv_count, k2 = inv * inv * sums[c * 2 + 1] * inv_count;
-      const float4 g = reinterpret_cast<const float4*>(dy)[i];
+      float4 g = reinterpret_cast<const float4*>(dy)[i];
       const float4 xv = reinterpret_cast<const float4*>(x)[i];
+      if (beta) {
+        const float zb = beta[c];
+        if (!(bn_affine(xv.x, mu, k0, zb) >= 0.f)) g.x = 0.f;
+        if (!(bn_affine(xv.y, mu, k0, zb) >= 0.f)) g.y = 0.f;
+        if (!(bn_affine(xv.z, mu, k0, zb) >= 0.f)) g.z = 0.f;
+        if (!(bn_affine(xv.w, mu, k0, zb) >= 0.f)) g.w = 0.f;
+      }
       float4 o;
       o.x = k0 * (g.x - k1 - (xv.x - mu) * k2); o.y = k0 * (g.y - k1 - (xv.y - mu) * k2);
       o.z = k0 * (g.z - k1 - (xv.z - mu) * k2); o.w = k0 * (g.w - k1 - (xv.w - mu) * k2);
@@ -167,7 +194,9 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(float* __restrict__ dx, 
       const int64_t c = (i / P) % C;
       const float inv = invstd[c];
       const float k0 = gamma[c] * inv, k1 = sums[c * 2] * inv_count, k2 = inv * inv * sums[c * 2 + 1] * inv_count;
-      dx[i] = k0 * (dy[i] - k1 - (x[i] - mean[c]) * k2);
+      float g = dy[i];
+      if (beta && !(bn_affine(x[i], mean[c], k0, beta[c]) >= 0.f)) g = 0.f;
+      dx[i] = k0 * (g - k1 - (x[i] - mean[c]) * k2);
     }
   }
 }
@@ -195,19 +224,21 @@ using namespace ng;
 
 extern "C" {
 
-int ng_bn2d_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
-                      uint64_t running_var, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C,
-                      int64_t HW, float eps, float momentum) {
+int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
+                          uint64_t running_var, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C,
+                          int64_t HW, float eps, float momentum, int act) {
   NG_ENSURE_INIT();
   NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_fwd_train: empty input");
   NG_REQUIRE(C <= 65535, "ng_bn2d_fwd_train: too many channels");
+  NG_REQUIRE(act == 0 || act == 1, "ng_bn2d_act_fwd_train: act must be 0 (none) or 1 (ReLU)");
   int64_t n_per = 0;
   const int S = bn_split(N, C, HW, &n_per);
   float* partial = nullptr;
   if (pool_alloc((void**)&partial, (uint64_t)S * C * 2 * sizeof(float))) return 1;
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
   NG_LAUNCH((bn_reduce_kernel<0>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
-            (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec);
+            (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr,
+            (const float*)nullptr, (const float*)nullptr);
   NG_CHECK_LAUNCH();
   NG_LAUNCH(bn_fwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, dptr<const float>(x),
             dptr<float>(save_mean), dptr<float>(save_invstd), running_mean ? dptr<float>(running_mean) : nullptr,
@@ -216,38 +247,60 @@ int ng_bn2d_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uin
   const int64_t total = N * C * HW;
   NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
             dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(save_mean),
-            dptr<const float>(save_invstd), total, C, HW, eps, 0, vec);
+            dptr<const float>(save_invstd), total, C, HW, eps, 0, vec, act);
   NG_CHECK_LAUNCH();
   pool_free(partial);
   return 0;
 }
 
-int ng_bn2d_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
-                     uint64_t running_var, int64_t N, int64_t C, int64_t HW, float eps) {
+int ng_bn2d_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
+                      uint64_t running_var, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C,
+                      int64_t HW, float eps, float momentum) {
+  return ng_bn2d_act_fwd_train(y, x, gamma, beta, running_mean, running_var, save_mean, save_invstd, N, C, HW, eps,
+                               momentum, 0);
+}
+
+int ng_bn2d_act_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
+                         uint64_t running_var, int64_t N, int64_t C, int64_t HW, float eps, int act) {
   NG_ENSURE_INIT();
+  NG_REQUIRE(act == 0 || act == 1, "ng_bn2d_act_fwd_eval: act must be 0 (none) or 1 (ReLU)");
   const int64_t total = N * C * HW;
   if (total <= 0) return 0;
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
   NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
             dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(running_mean),
-            dptr<const float>(running_var), total, C, HW, eps, 1, vec);
+            dptr<const float>(running_var), total, C, HW, eps, 1, vec, act);
   NG_CHECK_LAUNCH();
   return 0;
 }
 
-int ng_bn2d_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x, uint64_t gamma,
-                uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C, int64_t HW) {
+int ng_bn2d_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
+                     uint64_t running_var, int64_t N, int64_t C, int64_t HW, float eps) {
+  return ng_bn2d_act_fwd_eval(y, x, gamma, beta, running_mean, running_var, N, C, HW, eps, 0);
+}
+
+int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x, uint64_t gamma,
+                    uint64_t beta, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C, int64_t HW,
+                    int act) {
   NG_ENSURE_INIT();
   NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_bwd: empty input");
   NG_REQUIRE(C <= 65535, "ng_bn2d_bwd: too many channels");
+  NG_REQUIRE(act == 0 || (act == 1 && beta != 0), "ng_bn2d_act_bwd: act must be 0, or 1 (ReLU) with beta given");
   int64_t n_per = 0;
   const int S = bn_split(N, C, HW, &n_per);
   float* partial = nullptr;
   if (pool_alloc((void**)&partial, (uint64_t)(S + 1) * C * 2 * sizeof(float))) return 1;
   float* sums = partial + (int64_t)S * C * 2;
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0) && ((dx & 15u) == 0);
-  NG_LAUNCH((bn_reduce_kernel<1>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
-            dptr<const float>(dy), dptr<const float>(save_mean), N, C, HW, n_per, vec);
+  if (act) {
+    NG_LAUNCH((bn_reduce_kernel<2>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
+              dptr<const float>(dy), dptr<const float>(save_mean), N, C, HW, n_per, vec, dptr<const float>(gamma),
+              dptr<const float>(beta), dptr<const float>(save_invstd));
+  } else {
+    NG_LAUNCH((bn_reduce_kernel<1>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
+              dptr<const float>(dy), dptr<const float>(save_mean), N, C, HW, n_per, vec, (const float*)nullptr,
+              (const float*)nullptr, (const float*)nullptr);
+  }
   NG_CHECK_LAUNCH();
   NG_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial,
             dptr<const float>(save_invstd), dptr<float>(dgamma), dptr<float>(dbeta), sums, C, S);
@@ -255,10 +308,16 @@ int ng_bn2d_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint6
   const int64_t total = N * C * HW;
   NG_LAUNCH(bn_bwd_dx_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(dx), dptr<const float>(dy),
             dptr<const float>(x), dptr<const float>(gamma), dptr<const float>(save_mean),
-            dptr<const float>(save_invstd), (const float*)sums, total, C, HW, 1.f / (float)(N * HW), vec);
+            dptr<const float>(save_invstd), (const float*)sums, total, C, HW, 1.f / (float)(N * HW), vec,
+            act ? dptr<const float>(beta) : (const float*)nullptr);
   NG_CHECK_LAUNCH();
   pool_free(partial);
   return 0;
+}
+
+int ng_bn2d_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x, uint64_t gamma,
+                uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C, int64_t HW) {
+  return ng_bn2d_act_bwd(dx, dgamma, dbeta, dy, x, gamma, 0, save_mean, save_invstd, N, C, HW, 0);
 }
 
 }  // extern "C"

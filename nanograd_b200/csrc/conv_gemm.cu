@@ -628,8 +628,10 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
 #ifndef NG_EMU
   if (want_tensor_core(flags, flops))
     rc = umma::conv_fprop_tf32(p.out, p.a, p.b, p.bias, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW, p.relu,
-                               (flags & NG_F_TF32) ? 0 : 1);
+                               (flags & NG_F_TF32) ? 0 : 1, (flags & NG_F_X_NHWC) ? 1 : 0);
 #endif
+  if (rc < 0 && (flags & NG_F_X_NHWC))
+    rc = set_error("ng_conv2d_fprop: NG_F_X_NHWC given but this shape does not take the tensor-core kernel");
   if (rc < 0) rc = launch_conv_gather(p, false);
   prof_end(tok);
   return rc;
@@ -672,11 +674,44 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
 #ifndef NG_EMU
   if (want_tensor_core(flags, flops))
     rc = umma::conv_dgrad_tf32(p.out, p.a, p.b, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW,
-                               (flags & NG_F_TF32) ? 0 : 1);
+                               (flags & NG_F_TF32) ? 0 : 1, (flags & NG_F_DY_NHWC) ? 1 : 0);
 #endif
+  if (rc < 0 && (flags & NG_F_DY_NHWC))
+    rc = set_error("ng_conv2d_dgrad: NG_F_DY_NHWC given but this shape does not take the tensor-core kernel");
   if (rc < 0) rc = launch_conv_gather(p, stride > 1);
   prof_end(tok);
   return rc;
+}
+
+int ng_conv2d_tc_plan(int N, int C, int H, int W, int K, int R, int S, int stride, int OH, int OW, int flags,
+                      int* out_fprop_dgrad_wgrad) {
+  (void)H; (void)W;
+  const double flops = 2.0 * N * K * C * R * S * (double)OH * OW;
+  int f = 0, d = 0, w = 0;
+#ifndef NG_EMU
+  if (stride == 1 && want_tensor_core(flags, flops)) {
+    f = umma::gather_supported(C, K, R * S) ? 1 : 0;
+    d = umma::gather_supported(K, C, R * S) ? 1 : 0;
+    w = umma::wgrad_supported(C, K, R * S) ? 1 : 0;
+  }
+#else
+  (void)flops;
+#endif
+  out_fprop_dgrad_wgrad[0] = f;
+  out_fprop_dgrad_wgrad[1] = d;
+  out_fprop_dgrad_wgrad[2] = w;
+  return 0;
+}
+
+int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64_t HW, int flags) {
+  NG_ENSURE_INIT();
+#ifndef NG_EMU
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL, "ng_conv2d_stage_nhwc: bad dimensions");
+  return umma::to_nhwc(dptr<float>(dst), dptr<const float>(src), (int)N, (int)C, (int)HW, (flags & NG_F_TF32) ? 1 : 0);
+#else
+  (void)dst; (void)src; (void)N; (void)C; (void)HW; (void)flags;
+  return set_error("ng_conv2d_stage_nhwc: the tensor-core path does not exist in the emulation build");
+#endif
 }
 
 int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, int W, int K, int R, int S,
@@ -688,11 +723,14 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
     const int tok = prof_begin(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
                                4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
     const int rc = umma::conv_wgrad_tf32(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R,
-                                         S, stride, pad_t, pad_l, OH, OW, (flags & NG_F_TF32) ? 0 : 1);
+                                         S, stride, pad_t, pad_l, OH, OW, (flags & NG_F_TF32) ? 0 : 1,
+                                         (flags & NG_F_X_NHWC) ? 1 : 0, (flags & NG_F_DY_NHWC) ? 1 : 0);
     prof_end(tok);
     if (rc >= 0) return rc;
   }
 #endif
+  NG_REQUIRE(!(flags & (NG_F_X_NHWC | NG_F_DY_NHWC)),
+             "ng_conv2d_wgrad: staged NHWC operands given but this shape does not take the tensor-core kernel");
   WgradP p;
   memset(&p, 0, sizeof(p));
   p.x = dptr<const float>(x);

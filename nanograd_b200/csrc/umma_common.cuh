@@ -214,12 +214,16 @@ int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64
 // x3 = 0: TF32 inputs (rtol 1e-2 mode).  x3 = 1: error-compensated 3xTF32 (FP32-accurate).
 // Return 0 = done, -1 = shape not supported by the tensor-core path (use the SIMT kernel),
 // > 0 = error (ng_last_error is set).
+// *_is_nhwc: that operand is already a staged channels-last copy (to_nhwc with the same rounding).
 int conv_fprop_tf32(float* y, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int K,
-                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x3);
+                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x3, int x_is_nhwc);
 int conv_dgrad_tf32(float* dx, const float* dy, const float* w, int N, int C, int H, int W, int K, int R, int S,
-                    int stride, int pad_t, int pad_l, int OH, int OW, int x3);
+                    int stride, int pad_t, int pad_l, int OH, int OW, int x3, int dy_is_nhwc);
 int conv_wgrad_tf32(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
-                    int stride, int pad_t, int pad_l, int OH, int OW, int x3);
+                    int stride, int pad_t, int pad_l, int OH, int OW, int x3, int x_is_nhwc, int dy_is_nhwc);
+int to_nhwc(float* out, const float* in, int N, int C, int HW, int round);
+bool gather_supported(int KC, int J, int RS);
+bool wgrad_supported(int C, int K, int RS);
 
 }  // namespace umma
 }  // namespace ng

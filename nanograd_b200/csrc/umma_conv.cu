@@ -408,15 +408,19 @@ static inline int pow2_ceil(int v) {
   return r;
 }
 
+// Shapes the tensor-core kernels take (everything else runs on the FP32 SIMT kernels).
+bool gather_supported(int KC, int J, int RS) { return KC % 4 == 0 && KC >= 8 && RS <= 64 && J >= 8; }
+bool wgrad_supported(int C, int K, int RS) { return C % 32 == 0 && K % 32 == 0 && RS <= 64; }
+
 // Launches the gather kernel.  `act` is the gathered activation tensor [n_img, KC, AH, AW] (NCHW);
 // `filt` the KCRS filters addressed as filt[j*sj + kc*sc + rs]; the output is [n_img, J, OH, OW].
 // Returns 0 on success, -1 when the shape is not supported by this path (caller falls back to
 // the SIMT kernel), > 0 on error.
 static int launch_gather(float* out, const float* act, const float* filt, const float* bias, int n_img, int KC, int AH,
                          int AW, int J, int R, int S, long long sj, long long sc, int OH, int OW, const int* tap_dy,
-                         const int* tap_dx, int relu, int x3) {
+                         const int* tap_dx, int relu, int x3, int act_is_nhwc) {
   const int RS = R * S;
-  if (KC % 4 != 0 || KC < 8 || RS > 64 || J < 8) return -1;
+  if (!gather_supported(KC, J, RS)) return -1;
   GatherP p;
   memset(&p, 0, sizeof(p));
   p.out = out;
@@ -457,9 +461,11 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   // staging: activations -> NHWC, filters -> [tap][j][kc]
   float* act_t = nullptr;
   float* wt = nullptr;
-  if (pool_alloc((void**)&act_t, (uint64_t)n_img * KC * AH * AW * sizeof(float))) return 1;
+  if (!act_is_nhwc && pool_alloc((void**)&act_t, (uint64_t)n_img * KC * AH * AW * sizeof(float))) return 1;
   if (pool_alloc((void**)&wt, (uint64_t)RS * J * KC * sizeof(float))) { pool_free(act_t); return 1; }
-  int rc = to_nhwc(act_t, act, n_img, KC, AH * AW, /*round=*/x3 ? 0 : 1);
+  int rc = 0;
+  const float* act_nhwc = act_is_nhwc ? act : act_t;
+  if (!act_is_nhwc) rc = to_nhwc(act_t, act, n_img, KC, AH * AW, /*round=*/x3 ? 0 : 1);
   if (rc == 0) {
     const long long n = (long long)RS * J * KC;
     int g = (int)ceil_div(n, 256);
@@ -468,7 +474,7 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
     const uint64_t dims[4] = {(uint64_t)KC, (uint64_t)AW, (uint64_t)AH, (uint64_t)n_img};
     const uint64_t strides[3] = {(uint64_t)KC * 4u, (uint64_t)AW * KC * 4u, (uint64_t)AH * AW * KC * 4u};
     const uint32_t box[4] = {(uint32_t)G_CCHUNK, (uint32_t)p.w_tile, (uint32_t)p.rows_tile, (uint32_t)p.imgs_tile};
-    if (encode_tensor_map(&p.tm_a, act_t, 4, dims, strides, box, SWZ_128B)) rc = -1;
+    if (encode_tensor_map(&p.tm_a, act_nhwc, 4, dims, strides, box, SWZ_128B)) rc = -1;
   }
   if (rc == 0) {
     const uint64_t dims[3] = {(uint64_t)KC, (uint64_t)J, (uint64_t)RS};
@@ -515,18 +521,18 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
 }
 
 int conv_fprop_tf32(float* y, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int K,
-                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x3) {
+                    int R, int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x3, int x_is_nhwc) {
   if (stride != 1) return -1;
   int dy[64], dx[64];
   if (R * S > 64) return -1;
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) { dy[r * S + s] = r - pad_t; dx[r * S + s] = s - pad_l; }
   return launch_gather(y, x, w, bias, N, C, H, W, K, R, S, (long long)C * R * S, (long long)R * S, OH, OW, dy, dx,
-                       relu, x3);
+                       relu, x3, x_is_nhwc);
 }
 
 int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int C, int H, int W, int K, int R, int S,
-                    int stride, int pad_t, int pad_l, int OH, int OW, int x3) {
+                    int stride, int pad_t, int pad_l, int OH, int OW, int x3, int dy_is_nhwc) {
   if (stride != 1) return -1;
   int dy[64], dx[64];
   if (R * S > 64) return -1;
@@ -534,7 +540,7 @@ int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int 
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) { dy[r * S + s] = pad_t - r; dx[r * S + s] = pad_l - s; }
   return launch_gather(dx_out, dyv, w, nullptr, N, K, OH, OW, C, R, S, (long long)R * S, (long long)C * R * S, H, W,
-                       dy, dx, 0, x3);
+                       dy, dx, 0, x3, dy_is_nhwc);
 }
 
 
@@ -814,9 +820,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ d
 }
 
 int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, int H, int W, int K, int R, int S,
-                    int stride, int pad_t, int pad_l, int OH, int OW, int x3) {
+                    int stride, int pad_t, int pad_l, int OH, int OW, int x3, int x_is_nhwc, int dy_is_nhwc) {
   const int RS = R * S;
-  if (stride != 1 || C % 32 != 0 || K % 32 != 0 || RS > 64) return -1;
+  if (stride != 1 || !wgrad_supported(C, K, RS)) return -1;
   WgradUP p;
   memset(&p, 0, sizeof(p));
   p.C = C; p.K = K; p.RS = RS; p.S = S;
@@ -855,23 +861,26 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
   p.tmem_cols = (uint32_t)pow2_ceil((x3 ? 2 : 1) * (p.n_tile < 32 ? 32 : p.n_tile));
 
   float *x_t = nullptr, *dy_t = nullptr, *ws = nullptr;
-  if (pool_alloc((void**)&x_t, (uint64_t)N * C * H * W * sizeof(float))) return 1;
-  if (pool_alloc((void**)&dy_t, (uint64_t)N * K * OH * OW * sizeof(float))) { pool_free(x_t); return 1; }
+  if (!x_is_nhwc && pool_alloc((void**)&x_t, (uint64_t)N * C * H * W * sizeof(float))) return 1;
+  if (!dy_is_nhwc && pool_alloc((void**)&dy_t, (uint64_t)N * K * OH * OW * sizeof(float))) { pool_free(x_t); return 1; }
   if (pool_alloc((void**)&ws, (uint64_t)splits * RS * C * K * sizeof(float))) { pool_free(x_t); pool_free(dy_t); return 1; }
   p.ws = ws;
-  int rc = to_nhwc(x_t, x, N, C, H * W, x3 ? 0 : 1);
-  if (rc == 0) rc = to_nhwc(dy_t, dyv, N, K, OH * OW, x3 ? 0 : 1);
+  int rc = 0;
+  const float* x_nhwc = x_is_nhwc ? x : x_t;
+  const float* dy_nhwc = dy_is_nhwc ? dyv : dy_t;
+  if (!x_is_nhwc) rc = to_nhwc(x_t, x, N, C, H * W, x3 ? 0 : 1);
+  if (rc == 0 && !dy_is_nhwc) rc = to_nhwc(dy_t, dyv, N, K, OH * OW, x3 ? 0 : 1);
   if (rc == 0) {
     const uint64_t dims[5] = {32u, (uint64_t)W, (uint64_t)H, (uint64_t)(C / 32), (uint64_t)N};
     const uint64_t strides[4] = {(uint64_t)C * 4u, (uint64_t)W * C * 4u, 128u, (uint64_t)H * W * C * 4u};
     const uint32_t box[5] = {32u, (uint32_t)w_c, (uint32_t)p.rows_c, (uint32_t)(p.Cm / 32), 1u};
-    if (encode_tensor_map(&p.tm_x, x_t, 5, dims, strides, box, SWZ_128B_ATOM32)) rc = -1;
+    if (encode_tensor_map(&p.tm_x, x_nhwc, 5, dims, strides, box, SWZ_128B_ATOM32)) rc = -1;
   }
   if (rc == 0) {
     const uint64_t dims[5] = {32u, (uint64_t)OW, (uint64_t)OH, (uint64_t)(K / 32), (uint64_t)N};
     const uint64_t strides[4] = {(uint64_t)K * 4u, (uint64_t)OW * K * 4u, 128u, (uint64_t)OH * OW * K * 4u};
     const uint32_t box[5] = {32u, (uint32_t)w_c, (uint32_t)p.rows_c, (uint32_t)(p.n_tile / 32), 1u};
-    if (encode_tensor_map(&p.tm_dy, dy_t, 5, dims, strides, box, SWZ_128B_ATOM32)) rc = -1;
+    if (encode_tensor_map(&p.tm_dy, dy_nhwc, 5, dims, strides, box, SWZ_128B_ATOM32)) rc = -1;
   }
   if (rc == 0) {
     static bool configured = false;

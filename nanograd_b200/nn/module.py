@@ -143,8 +143,18 @@ class Sequential(Module):
             submodule.eval()
 
     def forward(self, x: Tensor) -> Tensor:
-        for layer in self.layers:
+        layers, i = self.layers, 0
+        while i < len(layers):
+            layer = layers[i]
+            # BatchNorm2d directly followed by ReLU runs as one fused device op when the device
+            # namespace provides it (same values as the two layers in sequence)
+            if (type(layer) is BatchNorm2d and i + 1 < len(layers) and type(layers[i + 1]) is ReLU
+                    and _fused(x, 'batchnorm2d')):
+                x = layer.forward(x, relu=True)
+                i += 2
+                continue
             x = layer(x)
+            i += 1
         return x
 
     def gpu(self):
@@ -232,13 +242,15 @@ class BatchNorm2d(Module):
         self.running_var = Tensor.ones(self.num_features, requires_grad=False, is_parameter=False,
                                        name="bn_running_var")
 
-    def forward(self, x: Tensor) -> Tensor:
+    def forward(self, x: Tensor, relu: bool = False) -> Tensor:
+        """``relu`` is set by Sequential when the next layer is a ReLU (fused device op only)."""
         if _fused(x, 'batchnorm2d'):
             out = x.batchnorm2d(self.weight, self.bias, running_mean=self.running_mean.data,
                                 running_var=self.running_var.data, eps=self.eps, momentum=self.momentum,
-                                training=bool(self.is_train))
+                                training=bool(self.is_train), relu=bool(relu))
             out.name = 'bn_2d_res'
             return out
+        assert not relu, "the fused BatchNorm2d+ReLU path exists on the device namespace only"
         if self.is_train:
             batch_mean = x.mean(axis=(0, 2, 3))
             batch_var = ((x - batch_mean.reshape(shape=[1, -1, 1, 1])) ** 2).mean(axis=(0, 2, 3))

@@ -540,26 +540,85 @@ def _conv_geometry(x_shape, w_shape, stride, padding):
     return n, c, h, w, k, r, s, oh, ow, pt, pl
 
 
-def _conv2d_forward(x, w, bias, stride, padding, flags=0):
+_PLAN_CACHE = {}
+
+
+def _tc_plan(geom, stride):
+    """(fprop, dgrad, wgrad) -> does that pass run on the tensor-core kernels (current math mode)?"""
+    key = (geom, stride, B.math_flags())
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        import ctypes
+        n, c, h, wd, k, r, s, oh, ow, pt, pl = geom
+        out = (ctypes.c_int * 3)()
+        _lib().ng_conv2d_tc_plan(n, c, h, wd, k, r, s, stride, oh, ow, B.math_flags(), out)
+        plan = _PLAN_CACHE[key] = (bool(out[0]), bool(out[1]), bool(out[2]))
+    return plan
+
+
+def _stage_nhwc(buf):
+    """Channels-last staging copy of an NCHW buffer for the tensor-core kernels (made once, shared
+    by the passes of one layer that read the same tensor)."""
+    n, c = buf.shape[0], buf.shape[1]
+    hw = _numel(buf.shape[2:])
+    out = DeviceBuffer(buf.shape)
+    _lib().ng_conv2d_stage_nhwc(out.ptr, buf.ptr, n, c, hw, B.math_flags())
+    out.staged_flags = B.math_flags()
+    return out
+
+
+def _conv2d_forward(x, w, bias, stride, padding, flags=0, x_nhwc=None):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x.shape, w.shape, stride, padding)
     y = DeviceBuffer((n, k, oh, ow))
-    _lib().ng_conv2d_fprop(y.ptr, x.ptr, w.ptr, bias.ptr if bias is not None else 0,
-                           n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, flags | B.math_flags())
+    src, extra = (x_nhwc, B.F_X_NHWC) if x_nhwc is not None else (x, 0)
+    _lib().ng_conv2d_fprop(y.ptr, src.ptr, w.ptr, bias.ptr if bias is not None else 0,
+                           n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, flags | B.math_flags() | extra)
     return y
 
 
-def _conv2d_dgrad(dy, w, x_shape, stride, padding):
+def _conv2d_dgrad(dy, w, x_shape, stride, padding, dy_nhwc=None):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x_shape, w.shape, stride, padding)
     dx = DeviceBuffer(x_shape)
-    _lib().ng_conv2d_dgrad(dx.ptr, dy.ptr, w.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, B.math_flags())
+    src, extra = (dy_nhwc, B.F_DY_NHWC) if dy_nhwc is not None else (dy, 0)
+    _lib().ng_conv2d_dgrad(dx.ptr, src.ptr, w.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow,
+                           B.math_flags() | extra)
     return dx
 
 
-def _conv2d_wgrad(dy, x, w_shape, stride, padding):
+def _conv2d_wgrad(dy, x, w_shape, stride, padding, x_nhwc=None, dy_nhwc=None):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x.shape, w_shape, stride, padding)
     dw = DeviceBuffer(w_shape)
-    _lib().ng_conv2d_wgrad(dw.ptr, dy.ptr, x.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, B.math_flags())
+    xs, fx = (x_nhwc, B.F_X_NHWC) if x_nhwc is not None else (x, 0)
+    ds, fd = (dy_nhwc, B.F_DY_NHWC) if dy_nhwc is not None else (dy, 0)
+    _lib().ng_conv2d_wgrad(dw.ptr, ds.ptr, xs.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow,
+                           B.math_flags() | fx | fd)
     return dw
+
+
+def _conv_forward_shared(ctx, input, weight, bias, stride, padding):
+    """Forward of Conv2d / Conv2dBias.  When both fprop and wgrad will run on tensor cores the NHWC
+    staging copy of the input is made once here and kept for the backward."""
+    geom = _conv_geometry(input.shape, weight.shape, stride, padding)
+    f_tc, d_tc, w_tc = _tc_plan(geom, stride)
+    x_nhwc = None
+    if f_tc and w_tc and _needs(ctx, 1):
+        x_nhwc = _stage_nhwc(input)
+    ctx.conv_nhwc = x_nhwc
+    return _conv2d_forward(input, weight, bias, stride, padding, x_nhwc=x_nhwc)
+
+
+def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding):
+    geom = _conv_geometry(input.shape, weight.shape, stride, padding)
+    f_tc, d_tc, w_tc = _tc_plan(geom, stride)
+    need_dx, need_dw = _needs(ctx, 0), _needs(ctx, 1)
+    x_nhwc = getattr(ctx, "conv_nhwc", None)
+    if x_nhwc is not None and (not w_tc or getattr(x_nhwc, "staged_flags", None) != B.math_flags()):
+        x_nhwc = None  # math mode changed between forward and backward: restage inside the call
+    dy_nhwc = _stage_nhwc(grad_output) if (need_dx and need_dw and d_tc and w_tc) else None
+    dx = _conv2d_dgrad(grad_output, weight, input.shape, stride, padding, dy_nhwc=dy_nhwc) if need_dx else None
+    dw = _conv2d_wgrad(grad_output, input, weight.shape, stride, padding, x_nhwc=x_nhwc, dy_nhwc=dy_nhwc) \
+        if need_dw else None
+    return dx, dw
 
 
 def _channel_sum(dy):
@@ -578,14 +637,12 @@ class Conv2d(Function):
     def forward(ctx, input, weight, stride=1):
         stride = _scalar_int(stride)
         ctx.save_for_backward(input, weight, stride)
-        return _conv2d_forward(input, weight, None, stride, (0, 0, 0, 0))
+        return _conv_forward_shared(ctx, input, weight, None, stride, (0, 0, 0, 0))
 
     @staticmethod
     def backward(ctx, grad_output):
         input, weight, stride = ctx.saved_tensors
-        dx = _conv2d_dgrad(grad_output, weight, input.shape, stride, (0, 0, 0, 0)) if _needs(ctx, 0) else None
-        dw = _conv2d_wgrad(grad_output, input, weight.shape, stride, (0, 0, 0, 0)) if _needs(ctx, 1) else None
-        return dx, dw
+        return _conv_backward_shared(ctx, grad_output, input, weight, stride, (0, 0, 0, 0))
 
 
 def _as4d(buf):
@@ -628,13 +685,12 @@ class Conv2dBias(Function):
         stride = _scalar_int(stride)
         padding = tuple(int(p) for p in padding)
         ctx.save_for_backward(input, weight, stride, padding)
-        return _conv2d_forward(input, weight, bias, stride, padding)
+        return _conv_forward_shared(ctx, input, weight, bias, stride, padding)
 
     @staticmethod
     def backward(ctx, grad_output):
         input, weight, stride, padding = ctx.saved_tensors
-        dx = _conv2d_dgrad(grad_output, weight, input.shape, stride, padding) if _needs(ctx, 0) else None
-        dw = _conv2d_wgrad(grad_output, input, weight.shape, stride, padding) if _needs(ctx, 1) else None
+        dx, dw = _conv_backward_shared(ctx, grad_output, input, weight, stride, padding)
         db = _channel_sum(grad_output) if _needs(ctx, 2) else None
         return dx, dw, db
 
@@ -784,45 +840,52 @@ class NLLLoss(Function):
 
 class BatchNorm2d(Function):
     """nn.BatchNorm2d.forward fused (module.py:356-391).  ``running_mean`` / ``running_var`` are
-    raw buffers updated in place in training mode; parents are (x, gamma, beta)."""
+    raw buffers updated in place in training mode; parents are (x, gamma, beta).  ``relu=True``
+    also applies the ReLU that follows the layer (ops_cpu.py:254-263) in the same pass; the
+    backward then masks the incoming gradient with (z >= 0) recomputed from x."""
 
     @staticmethod
     def forward(ctx, input, gamma, beta, running_mean=None, running_var=None, eps=1e-5, momentum=0.1,
-                training=True):
+                training=True, relu=False):
         n, c = input.shape[0], input.shape[1]
         hw = _numel(input.shape[2:])
         out = DeviceBuffer(input.shape)
+        act = 1 if relu else 0
         if training:
             save_mean, save_invstd = DeviceBuffer((c,)), DeviceBuffer((c,))
-            _lib().ng_bn2d_fwd_train(out.ptr, input.ptr, gamma.ptr, beta.ptr,
-                                     running_mean.ptr if running_mean is not None else 0,
-                                     running_var.ptr if running_var is not None else 0,
-                                     save_mean.ptr, save_invstd.ptr, n, c, hw, float(eps), float(momentum))
+            _lib().ng_bn2d_act_fwd_train(out.ptr, input.ptr, gamma.ptr, beta.ptr,
+                                         running_mean.ptr if running_mean is not None else 0,
+                                         running_var.ptr if running_var is not None else 0,
+                                         save_mean.ptr, save_invstd.ptr, n, c, hw, float(eps), float(momentum), act)
         else:
-            _lib().ng_bn2d_fwd_eval(out.ptr, input.ptr, gamma.ptr, beta.ptr, running_mean.ptr, running_var.ptr,
-                                    n, c, hw, float(eps))
+            _lib().ng_bn2d_act_fwd_eval(out.ptr, input.ptr, gamma.ptr, beta.ptr, running_mean.ptr, running_var.ptr,
+                                        n, c, hw, float(eps), act)
             # evaluation mode treats the running statistics as constants
             save_mean = running_mean
             save_invstd = _unary(B.U_RECIP, _unary(B.U_SQRT, _binary(B.B_ADD, running_var, ScalarBuffer(eps))))
-        ctx.save_for_backward(input, gamma, save_mean, save_invstd, bool(training))
+        ctx.save_for_backward(input, gamma, beta, save_mean, save_invstd, bool(training), act, out)
         return out
 
     @staticmethod
     def backward(ctx, grad_output):
-        input, gamma, save_mean, save_invstd, training = ctx.saved_tensors
+        input, gamma, beta, save_mean, save_invstd, training, act, out = ctx.saved_tensors
         n, c = input.shape[0], input.shape[1]
         hw = _numel(input.shape[2:])
         if training:
             dx = DeviceBuffer(input.shape)
             dgamma, dbeta = DeviceBuffer((c,)), DeviceBuffer((c,))
-            _lib().ng_bn2d_bwd(dx.ptr, dgamma.ptr, dbeta.ptr, grad_output.ptr, input.ptr, gamma.ptr,
-                               save_mean.ptr, save_invstd.ptr, n, c, hw)
+            _lib().ng_bn2d_act_bwd(dx.ptr, dgamma.ptr, dbeta.ptr, grad_output.ptr, input.ptr, gamma.ptr, beta.ptr,
+                                   save_mean.ptr, save_invstd.ptr, n, c, hw, act)
             return dx, dgamma, dbeta
         # constants statistics: y = (x - m) * g * inv + b
         bshape = (1, c) + (1,) * (len(input.shape) - 2)
         scale = _binary(B.B_MUL, gamma, save_invstd).view(bshape)
-        dx = _binary(B.B_MUL, grad_output, scale)
         xhat = _binary(B.B_MUL, _binary(B.B_SUB, input, save_mean.view(bshape)), save_invstd.view(bshape))
+        if act:
+            # relu'(z) with z = xhat * gamma + beta (the reference's >= 0 subgradient)
+            z = _binary(B.B_ADD, _binary(B.B_MUL, xhat, gamma.view(bshape)), beta.view(bshape))
+            grad_output = _binary(B.B_RELU_BWD, grad_output, z)
+        dx = _binary(B.B_MUL, grad_output, scale)
         axes = [0] + list(range(2, len(input.shape)))
         dgamma = _reduce(B.R_SUM, _binary(B.B_MUL, grad_output, xhat), axes)
         dbeta = _reduce(B.R_SUM, grad_output, axes)
