@@ -1,0 +1,48 @@
+"""tcgen05 convolution kernels vs the FP32 SIMT kernels (which the golden-vector tests pin to the
+reference), through the C ABI, over tile-edge cases: ragged widths/heights, channel counts that are
+not multiples of the 32-channel stage, more than 256 output channels (two N tiles), several images
+per 128-pixel tile, 1x1 and 5x5 filters, Conv1d-shaped problems (H = R = 1).
+
+FP32-accurate 3xTF32 mode: rtol 1e-4 (scale-relative); plain TF32 mode: rtol 1e-2."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+#        N   C   H   W    K  R  S  pad_h pad_w
+SHAPES = [
+    (2, 32, 32, 32, 32, 3, 3, 1, 1), (4, 64, 16, 16, 128, 3, 3, 1, 1), (4, 128, 8, 8, 256, 3, 3, 1, 1),
+    (3, 16, 32, 32, 48, 3, 3, 0, 0), (2, 8, 28, 28, 16, 3, 3, 0, 0), (2, 32, 32, 32, 32, 1, 1, 0, 0),
+    (5, 40, 12, 12, 24, 5, 5, 2, 2), (3, 64, 9, 13, 320, 3, 3, 1, 1), (7, 96, 5, 5, 40, 3, 3, 1, 1),
+    (2, 32, 4, 4, 32, 3, 3, 1, 1), (130, 32, 2, 2, 64, 1, 1, 0, 0), (2, 256, 20, 36, 32, 3, 3, 0, 0),
+    (1, 32, 33, 65, 32, 3, 3, 2, 2), (5, 32, 1, 100, 48, 1, 3, 0, 0), (9, 64, 1, 37, 64, 1, 5, 0, 2),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", H.RTOL_FP32), ("tf32", H.RTOL_TF32)])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_tensor_core_conv_matches_simt(shape, mode, rtol):
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    H.use_cuda_library()
+    lib = B.lib()
+    N, C, Hh, W, K, R, S, ph, pw = shape
+    OH, OW = Hh + 2 * ph - R + 1, W + 2 * pw - S + 1
+    rng = np.random.RandomState(sum(shape))
+    x = DeviceBuffer((N, C, Hh, W), hostbuf=rng.randn(N, C, Hh, W).astype(np.float32))
+    w = DeviceBuffer((K, C, R, S), hostbuf=(rng.randn(K, C, R, S) / np.sqrt(R * S * C)).astype(np.float32))
+    b = DeviceBuffer((K,), hostbuf=rng.randn(K).astype(np.float32))
+    dy = DeviceBuffer((N, K, OH, OW), hostbuf=rng.randn(N, K, OH, OW).astype(np.float32))
+    dims = (N, C, Hh, W, K, R, S, 1, ph, pw, OH, OW)
+    flag = {"tf32x3": B.F_TF32X3 | B.F_TC_FORCE, "tf32": B.F_TF32}[mode]
+    calls = {
+        "fprop": ((N, K, OH, OW), lambda o, f: lib.ng_conv2d_fprop(o.ptr, x.ptr, w.ptr, b.ptr, *dims, f)),
+        "dgrad": ((N, C, Hh, W), lambda o, f: lib.ng_conv2d_dgrad(o.ptr, dy.ptr, w.ptr, *dims, f)),
+        "wgrad": ((K, C, R, S), lambda o, f: lib.ng_conv2d_wgrad(o.ptr, dy.ptr, x.ptr, *dims, f)),
+    }
+    for name, (oshape, fn) in calls.items():
+        ref, got = DeviceBuffer(oshape), DeviceBuffer(oshape)
+        fn(ref, 0)
+        fn(got, flag)
+        H.assert_close(got.numpy(), ref.numpy(), rtol, f"{name} {mode} {shape}")

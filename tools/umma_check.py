@@ -30,15 +30,16 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-def run(N, C, H, W, K, R, S, pad, perf, passes):
+def run(N, C, H, W, K, R, S, pad, perf, passes, pad_h=None):
     lib = B.lib()
     rng = np.random.RandomState(0)
-    OH, OW = H + 2 * pad - R + 1, W + 2 * pad - S + 1
+    pad_h = pad if pad_h is None else pad_h
+    OH, OW = H + 2 * pad_h - R + 1, W + 2 * pad - S + 1
     x = DeviceBuffer((N, C, H, W), hostbuf=rng.randn(N, C, H, W).astype(np.float32))
     w = DeviceBuffer((K, C, R, S), hostbuf=(rng.randn(K, C, R, S) / np.sqrt(R * S * C)).astype(np.float32))
     b = DeviceBuffer((K,), hostbuf=rng.randn(K).astype(np.float32))
     dy = DeviceBuffer((N, K, OH, OW), hostbuf=rng.randn(N, K, OH, OW).astype(np.float32))
-    dims = (N, C, H, W, K, R, S, 1, pad, pad, OH, OW)
+    dims = (N, C, H, W, K, R, S, 1, pad_h, pad, OH, OW)
     flops = 2.0 * N * K * C * R * S * OH * OW
     row = {"shape": f"N{N} C{C} {H}x{W} K{K} {R}x{S} p{pad}"}
     calls = {
@@ -82,11 +83,16 @@ def main():
     small = [(2, 32, 32, 32, 32, 3, 3, 1), (2, 64, 32, 32, 64, 3, 3, 1), (4, 64, 16, 16, 128, 3, 3, 1),
              (4, 128, 8, 8, 256, 3, 3, 1), (3, 16, 32, 32, 48, 3, 3, 0), (2, 8, 28, 28, 16, 3, 3, 0),
              (2, 64, 64, 64, 64, 3, 3, 1), (2, 32, 32, 32, 32, 1, 1, 0), (5, 40, 12, 12, 24, 5, 5, 2)]
+    odd = [(3, 64, 9, 13, 320, 3, 3, 1), (7, 96, 5, 5, 40, 3, 3, 1), (2, 32, 4, 4, 32, 3, 3, 1),
+           (130, 32, 2, 2, 64, 1, 1, 0), (2, 256, 20, 36, 32, 3, 3, 0), (1, 32, 33, 65, 32, 3, 3, 2)]
     vgg = [(512, 64, 32, 32, 64, 3, 3, 1), (512, 64, 16, 16, 128, 3, 3, 1), (512, 128, 16, 16, 128, 3, 3, 1),
            (512, 128, 8, 8, 256, 3, 3, 1), (512, 256, 8, 8, 256, 3, 3, 1)]
     sweep = [(256, c, 32, 32, c, 3, 3, 0) for c in (16, 32, 64, 128, 256)]
-    for shp in {"small": small, "vgg": vgg, "sweep": sweep}[args.set]:
+    for shp in {"small": small, "vgg": vgg, "sweep": sweep, "odd": odd}[args.set]:
         run(*shp, perf=args.perf, passes=passes)
+    if args.set == "odd":   # conv1d-shaped problems (H = R = 1), as Conv1d issues them
+        run(5, 32, 1, 100, 48, 1, 3, 0, perf=args.perf, passes=passes, pad_h=0)
+        run(9, 64, 1, 37, 64, 1, 5, 2, perf=args.perf, passes=passes, pad_h=0)
 
 
 if __name__ == "__main__":
