@@ -132,7 +132,8 @@ int ng_onehot(uint64_t out, uint64_t labels, int64_t rows, int64_t classes);
 enum { NG_F_RELU = 1, NG_F_TF32 = 2, NG_F_TF32X3 = 4, NG_F_TC_FORCE = 8, NG_F_X_NHWC = 16, NG_F_DY_NHWC = 32 };
 /* C[M,N] = op(A) @ op(B) (+ bias[N]) ; row-major; op = transpose when the flag is set.
  * replaces matmul_op, ops_gpu.py:214-232, and the perm+matmul chain in MatMul.backward,
- * ops_gpu.py:452-459.  batch > 1: equally strided batches of A, B and C. */
+ * ops_gpu.py:452-459.  batch > 1: equally strided batches of A, B and C.
+ * flags: NG_F_RELU, and the math-mode flags below (tensor-core GEMM for unbatched problems). */
 int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
             int trans_a, int trans_b, int64_t batch, uint64_t bias, int flags);
 /* y[N,K,OH,OW] = conv(x[N,C,H,W], w[K,C,R,S]) (+ bias[K]) ; cross-correlation, one stride for

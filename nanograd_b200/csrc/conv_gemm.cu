@@ -785,6 +785,16 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
   NG_REQUIRE(M < 2147483647LL && N < 2147483647LL && K < 2147483647LL && batch <= 65535,
              "ng_gemm: dimension too large");
   if (M == 0 || N == 0) return 0;
+#ifndef NG_EMU
+  if (batch == 1 && K > 0 && want_tensor_core(flags, 2.0 * (double)M * N * K)) {
+    const int tok = prof_begin(NG_PROF_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N));
+    const int rc = umma::gemm_tf32(dptr<float>(c), dptr<const float>(a), dptr<const float>(b),
+                                   bias ? dptr<const float>(bias) : nullptr, M, N, K, trans_a, trans_b,
+                                   (flags & NG_F_RELU) ? 1 : 0, (flags & NG_F_TF32) ? 0 : 1);
+    prof_end(tok);
+    if (rc >= 0) return rc;
+  }
+#endif
   // Row-major C[M,N]: the contiguous output index is n → I = N, J = M.
   //   a(i=n, k) = B[k, n]  → !trans_b: B is [K,N], sai = 1,  sak = N ; trans_b: B is [N,K], sai = K, sak = 1
   //   b(k, j=m) = A[m, k]  → !trans_a: A is [M,K], sbj = K,  sbk = 1 ; trans_a: A is [K,M], sbj = 1, sbk = M

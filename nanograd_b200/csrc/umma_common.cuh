@@ -70,6 +70,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volati
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -203,6 +209,58 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a
   return d;
 }
 
+// Round-to-nearest (ties away) FP32 -> TF32.  The tensor core would otherwise truncate the 13 low
+// mantissa bits (a biased, twice larger error); the staging copies round once, for free.
+__device__ __forceinline__ float tf32_round(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+
+// ------------------------------------------------------------------ 3xTF32 operand split
+// FP32-accurate mode.  The tensor core reads an FP32 word as TF32 by ignoring its 13 low mantissa
+// bits, so the stage as TMA wrote it already IS the "hi" operand: hi = trunc13(v).  The split warps
+// only produce  lo = tf32(v - hi)  (exact difference, then rounded) into a separate "lo" operand
+// set, and the MMA warp issues  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is
+// ~2^-20 relative to one product).  128 threads, conflict-free 16-byte accesses; the generic-proxy
+// writes are published to the tensor core's async proxy with fence.proxy.async before the arrive.
+// lo = v - trunc13(v): exact in FP32 and two instructions.  The tensor core truncates lo itself when
+// it reads it (|error| < 2^-10 |lo| < 2^-20 |v|); rounding it here with cvt.rna would cost ~6 more ALU
+// instructions per element and made the split warps, not the tensor pipe, the critical path.
+__device__ __forceinline__ float tf32_lo(float v) {
+  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  return v - hi;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Explicit shared-space accesses in batches of 8 independent 16-byte loads per thread: with generic
+// pointers the compiler serialised load -> convert -> store per element (one load in flight).
+__device__ __forceinline__ void split_stage_hi_lo(const uint8_t* stage_raw, uint8_t* stage_lo, uint32_t bytes, int t,
+                                                  int exp_flags = 0) {
+  const uint32_t raw = smem_u32(stage_raw), lo = smem_u32(stage_lo);
+  int n4 = (int)(bytes >> 4);
+  if (exp_flags & 16) n4 = 0;
+  for (int base = t; base < n4; base += 128 * 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (base + 128 * u < n4) v[u] = lds128(raw + (uint32_t)(base + 128 * u) * 16u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (base + 128 * u < n4)
+        sts128(lo + (uint32_t)(base + 128 * u) * 16u,
+               make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w)));
+  }
+  if (!(exp_flags & 8)) fence_proxy_async();
+}
+
 // ---------------------------------------------------------------- host: tensor maps
 // Encodes a tiled FP32 tensor map.  dims/box are innermost-first; strides_bytes[i] is the byte
 // stride of dimension i+1 (dimension 0 is contiguous).  swizzle is one of the SWZ_* codes.
@@ -222,6 +280,10 @@ int conv_dgrad_tf32(float* dx, const float* dy, const float* w, int N, int C, in
 int conv_wgrad_tf32(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int x3, int x_is_nhwc, int dy_is_nhwc);
 int to_nhwc(float* out, const float* in, int N, int C, int HW, int round);
+// C[M,N] = op(A) @ op(B) (+ bias[N]) (ReLU), row-major FP32 (umma_gemm.cu)
+int gemm_tf32(float* c, const float* a, const float* b, const float* bias, long long M, long long N, long long K,
+              int trans_a, int trans_b, int relu, int x3);
+bool gemm_supported(long long M, long long N, long long K, int trans_a, int trans_b);
 bool gather_supported(int KC, int J, int RS);
 bool wgrad_supported(int C, int K, int RS);
 

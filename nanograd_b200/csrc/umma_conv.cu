@@ -69,14 +69,6 @@ int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64
   return 0;
 }
 
-// Round-to-nearest (ties away) FP32 -> TF32.  The tensor core would otherwise truncate the 13 low
-// mantissa bits (a biased, twice larger error); the staging copies round once, for free.
-__device__ __forceinline__ float tf32_round(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
-}
-
 // ------------------------------------------------------------------ filter re-layout
 // dst[(rs*J + j)*KC + kc] = w[j*sj + kc*sc + rs]
 __global__ void __launch_bounds__(256) filter_relayout_kernel(float* __restrict__ dst, const float* __restrict__ w,
@@ -122,49 +114,6 @@ int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
   NG_LAUNCH(nchw_to_nhwc_kernel, grid, 256, 0, out, in, C, HW, round);
   NG_CHECK_LAUNCH();
   return 0;
-}
-
-// ------------------------------------------------------------------ 3xTF32 operand split
-// FP32-accurate mode.  The tensor core reads an FP32 word as TF32 by ignoring its 13 low mantissa
-// bits, so the stage as TMA wrote it already IS the "hi" operand: hi = trunc13(v).  The split warps
-// only produce  lo = tf32(v - hi)  (exact difference, then rounded) into a separate "lo" operand
-// set, and the MMA warp issues  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is
-// ~2^-20 relative to one product).  128 threads, conflict-free 16-byte accesses; the generic-proxy
-// writes are published to the tensor core's async proxy with fence.proxy.async before the arrive.
-// lo = v - trunc13(v): exact in FP32 and two instructions.  The tensor core truncates lo itself when
-// it reads it (|error| < 2^-10 |lo| < 2^-20 |v|); rounding it here with cvt.rna would cost ~6 more ALU
-// instructions per element and made the split warps, not the tensor pipe, the critical path.
-__device__ __forceinline__ float tf32_lo(float v) {
-  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-  return v - hi;
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// Explicit shared-space accesses in batches of 8 independent 16-byte loads per thread: with generic
-// pointers the compiler serialised load -> convert -> store per element (one load in flight).
-__device__ __forceinline__ void split_stage_hi_lo(const uint8_t* stage_raw, uint8_t* stage_lo, uint32_t bytes, int t,
-                                                  int exp_flags = 0) {
-  const uint32_t raw = smem_u32(stage_raw), lo = smem_u32(stage_lo);
-  int n4 = (int)(bytes >> 4);
-  if (exp_flags & 16) n4 = 0;
-  for (int base = t; base < n4; base += 128 * 8) {
-    float4 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (base + 128 * u < n4) v[u] = lds128(raw + (uint32_t)(base + 128 * u) * 16u);
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (base + 128 * u < n4)
-        sts128(lo + (uint32_t)(base + 128 * u) * 16u,
-               make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w)));
-  }
-  if (!(exp_flags & 8)) fence_proxy_async();
 }
 
 // ------------------------------------------------------------------ gather kernel (fprop / dgrad)

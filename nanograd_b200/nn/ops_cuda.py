@@ -506,7 +506,7 @@ def _gemm(a, b, trans_a=False, trans_b=False, bias=None, flags=0):
         raise Exception(f"matmul: inner dimensions differ ({a.shape} @ {b.shape}, trans_a={trans_a}, trans_b={trans_b})")
     out = DeviceBuffer(tuple(batch_shape) + (am, bn))
     _lib().ng_gemm(out.ptr, a.ptr, b.ptr, am, bn, ak, int(trans_a), int(trans_b), max(batch, 1),
-                   bias.ptr if bias is not None else 0, flags)
+                   bias.ptr if bias is not None else 0, flags | B.math_flags())
     return out
 
 

@@ -46,3 +46,33 @@ def test_tensor_core_conv_matches_simt(shape, mode, rtol):
         fn(ref, 0)
         fn(got, flag)
         H.assert_close(got.numpy(), ref.numpy(), rtol, f"{name} {mode} {shape}")
+
+
+GEMM_SHAPES = [(512, 256, 4096), (256, 4096, 512), (128, 64, 96), (148, 96, 132), (64, 32, 32), (300, 160, 1000),
+               (512, 10, 256)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", H.RTOL_FP32), ("tf32", H.RTOL_TF32)])
+@pytest.mark.parametrize("mnk", GEMM_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_tensor_core_gemm_matches_simt(mnk, mode, rtol):
+    """ng_gemm on tcgen05 (K-major and MN-major operands read in place by TMA, split-K, bias + ReLU
+    epilogue) vs the FP32 SIMT GEMM for every transpose combination; shapes the tensor-core kernel does
+    not take (N = 10, M % 32 != 0 with a transposed A) exercise the per-call fallback."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    H.use_cuda_library()
+    lib = B.lib()
+    M, N, K = mnk
+    rng = np.random.RandomState(M + N + K)
+    flag = {"tf32x3": B.F_TF32X3 | B.F_TC_FORCE, "tf32": B.F_TF32}[mode]
+    for ta in (0, 1):
+        for tb in (0, 1):
+            a = rng.randn(*((K, M) if ta else (M, K))).astype(np.float32)
+            b = rng.randn(*((N, K) if tb else (K, N))).astype(np.float32)
+            bias = rng.randn(N).astype(np.float32)
+            ad, bd, biasd = DeviceBuffer(a.shape, hostbuf=a), DeviceBuffer(b.shape, hostbuf=b), DeviceBuffer((N,), hostbuf=bias)
+            ref, got = DeviceBuffer((M, N)), DeviceBuffer((M, N))
+            lib.ng_gemm(ref.ptr, ad.ptr, bd.ptr, M, N, K, ta, tb, 1, biasd.ptr, B.F_RELU)
+            lib.ng_gemm(got.ptr, ad.ptr, bd.ptr, M, N, K, ta, tb, 1, biasd.ptr, B.F_RELU | flag)
+            H.assert_close(got.numpy(), ref.numpy(), rtol, f"gemm {mode} {mnk} ta={ta} tb={tb}")
