@@ -121,6 +121,7 @@ constexpr int G_THREADS = 192;       // TF32 mode: producer, MMA, 4 epilogue war
 constexpr int G_THREADS_X3 = 320;    // 3xTF32 mode: + 4 operand-split warps
 constexpr int G_CCHUNK = 32;        // channels per pipeline stage (4 MMAs of K = 8)
 constexpr int G_MAX_STAGES = 8;
+constexpr int G_A_RING = 3;         // 3xTF32: A (hi, lo) buffers in TMEM, 64 columns each
 
 struct GatherP {
   CUtensorMap tm_a;  // activations NHWC, dims (C, W, H, N)
@@ -154,13 +155,17 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
   // Shared memory: `stages` operand sets (A tile + B tile) filled by TMA, then — 3xTF32 mode only — a
   // ring of 2 "lo" sets.  A lo set lives only from the split to the end of its MMAs, an operand set
   // from the TMA issue on, so most of the capacity stays available for loads in flight.
+  // 3xTF32 mode: the split warps move the A tile into TMEM (hi and lo, G_A_RING buffers of 64 columns)
+  // and write only B's lo part back to shared memory (ring of 2), so the MMAs read just B from shared
+  // memory: 32 KB of shared-memory traffic per K step of a 128x128 tile instead of 48 KB.
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
-  uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (p.x3 ? 2u * stage_bytes : 0u));
+  uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;   // x3: 2 x stage_b_bytes (B lo)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (p.x3 ? 2u * p.stage_b_bytes : 0u));
   uint64_t* empty_bar = full_bar + G_MAX_STAGES;
   uint64_t* split_bar = empty_bar + G_MAX_STAGES;
   uint64_t* lo_empty = split_bar + G_MAX_STAGES;   // [2]
-  uint64_t* tmem_full = lo_empty + 2;
+  uint64_t* a_empty = lo_empty + 2;                // [G_A_RING]
+  uint64_t* tmem_full = a_empty + G_A_RING;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       mbar_init(&tmem_empty[s], 4);
       mbar_init(&lo_empty[s], 1);
     }
+    for (int s = 0; s < G_A_RING; ++s) mbar_init(&a_empty[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -188,6 +194,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a0 = tmem_base + (uint32_t)(2 * p.n_tile);   // x3: A ring after the two accumulators
   if (threadIdx.x == 0 && blockIdx.x == 0) { NG_DBG(4, tmem_base); NG_DBG(5, 0x1111u); }
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
@@ -243,18 +250,20 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
         uint32_t a_lo = smem_desc_lo(sa, 16u), b_lo = smem_desc_lo(sa + p.stage_a_bytes, 16u);
         if (p.x3) {
-          const uint32_t la = lo0 + (lo_i & 1u) * stage_bytes;
-          uint32_t al_lo = smem_desc_lo(la, 16u), bl_lo = smem_desc_lo(la + p.stage_a_bytes, 16u);
+          uint32_t bl_lo = smem_desc_lo(lo0 + (lo_i & 1u) * p.stage_b_bytes, 16u);
+          const uint32_t aj = lo_i % G_A_RING;
+          uint32_t a_t = tmem_a0 + aj * 64u;   // hi: columns [0,32), lo: [32,64) of the A buffer
           if (elect_one()) {
             for (int k = 0; k < ksteps; ++k) {
-              mma_tf32(d_tmem, desc64(al_lo, dhi), desc64(b_lo, dhi), p.idesc, accumulate);
-              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(bl_lo, dhi), p.idesc, 1u);
-              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(b_lo, dhi), p.idesc, 1u);
+              mma_tf32_ts(d_tmem, a_t + 32u, desc64(b_lo, dhi), p.idesc, accumulate);
+              mma_tf32_ts(d_tmem, a_t, desc64(bl_lo, dhi), p.idesc, 1u);
+              mma_tf32_ts(d_tmem, a_t, desc64(b_lo, dhi), p.idesc, 1u);
               accumulate = 1;
-              a_lo += 2; b_lo += 2; al_lo += 2; bl_lo += 2;   // 32 bytes along K
+              a_t += 8u; b_lo += 2; bl_lo += 2;   // 8 TMEM columns / 32 bytes along K
             }
             mma_commit(&empty_bar[s]);
             mma_commit(&lo_empty[lo_i & 1u]);
+            mma_commit(&a_empty[aj]);
           }
         } else {
           if (elect_one()) {
@@ -279,17 +288,43 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
     }
   } else if (warp >= 6) {
     // 3xTF32 operand split (these warps exist only in x3 launches)
+    // Thread <-> pixel row m of the A tile <-> TMEM lane m (a warp may touch lane quarter warp % 4).
     const int t = threadIdx.x - 192;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t smem0 = smem_u32(smem), lo0 = smem_u32(lo_ring);
     int s = 0;
     uint32_t ph = 0;
     uint32_t lo_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int it = 0; it < k_iters; ++it) {
+        const uint32_t aj = lo_i % G_A_RING;
+        mbar_wait(&a_empty[aj], ((lo_i / G_A_RING) & 1u) ^ 1u, p.dbg, 0x700u + aj);
         mbar_wait(&lo_empty[lo_i & 1u], ((lo_i >> 1) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i & 1u));
         mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
-        if (!(p.exp_flags & 1))
-          split_stage_hi_lo(smem + (size_t)s * stage_bytes, lo_ring + (size_t)(lo_i & 1u) * stage_bytes, stage_bytes, t,
-                            p.exp_flags);
+        tc_fence_after();
+        if (!(p.exp_flags & 1)) {
+          // A: own 128-byte row (32 channels), 16-byte chunks un-swizzled (chunk ^ (row & 7))
+          const uint32_t row = smem0 + (uint32_t)s * stage_bytes + (uint32_t)m * 128u;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = lds128(row + (uint32_t)((c ^ (m & 7)) << 4));
+            hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+            hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+            lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x)); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
+            lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z)); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+          }
+          const uint32_t a_t = tmem_a0 + aj * 64u + lane_addr;
+          tmem_st_32x32(a_t, hi);
+          tmem_st_32x32(a_t + 32u, lo);
+          // B: lo part to the shared-memory ring
+          split_stage_hi_lo(smem + (size_t)s * stage_bytes + p.stage_a_bytes,
+                            lo_ring + (size_t)(lo_i & 1u) * p.stage_b_bytes, p.stage_b_bytes, t, p.exp_flags);
+          tmem_st_wait();
+        }
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[s]);
         ++lo_i;
@@ -398,11 +433,13 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   p.stage_b_bytes = (uint32_t)n_tile * 128u;
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
   const uint32_t budget = 227u * 1024u - 2048u;
-  int stages = (int)(budget / stage_bytes) - (x3 ? 2 : 0);  // x3: two lo sets share the capacity
+  // x3: two B-lo sets share the capacity
+  int stages = (int)((budget - (x3 ? 2u * p.stage_b_bytes : 0u)) / stage_bytes);
   if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
   if (stages < 2) return -1;
   p.stages = stages;
-  p.tmem_cols = (uint32_t)pow2_ceil(2 * n_tile < 32 ? 32 : 2 * n_tile);
+  // TMEM: two accumulators (+ the A ring in x3 mode: 2*128 + 3*64 = 448 <= 512 columns)
+  p.tmem_cols = (uint32_t)pow2_ceil(2 * n_tile + (x3 ? G_A_RING * 64 : 0) < 32 ? 32 : 2 * n_tile + (x3 ? G_A_RING * 64 : 0));
   p.relu = relu;
   { const char* e = getenv("NG_UMMA_EXP"); p.exp_flags = e ? atoi(e) : 0; }
   for (int t = 0; t < RS; ++t) { p.tap_dx[t] = (short)tap_dx[t]; p.tap_dy[t] = (short)tap_dy[t]; }
@@ -441,7 +478,7 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
     }
   }
   if (rc == 0) {
-    const size_t smem_bytes = (size_t)(stages + (x3 ? 2 : 0)) * stage_bytes + 1024 + 512;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + (x3 ? 2u * p.stage_b_bytes : 0u) + 1024 + 512;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_img * p.n_tiles;
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int grid = total_tiles < sms ? total_tiles : sms;
