@@ -118,7 +118,7 @@ int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
 
 // ------------------------------------------------------------------ gather kernel (fprop / dgrad)
 constexpr int G_THREADS = 192;       // TF32 mode: producer, MMA, 4 epilogue warps
-constexpr int G_THREADS_X3 = 320;    // 3xTF32 mode: + 4 operand-split warps
+constexpr int G_THREADS_X3 = 448;    // 3xTF32 mode: + 2 groups of 4 operand-split warps
 constexpr int G_CCHUNK = 32;        // channels per pipeline stage (4 MMAs of K = 8)
 constexpr int G_MAX_STAGES = 8;
 constexpr int G_A_RING = 3;         // 3xTF32: A (hi, lo) buffers in TMEM, 64 columns each
@@ -288,48 +288,49 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
     }
   } else if (warp >= 6) {
     // 3xTF32 operand split (these warps exist only in x3 launches)
+    // Two groups of four split warps take alternate stages (group g: stage counters g, g+2, ...), so
+    // the barrier wake-up / LDS / TMEM-store latency of one stage overlaps the other group's work.
     // Thread <-> pixel row m of the A tile <-> TMEM lane m (a warp may touch lane quarter warp % 4).
-    const int t = threadIdx.x - 192;
+    const int grp = (warp - 6) >> 2;
+    const int t = (threadIdx.x - 192) & 127;
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t smem0 = smem_u32(smem), lo0 = smem_u32(lo_ring);
-    int s = 0;
-    uint32_t ph = 0;
-    uint32_t lo_i = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int it = 0; it < k_iters; ++it) {
-        const uint32_t aj = lo_i % G_A_RING;
-        mbar_wait(&a_empty[aj], ((lo_i / G_A_RING) & 1u) ^ 1u, p.dbg, 0x700u + aj);
-        mbar_wait(&lo_empty[lo_i & 1u], ((lo_i >> 1) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i & 1u));
-        mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
-        tc_fence_after();
-        if (!(p.exp_flags & 1)) {
-          // A: own 128-byte row (32 channels), 16-byte chunks un-swizzled (chunk ^ (row & 7))
-          const uint32_t row = smem0 + (uint32_t)s * stage_bytes + (uint32_t)m * 128u;
-          uint32_t hi[32], lo[32];
+    const uint32_t smem0 = smem_u32(smem);
+    int my_tiles = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
+    const uint32_t total_iters = (uint32_t)my_tiles * (uint32_t)k_iters;
+    for (uint32_t lo_i = (uint32_t)grp; lo_i < total_iters; lo_i += 2u) {
+      const int s = (int)(lo_i % (uint32_t)p.stages);
+      const uint32_t ph = (lo_i / (uint32_t)p.stages) & 1u;
+      const uint32_t aj = lo_i % G_A_RING;
+      mbar_wait(&a_empty[aj], ((lo_i / G_A_RING) & 1u) ^ 1u, p.dbg, 0x700u + aj);
+      mbar_wait(&lo_empty[lo_i & 1u], ((lo_i >> 1) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i & 1u));
+      mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
+      tc_fence_after();
+      if (!(p.exp_flags & 1)) {
+        // A: own 128-byte row (32 channels), 16-byte chunks un-swizzled (chunk ^ (row & 7))
+        const uint32_t row = smem0 + (uint32_t)s * stage_bytes + (uint32_t)m * 128u;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = lds128(row + (uint32_t)((c ^ (m & 7)) << 4));
-            hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
-            hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
-            lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x)); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
-            lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z)); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
-          }
-          const uint32_t a_t = tmem_a0 + aj * 64u + lane_addr;
-          tmem_st_32x32(a_t, hi);
-          tmem_st_32x32(a_t + 32u, lo);
-          // B: lo part to the shared-memory ring
-          split_stage_hi_lo(smem + (size_t)s * stage_bytes + p.stage_a_bytes,
-                            lo_ring + (size_t)(lo_i & 1u) * p.stage_b_bytes, p.stage_b_bytes, t, p.exp_flags);
-          tmem_st_wait();
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = lds128(row + (uint32_t)((c ^ (m & 7)) << 4));
+          hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+          hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+          lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x)); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
+          lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z)); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&split_bar[s]);
-        ++lo_i;
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        const uint32_t a_t = tmem_a0 + aj * 64u + lane_addr;
+        tmem_st_32x32(a_t, hi);
+        tmem_st_32x32(a_t + 32u, lo);
+        // B: lo part to the shared-memory ring
+        split_stage_hi_lo(smem + (size_t)s * stage_bytes + p.stage_a_bytes,
+                          lo_ring + (size_t)(lo_i & 1u) * p.stage_b_bytes, p.stage_b_bytes, t, p.exp_flags);
+        tmem_st_wait();
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[s]);
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
