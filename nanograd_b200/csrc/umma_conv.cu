@@ -544,7 +544,8 @@ int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int 
 // [split][tap][c][k] and a second pass reduces the splits in a fixed order (deterministic) and
 // writes KCRS.
 constexpr int W_THREADS = 192;
-constexpr int W_THREADS_X3 = 320;
+constexpr int W_THREADS_X3 = 448;   // + 2 groups of 4 operand-split warps
+constexpr int W_A_RING = 3;         // X3: x operand (hi, lo) buffers in TMEM, 64 columns each
 constexpr int W_MAX_STAGES = 6;
 
 struct WgradUP {
@@ -576,12 +577,15 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
-  uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;   // X3: two "lo" operand sets
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? 2u * stage_bytes : 0u));
+  // X3: the x operand (hi, lo) goes to TMEM (ring of W_A_RING buffers of 64 columns, written by the
+  // split warps), only dy's lo part goes back to shared memory (ring of 2)
+  uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? 2u * p.stage_b_bytes : 0u));
   uint64_t* empty_bar = full_bar + W_MAX_STAGES;
   uint64_t* split_bar = empty_bar + W_MAX_STAGES;
   uint64_t* lo_empty = split_bar + W_MAX_STAGES;   // [2]
-  uint64_t* acc_full = lo_empty + 2;               // [2]
+  uint64_t* a_empty = lo_empty + 2;                // [W_A_RING]
+  uint64_t* acc_full = a_empty + W_A_RING;         // [2]
   uint64_t* acc_empty = acc_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -599,6 +603,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
       mbar_init(&acc_empty[b], 4);
       mbar_init(&lo_empty[b], 1);
     }
+    for (int b = 0; b < W_A_RING; ++b) mbar_init(&a_empty[b], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -609,6 +614,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a0 = tmem_base + (uint32_t)(2 * p.n_tile);   // X3: A ring after the two accumulators
 
   // work item
   int item = blockIdx.x;
@@ -672,19 +678,21 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
         uint32_t a_lo = smem_desc_lo(sa, 4096u), b_lo = smem_desc_lo(sa + p.stage_a_bytes, 4096u);
         if (X3) {
-          const uint32_t la = lo0 + (uint32_t)(ch & 1) * stage_bytes;
-          uint32_t al_lo = smem_desc_lo(la, 4096u), bl_lo = smem_desc_lo(la + p.stage_a_bytes, 4096u);
+          uint32_t bl_lo = smem_desc_lo(lo0 + (uint32_t)(ch & 1) * p.stage_b_bytes, 4096u);
+          const uint32_t aj = (uint32_t)ch % W_A_RING;
+          uint32_t a_t = tmem_a0 + aj * 64u;   // hi: columns [0,32), lo: [32,64)
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              mma_tf32(d_tmem, desc64(al_lo, dhi), desc64(b_lo, dhi), p.idesc, accumulate);
-              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(bl_lo, dhi), p.idesc, 1u);
-              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(b_lo, dhi), p.idesc, 1u);
+              mma_tf32_ts(d_tmem, a_t + 32u, desc64(b_lo, dhi), p.idesc, accumulate);
+              mma_tf32_ts(d_tmem, a_t, desc64(bl_lo, dhi), p.idesc, 1u);
+              mma_tf32_ts(d_tmem, a_t, desc64(b_lo, dhi), p.idesc, 1u);
               accumulate = 1;
-              a_lo += 64; b_lo += 64; al_lo += 64; bl_lo += 64;   // 1024 bytes = 8 pixel rows
+              a_t += 8u; b_lo += 64; bl_lo += 64;   // 8 pixels: 8 TMEM columns / 1024 bytes
             }
             mma_commit(&empty_bar[s]);
             mma_commit(&lo_empty[ch & 1]);
+            mma_commit(&a_empty[aj]);
           }
         } else {
           if (elect_one()) {
@@ -708,16 +716,43 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
     // 3xTF32 operand split (X3 launches only).  A last tap group with fewer taps leaves part of
     // the A region unwritten by TMA: splitting that garbage is harmless (those D rows are never stored).
     if (X3) {
-      const int t = threadIdx.x - 192;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      // Two groups of four split warps take alternate chunks.  Thread <-> row m = (tap, channel) of the
+      // x operand <-> TMEM lane m; its 32 pixel values come from one shared-memory column of the
+      // [pixel][32 channels] group (32-byte chunks swizzled by pixel & 3).
+      const int grp = (warp - 6) >> 2;
+      const int t = (threadIdx.x - 192) & 127;
+      const int q = warp & 3;
+      const int m = q * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      const uint32_t smem0 = smem_u32(smem);
+      const uint32_t col_base = (uint32_t)(m >> 5) * 4096u + (uint32_t)(m & 7) * 4u;  // group, position in 32B chunk
+      const uint32_t chunk32 = (uint32_t)((m & 31) >> 3);
+      for (int ch = grp; ch < n_chunks; ch += 2) {
+        const int s = ch % p.stages;
+        const uint32_t ph = (uint32_t)(ch / p.stages) & 1u;
+        const uint32_t aj = (uint32_t)ch % W_A_RING;
+        mbar_wait(&a_empty[aj], (uint32_t)((((uint32_t)ch / W_A_RING) & 1u) ^ 1u), p.dbg, 0x700u + aj);
         mbar_wait(&lo_empty[ch & 1], (uint32_t)(((ch >> 1) & 1) ^ 1), p.dbg, 0x600u + (ch & 1));
         mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
-        split_stage_hi_lo(smem + (size_t)s * stage_bytes, lo_ring + (size_t)(ch & 1) * stage_bytes, stage_bytes, t);
+        tc_fence_after();
+        const uint32_t sa = smem0 + (uint32_t)s * stage_bytes + col_base;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa + (uint32_t)k * 128u + ((chunk32 ^ (uint32_t)(k & 3)) << 5)));
+          hi[k] = __float_as_uint(v);
+          lo[k] = __float_as_uint(tf32_lo(v));
+        }
+        const uint32_t a_t = tmem_a0 + aj * 64u + lane_addr;
+        tmem_st_32x32(a_t, hi);
+        tmem_st_32x32(a_t + 32u, lo);
+        split_stage_hi_lo(smem + (size_t)s * stage_bytes + p.stage_a_bytes,
+                          lo_ring + (size_t)(ch & 1) * p.stage_b_bytes, p.stage_b_bytes, t);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
@@ -837,15 +872,16 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
   p.chunks_per_split = (int)ceil_div(p.total_chunks, splits);
   splits = (int)ceil_div(p.total_chunks, p.chunks_per_split);
   p.splits = splits;
-  p.idesc = make_idesc_tf32(128, p.n_tile, /*a MN-major*/ 1, /*b MN-major*/ 1);
+  // X3: the x operand is read from TMEM (K-major by construction), dy stays MN-major in shared memory
+  p.idesc = make_idesc_tf32(128, p.n_tile, /*a MN-major*/ x3 ? 0 : 1, /*b MN-major*/ 1);
   p.stage_a_bytes = 128u * 128u;
   p.stage_b_bytes = (uint32_t)p.n_tile * 128u;
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
-  int stages = (int)((227u * 1024u - 2048u) / stage_bytes) - (x3 ? 2 : 0);
+  int stages = (int)((227u * 1024u - 2048u - (x3 ? 2u * p.stage_b_bytes : 0u)) / stage_bytes);
   if (stages > W_MAX_STAGES) stages = W_MAX_STAGES;
   if (stages < 2) return -1;
   p.stages = stages;
-  p.tmem_cols = (uint32_t)pow2_ceil((x3 ? 2 : 1) * (p.n_tile < 32 ? 32 : p.n_tile));
+  p.tmem_cols = (uint32_t)pow2_ceil(x3 ? 2 * p.n_tile + W_A_RING * 64 : (p.n_tile < 32 ? 32 : p.n_tile));
 
   float *x_t = nullptr, *dy_t = nullptr, *ws = nullptr;
   if (!x_is_nhwc && pool_alloc((void**)&x_t, (uint64_t)N * C * H * W * sizeof(float))) return 1;
@@ -882,7 +918,7 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
     }
   }
   if (rc == 0) {
-    const size_t smem_bytes = (size_t)(stages + (x3 ? 2 : 0)) * stage_bytes + 1024 + 512;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + (x3 ? 2u * p.stage_b_bytes : 0u) + 1024 + 512;
     const int grid = items * splits;
     static uint32_t* dbg_host = nullptr;
     const bool debug = getenv("NG_UMMA_DEBUG") != nullptr;
