@@ -320,9 +320,6 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     # this rank's shard of the global synthetic batch
     Xh, Yh = synthetic_batch(PER_GPU_BATCH, seed=1000 + rank)
     x_res, y_res = Tensor(Xh, device=Device.GPU), Tensor(Yh, device=Device.GPU)
-    x_pin, y_pin = B.pinned_empty(Xh.shape), B.pinned_empty(Yh.shape)
-    x_pin[...] = Xh
-    y_pin[...] = Yh
 
     W, K = max(args.warmup, 3), max(args.steps, 1)
 
@@ -364,17 +361,23 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     ms_per_step = ms_total / K
     value = PER_GPU_BATCH * world / (ms_per_step * 1e-3)
 
-    # ---- e2e: pinned host batch -> device each step, loss read back each step ----------------
-    for _ in range(2):
-        loss = train_step(model, opt, crit, Tensor(x_pin, device=Device.GPU), Tensor(y_pin, device=Device.GPU))
-        float(loss.numpy()[0])
-    dist.barrier()
-    B.sync()
-    e0, e1 = B.Event().record(), B.Event()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        xb = Tensor(x_pin, device=Device.GPU)   # H2D of this step's inputs (pinned source, async)
-        yb = Tensor(y_pin, device=Device.GPU)
+    # ---- e2e: the public input pipeline (nanograd_b200.data.BatchLoader) -----------------------
+    # Every step draws a random mini-batch from a host-resident synthetic dataset (the reference's loop,
+    # tests/helpers.py:294-299), gathers it into pinned staging memory, copies it host->device on the
+    # copy stream (overlapping the previous step) and reads the loss back to the host (blocking).
+    from nanograd_b200.data import BatchLoader
+    rng = np.random.RandomState(2000 + rank)
+    n_data = 4 * PER_GPU_BATCH
+    Xd = rng.randn(n_data, 3, 32, 32).astype(np.float32)
+    Yd = rng.randint(0, 10, n_data).astype(np.float32)
+    # one loader for 2 untimed + K timed steps (its pinned staging and thread exist before the clock starts)
+    e0, e1, t0 = None, B.Event(), 0.0
+    for i, (xb, yb) in enumerate(BatchLoader(Xd, Yd, PER_GPU_BATCH, 2 + K, device=Device.GPU)):
+        if i == 2:
+            dist.barrier()
+            B.sync()
+            e0 = B.Event().record()
+            t0 = time.perf_counter()
         loss = train_step(model, opt, crit, xb, yb)
         float(loss.numpy()[0])                  # D2H of the step's result (blocking)
     e1.record()

@@ -47,6 +47,25 @@ int ng_memset_zero(uint64_t ptr, uint64_t bytes);
 int ng_h2d(uint64_t dst, const void* src, uint64_t bytes);
 int ng_d2h(void* dst, uint64_t src, uint64_t bytes); /* blocking, like is_blocking=True */
 int ng_d2d(uint64_t dst, uint64_t src, uint64_t bytes);
+/* input pipeline: copy batch i+1 on a second stream while step i computes.
+ * slot in [0,4) names the done-event of one staging buffer; the copy is ordered after everything the
+ * compute stream was given before the call (the last readers of a double-buffered destination). */
+int ng_h2d_prefetch(int slot, uint64_t dst, const void* pinned_src, uint64_t bytes);
+int ng_prefetch_wait(int slot);   /* compute stream waits for the slot's copy */
+int ng_prefetch_sync(int slot);   /* host waits for the slot's copy (pinned source reusable) */
+/* Batch loader owned by the library (a host thread that never touches the Python interpreter): for every
+ * step t it gathers rows plan[offsets[t] .. offsets[t+1]) of the host dataset X (and labels Y, float32,
+ * may be NULL) into pinned memory and prefetches them into the caller's double-buffered device tensors
+ * x_dev[t & 1] / y_dev[t & 1].  ng_loader_next returns the slot of the next batch once its copy is
+ * ordered before the compute stream. */
+int ng_loader_create(uint64_t* out_handle, const void* X, const void* Y, int64_t n_rows, uint64_t row_bytes,
+                     int batch, int steps, const int64_t* plan, const int64_t* offsets,
+                     uint64_t x_dev0, uint64_t x_dev1, uint64_t y_dev0, uint64_t y_dev1);
+int ng_loader_next(uint64_t handle, int* out_slot, int64_t* out_rows);
+int ng_loader_destroy(uint64_t handle);
+/* host-side row gather into (pinned) staging memory: dst[i] = src[idx[i]], rows of row_bytes bytes */
+int ng_host_gather_rows(void* dst, const void* src, const int64_t* idx, int64_t n, uint64_t row_bytes,
+                        int64_t n_src_rows);
 int ng_pinned_alloc(void** out, uint64_t bytes);
 int ng_pinned_free(void* p);
 /* CUDA-event timers on the compute stream */
@@ -177,6 +196,11 @@ int ng_logsoftmax_bwd(uint64_t dx, uint64_t dy, uint64_t logp, int64_t rows, int
 /* fused NLLLoss.forward = -(logp * onehot(labels)).mean() over rows*cols (module.py:684-686) */
 int ng_nll_fwd(uint64_t loss1, uint64_t logp, uint64_t labels, int64_t rows, int64_t cols);
 int ng_nll_bwd(uint64_t dlogp, uint64_t dloss1, uint64_t labels, int64_t rows, int64_t cols);
+
+/* device-side accuracy (replaces the per-step D2H of the logits + host argmax, tests/helpers.py:310-313):
+ * out[r] = first argmax of row r as float32 ; out1[0] = #{i : a[i] == b[i]} */
+int ng_argmax_rows(uint64_t out, uint64_t in, int64_t rows, int64_t cols);
+int ng_count_equal(uint64_t out1, uint64_t a, uint64_t b, int64_t n);
 
 /* ------------------------------------------------------------------ batch norm ----- */
 /* fused BatchNorm2d.forward/_normalize (module.py:356-391): biased variance normalises,

@@ -34,6 +34,15 @@ _PROTOTYPES = {
     "ng_h2d": [u64, c_void_p, u64],
     "ng_d2h": [c_void_p, u64, u64],
     "ng_d2d": [u64, u64, u64],
+    "ng_h2d_prefetch": [i32, u64, c_void_p, u64],
+    "ng_prefetch_wait": [i32],
+    "ng_prefetch_sync": [i32],
+    "ng_host_gather_rows": [c_void_p, c_void_p, p_i64, i64, u64, i64],
+    "ng_loader_create": [p_u64, c_void_p, c_void_p, i64, u64, i32, i32, p_i64, p_i64, u64, u64, u64, u64],
+    "ng_loader_next": [u64, POINTER(c_int), p_i64],
+    "ng_loader_destroy": [u64],
+    "ng_argmax_rows": [u64, u64, i64, i64],
+    "ng_count_equal": [u64, u64, u64, i64],
     "ng_pinned_alloc": [POINTER(c_void_p), u64],
     "ng_pinned_free": [c_void_p],
     "ng_event_create": [p_u64],

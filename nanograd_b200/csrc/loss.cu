@@ -81,6 +81,33 @@ static inline int row_grid(int64_t rows) {
   return (int)g;
 }
 
+// ---- evaluation metrics on the device (the reference copies logits to the host every step to take an
+// argmax, tests/helpers.py:310-313,326-334) --------------------------------------------------------------
+// out[r] = index of the first maximum of row r (np.argmax semantics), as float32
+__global__ void __launch_bounds__(256) argmax_rows_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                          int64_t rows, int64_t cols) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* row = in + r * cols;
+  float best = row[0];
+  int64_t arg = 0;
+  for (int64_t c = 1; c < cols; ++c) {
+    const float v = row[c];
+    if (v > best) { best = v; arg = c; }
+  }
+  out[r] = (float)arg;
+}
+
+// out[0] = number of i with a[i] == b[i] (one block; exact while n < 2^24)
+__global__ void __launch_bounds__(1024) count_equal_kernel(float* __restrict__ out, const float* __restrict__ a,
+                                                           const float* __restrict__ b, int64_t n) {
+  __shared__ float scratch[32];
+  float cnt = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) cnt += (a[i] == b[i]) ? 1.f : 0.f;
+  const float total = block_sum(cnt, scratch);
+  if (threadIdx.x == 0) out[0] = total;
+}
+
 }  // namespace ng
 
 using namespace ng;
@@ -121,6 +148,23 @@ int ng_nll_bwd(uint64_t dlogp, uint64_t dloss1, uint64_t labels, int64_t rows, i
   if (g > cap) g = cap;
   NG_LAUNCH(nll_bwd_kernel, (int)g, 256, 0, dptr<float>(dlogp), dptr<const float>(dloss1),
             dptr<const float>(labels), rows, cols);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_argmax_rows(uint64_t out, uint64_t in, int64_t rows, int64_t cols) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(rows >= 0 && cols > 0, "ng_argmax_rows: bad shape");
+  if (rows == 0) return 0;
+  NG_LAUNCH(argmax_rows_kernel, (int)ceil_div(rows, 256), 256, 0, dptr<float>(out), dptr<const float>(in), rows, cols);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_count_equal(uint64_t out1, uint64_t a, uint64_t b, int64_t n) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(n >= 0 && n < (1LL << 24), "ng_count_equal: n must be below 2^24 (float32 counter)");
+  NG_LAUNCH(count_equal_kernel, 1, 1024, 0, dptr<float>(out1), dptr<const float>(a), dptr<const float>(b), n);
   NG_CHECK_LAUNCH();
   return 0;
 }
