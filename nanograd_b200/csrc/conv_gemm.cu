@@ -221,6 +221,110 @@ __global__ void __launch_bounds__(CT_THREADS, 2) conv_gather_kernel(const __grid
 }
 
 // =====================================================================================
+// fprop for the image-facing layer (C <= 4, 3x3, stride 1): with C*9 <= 36 reduction terms the
+// implicit GEMM spends most of its time staging.  Here a thread owns a strip of 4 output pixels,
+// holds its C x 3 x 6 input window in registers and walks the output channels: per channel the
+// filter row comes from shared memory as warp-uniform LDS.128, C*36 FFMA follow, and the warp
+// stores 512 contiguous bytes of one (image, channel) plane.  blockIdx.y splits the channels so
+// that small batches still fill the machine.
+// =====================================================================================
+struct FpropSmallP {
+  const float* x;
+  const float* w;
+  const float* bias;
+  float* out;
+  int N, H, W, K, OH, OW, pad_t, pad_l;
+  int strips, kper, relu;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) conv_fprop_smallc_kernel(const __grid_constant__ FpropSmallP p) {
+  constexpr int CRS = C * 9, WP = (CRS + 3) & ~3;
+  NG_DYN_SMEM(float, wsm);  // [kn][WP]
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.y * p.kper;
+  const int kn = p.K - k0 < p.kper ? p.K - k0 : p.kper;
+  for (int e = tid; e < kn * WP; e += 256) {
+    const int kk = e / WP, j = e - kk * WP;
+    wsm[e] = j < CRS ? p.w[(long long)(k0 + kk) * CRS + j] : 0.f;
+  }
+  __syncthreads();
+  const int strip = blockIdx.x * 256 + tid;
+  if (strip >= p.strips) return;
+  const int ow4 = p.OW >> 2, per_img = p.OH * ow4;
+  const int n = strip / per_img, rem = strip - n * per_img;
+  const int oh = rem / ow4, ow0 = (rem - oh * ow4) * 4;
+  float xv[C][3][6];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh + r - p.pad_t;
+      const float* row = p.x + ((long long)(n * C + c) * p.H + ih) * p.W;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int iw = ow0 + j - p.pad_l;
+        xv[c][r][j] = (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) ? row[iw] : 0.f;
+      }
+    }
+  const long long plane = (long long)p.OH * p.OW;
+  float* o = p.out + ((long long)n * p.K + k0) * plane + (long long)oh * p.OW + ow0;
+  for (int kk = 0; kk < kn; ++kk) {
+    float wv[WP];
+#pragma unroll
+    for (int j = 0; j < WP; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(wsm + kk * WP + j);
+      wv[j] = t.x; wv[j + 1] = t.y; wv[j + 2] = t.z; wv[j + 3] = t.w;
+    }
+    const float b = p.bias ? p.bias[k0 + kk] : 0.f;
+    float4 a;
+    a.x = a.y = a.z = a.w = b;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const float wgt = wv[(c * 3 + r) * 3 + s];
+          a.x = fmaf(wgt, xv[c][r][s], a.x);
+          a.y = fmaf(wgt, xv[c][r][s + 1], a.y);
+          a.z = fmaf(wgt, xv[c][r][s + 2], a.z);
+          a.w = fmaf(wgt, xv[c][r][s + 3], a.w);
+        }
+    if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    *reinterpret_cast<float4*>(o + kk * plane) = a;
+  }
+}
+
+static int launch_fprop_smallc(const ConvGatherP& g, int N, int C, int H, int W, int K, int OH, int OW, int pad_t,
+                               int pad_l) {
+  FpropSmallP p;
+  memset(&p, 0, sizeof(p));
+  p.x = g.a; p.w = g.b; p.bias = g.bias; p.out = g.out;
+  p.N = N; p.H = H; p.W = W; p.K = K; p.OH = OH; p.OW = OW; p.pad_t = pad_t; p.pad_l = pad_l;
+  p.strips = N * OH * (OW / 4);
+  p.relu = g.relu;
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  const int gx = (int)ceil_div(p.strips, 256);
+  int ksplit = 1;
+  while (gx * ksplit < 6 * sms && K / (ksplit * 2) >= 16) ksplit *= 2;
+  p.kper = (int)ceil_div(K, ksplit);
+  const int gy = (int)ceil_div(K, p.kper);
+  const int wp = (C * 9 + 3) & ~3;
+  const size_t smem = sizeof(float) * (size_t)p.kper * wp;
+  if (smem > 48 * 1024) return -1;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  switch (C) {
+    case 1: NG_LAUNCH((conv_fprop_smallc_kernel<1>), grid, 256, smem, p); break;
+    case 2: NG_LAUNCH((conv_fprop_smallc_kernel<2>), grid, 256, smem, p); break;
+    case 3: NG_LAUNCH((conv_fprop_smallc_kernel<3>), grid, 256, smem, p); break;
+    default: NG_LAUNCH((conv_fprop_smallc_kernel<4>), grid, 256, smem, p); break;
+  }
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+// =====================================================================================
 // dense epilogue shared by wgrad and GEMM: out[z][j*ldc + i]
 // =====================================================================================
 template <class T>
@@ -386,6 +490,93 @@ __global__ void __launch_bounds__(CT_THREADS, 2) conv_wgrad_kernel(const __grid_
   }
   float* out = p.out + (long long)blockIdx.z * p.K * p.CRS;
   dense_store<T>(out, p.CRS, p.CRS, p.K, tile_i0, tile_j0, c, acc, nullptr, 0, p.vec_store);
+}
+
+// =====================================================================================
+// wgrad for the image-facing layer (C*R <= 12 filter rows, S == 3, stride 1): the implicit GEMM
+// above has only C*R*S = 27 useful columns in a 64-wide tile, so this case gets a direct kernel.
+// A CTA stages TR output rows of one image — dy as [K][TR*OW (+4 pad)] and x with its halo as
+// [C][TR+R-1][OW+4], shifted by pad_l so that column ow+s of a strip starts 16-byte aligned — and
+// thread (k, g) keeps dW[k][row][0..2] for its RPG filter rows (row = c*R + r) in registers:
+// per 4-pixel strip one LDS.128 of dy and two warp-uniform LDS.128 of x per row feed 12 FFMA.
+// CTAs walk tiles grid-strided and write one partial per CTA; splitk_reduce_kernel sums them
+// in a fixed order.
+// =====================================================================================
+struct WgradSmallP {
+  const float* x;
+  const float* dy;
+  float* ws;  // [gridDim.x][K][C*R*3]
+  int N, C, H, W, K, R, OH, OW, pad_t, pad_l;
+  int TR, row_blocks, tiles, NR, xrows, xpitch, dpitch;
+};
+
+template <int RPG>
+__global__ void __launch_bounds__(1024) conv_wgrad_smallc_kernel(const __grid_constant__ WgradSmallP p) {
+  NG_DYN_SMEM(float, sm);
+  float* dys = sm;
+  float* xs = sm + p.K * p.dpitch;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int k = tid % p.K, g = tid / p.K;
+  const int PX = p.TR * p.OW, PX4 = PX >> 2;
+  int xoff[RPG];
+  bool live[RPG];
+  float acc[RPG][3];
+#pragma unroll
+  for (int q = 0; q < RPG; ++q) {
+    const int row = g * RPG + q;
+    live[q] = row < p.NR;
+    const int c = live[q] ? row / p.R : 0, r = live[q] ? row % p.R : 0;
+    xoff[q] = (c * p.xrows + r) * p.xpitch;
+    acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+  }
+  const int xtile = p.C * p.xrows * p.xpitch;
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    const int n = tile / p.row_blocks, oh0 = (tile - n * p.row_blocks) * p.TR;
+    const int nvalid = (p.OH - oh0 < p.TR ? p.OH - oh0 : p.TR) * p.OW;
+    __syncthreads();  // the previous tile has been consumed
+    for (int e = tid; e < p.K * PX4; e += nthr) {
+      const int kk = e / PX4, q4 = (e - kk * PX4) * 4;
+      float4 v;
+      v.x = v.y = v.z = v.w = 0.f;
+      if (q4 < nvalid)
+        v = *reinterpret_cast<const float4*>(p.dy + ((long long)(n * p.K + kk) * p.OH + oh0) * p.OW + q4);
+      *reinterpret_cast<float4*>(dys + kk * p.dpitch + q4) = v;
+    }
+    for (int e = tid; e < xtile; e += nthr) {
+      const int j = e % p.xpitch, t = e / p.xpitch;
+      const int rr = t % p.xrows, c = t / p.xrows;
+      const int ih = oh0 + rr - p.pad_t, iw = j - p.pad_l;
+      float v = 0.f;
+      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = p.x[((long long)(n * p.C + c) * p.H + ih) * p.W + iw];
+      xs[e] = v;
+    }
+    __syncthreads();
+    const float* drow = dys + k * p.dpitch;
+    for (int tr = 0; tr < p.TR; ++tr) {
+      for (int ow0 = 0; ow0 < p.OW; ow0 += 4) {
+        const float4 d = *reinterpret_cast<const float4*>(drow + tr * p.OW + ow0);
+#pragma unroll
+        for (int q = 0; q < RPG; ++q) {
+          if (!live[q]) continue;
+          const float* xr = xs + xoff[q] + tr * p.xpitch + ow0;
+          const float4 a = *reinterpret_cast<const float4*>(xr);
+          const float4 b = *reinterpret_cast<const float4*>(xr + 4);
+          acc[q][0] = fmaf(d.x, a.x, fmaf(d.y, a.y, fmaf(d.z, a.z, fmaf(d.w, a.w, acc[q][0]))));
+          acc[q][1] = fmaf(d.x, a.y, fmaf(d.y, a.z, fmaf(d.z, a.w, fmaf(d.w, b.x, acc[q][1]))));
+          acc[q][2] = fmaf(d.x, a.z, fmaf(d.y, a.w, fmaf(d.z, b.x, fmaf(d.w, b.y, acc[q][2]))));
+        }
+      }
+    }
+  }
+  float* out = p.ws + ((long long)blockIdx.x * p.K + k) * (p.NR * 3);
+#pragma unroll
+  for (int q = 0; q < RPG; ++q) {
+    if (!live[q]) continue;
+    const int row = g * RPG + q;
+    out[row * 3 + 0] = acc[q][0];
+    out[row * 3 + 1] = acc[q][1];
+    out[row * 3 + 2] = acc[q][2];
+  }
 }
 
 // =====================================================================================
@@ -632,6 +823,9 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
 #endif
   if (rc < 0 && (flags & NG_F_X_NHWC))
     rc = set_error("ng_conv2d_fprop: NG_F_X_NHWC given but this shape does not take the tensor-core kernel");
+  if (rc < 0 && C <= 4 && R == 3 && S == 3 && stride == 1 && OW % 4 == 0 && (y & 15u) == 0 &&
+      (long long)N * OH * OW >= 4096)
+    rc = launch_fprop_smallc(p, N, C, H, W, K, OH, OW, pad_t, pad_l);
   if (rc < 0) rc = launch_conv_gather(p, false);
   prof_end(tok);
   return rc;
@@ -731,6 +925,53 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
 #endif
   NG_REQUIRE(!(flags & (NG_F_X_NHWC | NG_F_DY_NHWC)),
              "ng_conv2d_wgrad: staged NHWC operands given but this shape does not take the tensor-core kernel");
+  const int sms_all = g_sm_count > 0 ? g_sm_count : 148;
+  {
+    // image-facing layer: direct kernel (see conv_wgrad_smallc_kernel)
+    const int NR = C * R, RPG = NR < 3 ? NR : 3, G = (NR + RPG - 1) / RPG;
+    const int px_budget = (40 * 1024 / 4) / K - 4;
+    const int TR = px_budget / OW < OH ? px_budget / OW : OH;
+    if (S == 3 && stride == 1 && NR <= 12 && K % 32 == 0 && K * G <= 1024 && K * G >= 64 && OW % 4 == 0 && TR >= 1 &&
+        (dy & 15u) == 0 && (long long)N * OH * OW >= 4096) {
+      WgradSmallP q;
+      memset(&q, 0, sizeof(q));
+      q.x = dptr<const float>(x);
+      q.dy = dptr<const float>(dy);
+      q.N = N; q.C = C; q.H = H; q.W = W; q.K = K; q.R = R; q.OH = OH; q.OW = OW;
+      q.pad_t = pad_t; q.pad_l = pad_l;
+      q.TR = TR;
+      q.row_blocks = (int)ceil_div(OH, TR);
+      q.tiles = N * q.row_blocks;
+      q.NR = NR;
+      q.xrows = TR + R - 1;
+      q.xpitch = OW + 4;
+      q.dpitch = TR * OW + 4;
+      const size_t smem = sizeof(float) * ((size_t)K * q.dpitch + (size_t)C * q.xrows * q.xpitch);
+      if (smem <= 48 * 1024) {
+        const int ctas_per_sm = (K * G <= 256) ? 3 : 1;
+        int grid = sms_all * ctas_per_sm;
+        if (grid > q.tiles) grid = q.tiles;
+        const long long out_elems = (long long)K * NR * 3;
+        float* ws = nullptr;
+        int r = pool_alloc((void**)&ws, (uint64_t)((long long)grid * out_elems) * sizeof(float));
+        if (r) return r;
+        q.ws = ws;
+        const int tok = prof_begin(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
+                                   4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
+        if (RPG == 1) NG_LAUNCH((conv_wgrad_smallc_kernel<1>), grid, K * G, smem, q);
+        else if (RPG == 2) NG_LAUNCH((conv_wgrad_smallc_kernel<2>), grid, K * G, smem, q);
+        else NG_LAUNCH((conv_wgrad_smallc_kernel<3>), grid, K * G, smem, q);
+        NG_CHECK_LAUNCH();
+        int g = (int)ceil_div(out_elems, 256);
+        NG_LAUNCH(splitk_reduce_kernel, g, 256, 0, dptr<float>(dw), (const float*)ws, grid, out_elems,
+                  (const float*)nullptr, 1, 0);
+        NG_CHECK_LAUNCH();
+        pool_free(ws);
+        prof_end(tok);
+        return 0;
+      }
+    }
+  }
   WgradP p;
   memset(&p, 0, sizeof(p));
   p.x = dptr<const float>(x);
