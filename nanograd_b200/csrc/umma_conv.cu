@@ -117,8 +117,8 @@ int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
 }
 
 // ------------------------------------------------------------------ gather kernel (fprop / dgrad)
-constexpr int G_THREADS = 192;       // TF32 mode: producer, MMA, 4 epilogue warps
-constexpr int G_THREADS_X3 = 448;    // 3xTF32 mode: + 2 groups of 4 operand-split warps
+constexpr int G_THREADS = 224;       // TF32 mode: producer, MMA, 4 epilogue warps, second producer
+constexpr int G_THREADS_X3 = 480;    // 3xTF32 mode: + 2 groups of 4 operand-split warps before the second producer
 constexpr int G_CCHUNK = 32;        // channels per pipeline stage (4 MMAs of K = 8)
 constexpr int G_MAX_STAGES = 8;
 constexpr int G_A_RING = 3;         // 3xTF32: A (hi, lo) buffers in TMEM, 64 columns each
@@ -201,8 +201,11 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
   const int total_tiles = m_tiles * p.n_tiles;
   const int k_iters = p.RS * p.c_chunks;
 
-  if (warp == 0) {
+  const int producer2 = p.x3 ? 14 : 6;   // two TMA-issuing warps alternate stages (see W_THREADS below)
+  if (warp == 0 || warp == producer2) {
     if (lane == 0) {
+      const uint32_t pid = warp == 0 ? 0u : 1u;
+      uint32_t it = 0;
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -214,13 +217,14 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
         const int col0 = tw * p.w_tile, row0 = th * p.rows_tile, img0 = ti * p.imgs_tile;
         for (int rs = 0; rs < p.RS; ++rs) {
           const int cx = col0 + p.tap_dx[rs], cy = row0 + p.tap_dy[rs];
-          for (int cc = 0; cc < p.c_chunks; ++cc) {
-            mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
-            uint8_t* sa = smem + (size_t)s * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-            tma_load_4d(sa, &p.tm_a, &full_bar[s], cc * G_CCHUNK, cx, cy, img0);
-            tma_load_3d(sa + p.stage_a_bytes, &p.tm_b, &full_bar[s], cc * G_CCHUNK, n_t * p.n_tile, rs);
-            if (blockIdx.x == 0) NG_DBG(8, (uint32_t)(rs * 256 + cc + 1));
+          for (int cc = 0; cc < p.c_chunks; ++cc, ++it) {
+            if ((it & 1u) == pid) {
+              mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
+              uint8_t* sa = smem + (size_t)s * stage_bytes;
+              mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+              tma_load_4d(sa, &p.tm_a, &full_bar[s], cc * G_CCHUNK, cx, cy, img0);
+              tma_load_3d(sa + p.stage_a_bytes, &p.tm_b, &full_bar[s], cc * G_CCHUNK, n_t * p.n_tile, rs);
+            }
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -543,9 +547,13 @@ int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int 
 // CTA = (tap group, c tile, k tile, split of the pixel range); partial sums go to a workspace
 // [split][tap][c][k] and a second pass reduces the splits in a fixed order (deterministic) and
 // writes KCRS.
-constexpr int W_THREADS = 192;
-constexpr int W_THREADS_X3 = 448;   // + 2 groups of 4 operand-split warps
-constexpr int W_A_RING = 3;         // X3: x operand (hi, lo) buffers in TMEM, 64 columns each
+// One thread needs ~200 cycles to issue a TMA box (plus ~150 for the barrier handshake) whatever the
+// box size (tools/tma_bw.cu), which caps a single producer at 8-20 B/clk/SM for the 8-16 KB boxes of
+// this kernel; issue scales linearly with the number of producer WARPS, so two warps alternate chunks.
+constexpr int W_THREADS = 224;      // producer, MMA, 4 epilogue warps, second producer
+constexpr int W_THREADS_X3 = 480;   // ... + 2 groups of 4 operand-split warps before the second producer
+constexpr int W_A_RING_MAX = 6;     // X3: x operand (hi, lo) buffers in TMEM, 64 columns each
+constexpr int W_LO_RING_MAX = 4;    // X3: dy lo-part buffers in shared memory
 constexpr int W_MAX_STAGES = 6;
 
 struct WgradUP {
@@ -559,6 +567,8 @@ struct WgradUP {
   uint32_t idesc, stage_a_bytes, stage_b_bytes, tmem_cols;
   int stages;
   int x3;
+  int a_ring, lo_ring;   // X3 ring depths (TMEM x buffers, shared-memory dy-lo buffers)
+  int exp_flags;         // experiments (NG_UMMA_EXP): 1 skip x split loads, 2 skip MMAs, 4 skip TMEM stores, 16 skip dy split, 32 skip promotion
   uint32_t* dbg;
 };
 
@@ -577,15 +587,15 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
-  // X3: the x operand (hi, lo) goes to TMEM (ring of W_A_RING buffers of 64 columns, written by the
-  // split warps), only dy's lo part goes back to shared memory (ring of 2)
+  // X3: the x operand (hi, lo) goes to TMEM (ring of p.a_ring buffers of 64 columns, written by the
+  // split warps), only dy's lo part goes back to shared memory (ring of p.lo_ring)
   uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? 2u * p.stage_b_bytes : 0u));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? (uint32_t)p.lo_ring * p.stage_b_bytes : 0u));
   uint64_t* empty_bar = full_bar + W_MAX_STAGES;
   uint64_t* split_bar = empty_bar + W_MAX_STAGES;
-  uint64_t* lo_empty = split_bar + W_MAX_STAGES;   // [2]
-  uint64_t* a_empty = lo_empty + 2;                // [W_A_RING]
-  uint64_t* acc_full = a_empty + W_A_RING;         // [2]
+  uint64_t* lo_empty = split_bar + W_MAX_STAGES;   // [W_LO_RING_MAX]
+  uint64_t* a_empty = lo_empty + W_LO_RING_MAX;    // [W_A_RING_MAX]
+  uint64_t* acc_full = a_empty + W_A_RING_MAX;     // [2]
   uint64_t* acc_empty = acc_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -601,9 +611,9 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 4);
-      mbar_init(&lo_empty[b], 1);
     }
-    for (int b = 0; b < W_A_RING; ++b) mbar_init(&a_empty[b], 1);
+    for (int b = 0; b < W_LO_RING_MAX; ++b) mbar_init(&lo_empty[b], 1);
+    for (int b = 0; b < W_A_RING_MAX; ++b) mbar_init(&a_empty[b], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -633,27 +643,41 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
   const int groups_per_tap = p.Cm >> 5;
   const uint32_t tap_bytes = (uint32_t)groups_per_tap * 4096u;
 
-  if (warp == 0) {
+  constexpr int kProducer2 = X3 ? 14 : 6;
+  if (warp == 0 || warp == kProducer2) {
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int ch = chunk_begin; ch < chunk_end; ++ch) {
-        int t = ch;
-        const int cw = t % p.chunks_w; t /= p.chunks_w;
-        const int chh = t % p.chunks_h;
-        const int img = t / p.chunks_h;
+      // producer `pid` takes chunks pid, pid + 2, ...; the chunk position is stepped, not divided
+      const int pid = warp == 0 ? 0 : 1;
+      int s = pid % p.stages;
+      uint32_t ph = (uint32_t)(pid / p.stages) & 1u;
+      int t = chunk_begin + pid;
+      int cw = t % p.chunks_w; t /= p.chunks_w;
+      int chh = t % p.chunks_h;
+      int img = t / p.chunks_h;
+      int tdx[4], tdy[4];
+#pragma unroll
+      for (int tl = 0; tl < 4; ++tl) {
+        const int tap = tap0 + tl;
+        tdy[tl] = tap / p.S - p.pad_t;
+        tdx[tl] = tap % p.S - p.pad_l;
+      }
+      const uint32_t tx_bytes = (uint32_t)n_taps * tap_bytes + p.stage_b_bytes;
+      const int cg0 = c_t * groups_per_tap, ng0 = n_t * (p.n_tile >> 5);
+      for (int i = pid; i < n_chunks; i += 2) {
         const int ow0 = cw * p.w_c, oh0 = chh * p.rows_c;
         mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
         uint8_t* sa = smem + (size_t)s * stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)n_taps * tap_bytes + p.stage_b_bytes);
-        for (int tl = 0; tl < n_taps; ++tl) {
-          const int tap = tap0 + tl;
-          const int r = tap / p.S, sx = tap - r * p.S;
-          tma_load_5d(sa + (size_t)tl * tap_bytes, &p.tm_x, &full_bar[s], 0, ow0 + sx - p.pad_l, oh0 + r - p.pad_t,
-                      c_t * groups_per_tap, img);
-        }
-        tma_load_5d(sa + p.stage_a_bytes, &p.tm_dy, &full_bar[s], 0, ow0, oh0, n_t * (p.n_tile >> 5), img);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+#pragma unroll
+        for (int tl = 0; tl < 4; ++tl)
+          if (tl < n_taps)
+            tma_load_5d(sa + (size_t)tl * tap_bytes, &p.tm_x, &full_bar[s], 0, ow0 + tdx[tl], oh0 + tdy[tl], cg0, img);
+        tma_load_5d(sa + p.stage_a_bytes, &p.tm_dy, &full_bar[s], 0, ow0, oh0, ng0, img);
+        s += 2;
+        if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+        cw += 2;
+        while (cw >= p.chunks_w) { cw -= p.chunks_w; ++chh; }
+        while (chh >= p.chunks_h) { chh -= p.chunks_h; ++img; }
       }
     }
   } else if (warp == 1) {
@@ -678,12 +702,14 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
         uint32_t a_lo = smem_desc_lo(sa, 4096u), b_lo = smem_desc_lo(sa + p.stage_a_bytes, 4096u);
         if (X3) {
-          uint32_t bl_lo = smem_desc_lo(lo0 + (uint32_t)(ch & 1) * p.stage_b_bytes, 4096u);
-          const uint32_t aj = (uint32_t)ch % W_A_RING;
+          const uint32_t lj = (uint32_t)ch % (uint32_t)p.lo_ring;
+          uint32_t bl_lo = smem_desc_lo(lo0 + lj * p.stage_b_bytes, 4096u);
+          const uint32_t aj = (uint32_t)ch % (uint32_t)p.a_ring;
           uint32_t a_t = tmem_a0 + aj * 64u;   // hi: columns [0,32), lo: [32,64)
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+              if (p.exp_flags & 2) break;
               mma_tf32_ts(d_tmem, a_t + 32u, desc64(b_lo, dhi), p.idesc, accumulate);
               mma_tf32_ts(d_tmem, a_t, desc64(bl_lo, dhi), p.idesc, 1u);
               mma_tf32_ts(d_tmem, a_t, desc64(b_lo, dhi), p.idesc, 1u);
@@ -691,7 +717,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
               a_t += 8u; b_lo += 64; bl_lo += 64;   // 8 pixels: 8 TMEM columns / 1024 bytes
             }
             mma_commit(&empty_bar[s]);
-            mma_commit(&lo_empty[ch & 1]);
+            mma_commit(&lo_empty[lj]);
             mma_commit(&a_empty[aj]);
           }
         } else {
@@ -730,25 +756,28 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
       for (int ch = grp; ch < n_chunks; ch += 2) {
         const int s = ch % p.stages;
         const uint32_t ph = (uint32_t)(ch / p.stages) & 1u;
-        const uint32_t aj = (uint32_t)ch % W_A_RING;
-        mbar_wait(&a_empty[aj], (uint32_t)((((uint32_t)ch / W_A_RING) & 1u) ^ 1u), p.dbg, 0x700u + aj);
-        mbar_wait(&lo_empty[ch & 1], (uint32_t)(((ch >> 1) & 1) ^ 1), p.dbg, 0x600u + (ch & 1));
+        const uint32_t aj = (uint32_t)ch % (uint32_t)p.a_ring, lj = (uint32_t)ch % (uint32_t)p.lo_ring;
+        mbar_wait(&a_empty[aj], (uint32_t)((((uint32_t)ch / (uint32_t)p.a_ring) & 1u) ^ 1u), p.dbg, 0x700u + aj);
+        mbar_wait(&lo_empty[lj], (uint32_t)((((uint32_t)ch / (uint32_t)p.lo_ring) & 1u) ^ 1u), p.dbg, 0x600u + lj);
         mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
         tc_fence_after();
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes + col_base;
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-          float v;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa + (uint32_t)k * 128u + ((chunk32 ^ (uint32_t)(k & 3)) << 5)));
+          float v = 1.f;
+          if (!(p.exp_flags & 1))
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa + (uint32_t)k * 128u + ((chunk32 ^ (uint32_t)(k & 3)) << 5)));
           hi[k] = __float_as_uint(v);
           lo[k] = __float_as_uint(tf32_lo(v));
         }
         const uint32_t a_t = tmem_a0 + aj * 64u + lane_addr;
-        tmem_st_32x32(a_t, hi);
-        tmem_st_32x32(a_t + 32u, lo);
+        if (!(p.exp_flags & 4)) {
+          tmem_st_32x32(a_t, hi);
+          tmem_st_32x32(a_t + 32u, lo);
+        }
         split_stage_hi_lo(smem + (size_t)s * stage_bytes + p.stage_a_bytes,
-                          lo_ring + (size_t)(ch & 1) * p.stage_b_bytes, p.stage_b_bytes, t);
+                          lo_ring + (size_t)lj * p.stage_b_bytes, p.stage_b_bytes, t, p.exp_flags & 16);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -773,7 +802,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
         tc_fence_after();
 #pragma unroll
         for (int j0 = 0; j0 < W_X3_MAX_N; j0 += 32) {
-          if (j0 < p.n_tile) {
+          if (j0 < p.n_tile && !(p.exp_flags & 32)) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.n_tile + j0), r);
             tmem_ld_wait();
@@ -877,11 +906,19 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
   p.stage_a_bytes = 128u * 128u;
   p.stage_b_bytes = (uint32_t)p.n_tile * 128u;
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
-  int stages = (int)((227u * 1024u - 2048u - (x3 ? 2u * p.stage_b_bytes : 0u)) / stage_bytes);
+  p.a_ring = (512 - 2 * p.n_tile) / 64;
+  if (p.a_ring > W_A_RING_MAX) p.a_ring = W_A_RING_MAX;
+  p.lo_ring = W_LO_RING_MAX;
+  { const char* e = getenv("NG_UMMA_EXP"); p.exp_flags = e ? atoi(e) : 0; }
+  if (const char* e = getenv("NG_UMMA_WRING")) {   // experiment: "a,lo"
+    int a = 0, l = 0;
+    if (sscanf(e, "%d,%d", &a, &l) == 2 && a >= 1 && a <= p.a_ring && l >= 1 && l <= W_LO_RING_MAX) { p.a_ring = a; p.lo_ring = l; }
+  }
+  int stages = (int)((227u * 1024u - 2048u - (x3 ? (uint32_t)p.lo_ring * p.stage_b_bytes : 0u)) / stage_bytes);
   if (stages > W_MAX_STAGES) stages = W_MAX_STAGES;
   if (stages < 2) return -1;
   p.stages = stages;
-  p.tmem_cols = (uint32_t)pow2_ceil(x3 ? 2 * p.n_tile + W_A_RING * 64 : (p.n_tile < 32 ? 32 : p.n_tile));
+  p.tmem_cols = (uint32_t)pow2_ceil(x3 ? 2 * p.n_tile + p.a_ring * 64 : (p.n_tile < 32 ? 32 : p.n_tile));
 
   float *x_t = nullptr, *dy_t = nullptr, *ws = nullptr;
   if (!x_is_nhwc && pool_alloc((void**)&x_t, (uint64_t)N * C * H * W * sizeof(float))) return 1;
@@ -918,7 +955,7 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
     }
   }
   if (rc == 0) {
-    const size_t smem_bytes = (size_t)stages * stage_bytes + (x3 ? 2u * p.stage_b_bytes : 0u) + 1024 + 512;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + (x3 ? (uint32_t)p.lo_ring * p.stage_b_bytes : 0u) + 1024 + 512;
     const int grid = items * splits;
     static uint32_t* dbg_host = nullptr;
     const bool debug = getenv("NG_UMMA_DEBUG") != nullptr;
