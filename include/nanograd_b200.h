@@ -178,6 +178,9 @@ int ng_conv2d_tc_plan(int N, int C, int H, int W, int K, int R, int S, int strid
                       int flags, int* out_fprop_dgrad_wgrad);
 /* dst[n][p][c] = src[n][c][p] (p = h*W + w); rounds to TF32 when flags has NG_F_TF32. */
 int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64_t HW, int flags);
+/* The same copy for dy that also returns the bias gradient sums[c] = sum_{n,p} src[n][c][p]
+ * (Add.backward's unbroadcast of the conv bias, ops_cpu.py:12-18, module.py:476) from the one read. */
+int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t N, int64_t C, int64_t HW, int flags);
 
 /* -------------------------------------------------------------------- pooling ------ */
 /* fused replacements for Tensor._pool2d → Slice, Reshape, Max/Sum(axis=(3,5)), Mul

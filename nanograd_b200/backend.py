@@ -71,6 +71,7 @@ _PROTOTYPES = {
     "ng_conv2d_wgrad": [u64, u64, u64] + [i32] * 13,
     "ng_conv2d_tc_plan": [i32] * 11 + [POINTER(c_int)],
     "ng_conv2d_stage_nhwc": [u64, u64, i64, i64, i64, i32],
+    "ng_conv2d_stage_nhwc_sum": [u64, u64, u64, i64, i64, i64, i32],
     "ng_maxpool2d_fwd": [u64, u64, i64, i32, i32, i32, i32],
     "ng_maxpool2d_bwd": [u64, u64, u64, u64, i64, i32, i32, i32, i32],
     "ng_avgpool2d_fwd": [u64, u64, i64, i32, i32, i32, i32],

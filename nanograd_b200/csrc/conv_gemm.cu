@@ -908,6 +908,18 @@ int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64
 #endif
 }
 
+int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t N, int64_t C, int64_t HW, int flags) {
+  NG_ENSURE_INIT();
+#ifndef NG_EMU
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL && N <= 65535, "ng_conv2d_stage_nhwc_sum: bad dimensions");
+  return umma::to_nhwc_sum(dptr<float>(dst), dptr<const float>(src), dptr<float>(sums), (int)N, (int)C, (int)HW,
+                           (flags & NG_F_TF32) ? 1 : 0);
+#else
+  (void)dst; (void)src; (void)sums; (void)N; (void)C; (void)HW; (void)flags;
+  return set_error("ng_conv2d_stage_nhwc_sum: the tensor-core path does not exist in the emulation build");
+#endif
+}
+
 int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int flags) {
   NG_ENSURE_INIT();

@@ -307,6 +307,8 @@ int conv_dgrad_tf32(float* dx, const float* dy, const float* w, int N, int C, in
 int conv_wgrad_tf32(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int x3, int x_is_nhwc, int dy_is_nhwc);
 int to_nhwc(float* out, const float* in, int N, int C, int HW, int round);
+// to_nhwc plus sums[c] = sum over (n, p) of in[n][c][p] (the bias gradient when `in` is dy)
+int to_nhwc_sum(float* out, const float* in, float* sums, int N, int C, int HW, int round);
 // C[M,N] = op(A) @ op(B) (+ bias[N]) (ReLU), row-major FP32 (umma_gemm.cu)
 int gemm_tf32(float* c, const float* a, const float* b, const float* bias, long long M, long long N, long long K,
               int trans_a, int trans_b, int relu, int x3);

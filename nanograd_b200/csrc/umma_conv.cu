@@ -109,6 +109,76 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(float* __restrict__ o
   }
 }
 
+// The same staging copy for dy that also produces the bias gradient: a block walks every pixel tile
+// of one (image, 32-channel group), keeps the running channel sums in registers and writes one
+// partial per (image, channel); channel_partial_sum_kernel adds the images in a fixed order.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_sum_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                               float* __restrict__ partial, int C, int HW, int round) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32;
+  const long long img = (long long)blockIdx.y * C * HW;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int p0 = 0; p0 < HW; p0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i, p = p0 + tx;
+      const float v = (c < C && p < HW) ? in[img + (long long)c * HW + p] : 0.f;
+      tile[ty + 8 * i][tx] = v;
+      acc[i] += v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + ty + 8 * i, c = c0 + tx;
+      if (p < HW && c < C) {
+        const float v = tile[tx][ty + 8 * i];
+        out[img + (long long)p * C + c] = round ? tf32_round(v) : v;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int c = c0 + ty + 8 * i;
+    if (tx == 0 && c < C) partial[(long long)blockIdx.y * C + c] = v;
+  }
+}
+
+// sums[c] = sum_n partial[n][c]; block = 32 channels x 32 image lanes
+__global__ void __launch_bounds__(1024) channel_partial_sum_kernel(float* __restrict__ sums, const float* __restrict__ partial,
+                                                                   int N, int C) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (c < C)
+    for (int n = ty; n < N; n += 32) acc += partial[(long long)n * C + c];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += red[i][tx];
+    sums[c] = t;
+  }
+}
+
+int to_nhwc_sum(float* out, const float* in, float* sums, int N, int C, int HW, int round) {
+  float* partial = nullptr;
+  if (pool_alloc((void**)&partial, (uint64_t)N * C * sizeof(float))) return 1;
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)N);
+  NG_LAUNCH(nchw_to_nhwc_sum_kernel, grid, 256, 0, out, in, partial, C, HW, round);
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(channel_partial_sum_kernel, (int)ceil_div(C, 32), 1024, 0, sums, (const float*)partial, N, C);
+  NG_CHECK_LAUNCH();
+  pool_free(partial);
+  return 0;
+}
+
 int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
   dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N);
   NG_LAUNCH(nchw_to_nhwc_kernel, grid, 256, 0, out, in, C, HW, round);

@@ -556,15 +556,20 @@ def _tc_plan(geom, stride):
     return plan
 
 
-def _stage_nhwc(buf):
+def _stage_nhwc(buf, channel_sums=False):
     """Channels-last staging copy of an NCHW buffer for the tensor-core kernels (made once, shared
-    by the passes of one layer that read the same tensor)."""
+    by the passes of one layer that read the same tensor).  channel_sums=True also returns the
+    per-channel sums of `buf` from the same read (the bias gradient when `buf` is dy)."""
     n, c = buf.shape[0], buf.shape[1]
     hw = _numel(buf.shape[2:])
     out = DeviceBuffer(buf.shape)
-    _lib().ng_conv2d_stage_nhwc(out.ptr, buf.ptr, n, c, hw, B.math_flags())
     out.staged_flags = B.math_flags()
-    return out
+    if channel_sums and n <= 65535:
+        sums = DeviceBuffer((c,))
+        _lib().ng_conv2d_stage_nhwc_sum(out.ptr, buf.ptr, sums.ptr, n, c, hw, B.math_flags())
+        return out, sums
+    _lib().ng_conv2d_stage_nhwc(out.ptr, buf.ptr, n, c, hw, B.math_flags())
+    return (out, None) if channel_sums else out
 
 
 def _conv2d_forward(x, w, bias, stride, padding, flags=0, x_nhwc=None):
@@ -607,17 +612,22 @@ def _conv_forward_shared(ctx, input, weight, bias, stride, padding):
     return _conv2d_forward(input, weight, bias, stride, padding, x_nhwc=x_nhwc)
 
 
-def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding):
+def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding, want_db=False):
     geom = _conv_geometry(input.shape, weight.shape, stride, padding)
     f_tc, d_tc, w_tc = _tc_plan(geom, stride)
     need_dx, need_dw = _needs(ctx, 0), _needs(ctx, 1)
     x_nhwc = getattr(ctx, "conv_nhwc", None)
     if x_nhwc is not None and (not w_tc or getattr(x_nhwc, "staged_flags", None) != B.math_flags()):
         x_nhwc = None  # math mode changed between forward and backward: restage inside the call
-    dy_nhwc = _stage_nhwc(grad_output) if (need_dx and need_dw and d_tc and w_tc) else None
+    dy_nhwc = db = None
+    if need_dx and need_dw and d_tc and w_tc:
+        # one staging pass of dy serves dgrad and wgrad, and the bias gradient rides on its read
+        dy_nhwc, db = _stage_nhwc(grad_output, channel_sums=True) if want_db else (_stage_nhwc(grad_output), None)
     dx = _conv2d_dgrad(grad_output, weight, input.shape, stride, padding, dy_nhwc=dy_nhwc) if need_dx else None
     dw = _conv2d_wgrad(grad_output, input, weight.shape, stride, padding, x_nhwc=x_nhwc, dy_nhwc=dy_nhwc) \
         if need_dw else None
+    if want_db:
+        return dx, dw, (db if db is not None else _channel_sum(grad_output))
     return dx, dw
 
 
@@ -690,9 +700,10 @@ class Conv2dBias(Function):
     @staticmethod
     def backward(ctx, grad_output):
         input, weight, stride, padding = ctx.saved_tensors
+        if _needs(ctx, 2):
+            return _conv_backward_shared(ctx, grad_output, input, weight, stride, padding, want_db=True)
         dx, dw = _conv_backward_shared(ctx, grad_output, input, weight, stride, padding)
-        db = _channel_sum(grad_output) if _needs(ctx, 2) else None
-        return dx, dw, db
+        return dx, dw, None
 
 
 class Conv1dBias(Function):

@@ -76,3 +76,22 @@ def test_tensor_core_gemm_matches_simt(mnk, mode, rtol):
             lib.ng_gemm(ref.ptr, ad.ptr, bd.ptr, M, N, K, ta, tb, 1, biasd.ptr, B.F_RELU)
             lib.ng_gemm(got.ptr, ad.ptr, bd.ptr, M, N, K, ta, tb, 1, biasd.ptr, B.F_RELU | flag)
             H.assert_close(got.numpy(), ref.numpy(), rtol, f"gemm {mode} {mnk} ta={ta} tb={tb}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nchw", [(3, 40, 5, 10), (16, 64, 32, 32), (5, 33, 1, 37), (70, 256, 8, 8)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_stage_nhwc_with_channel_sums(nchw):
+    """ng_conv2d_stage_nhwc_sum: the channels-last staging copy of dy (bit-exact transpose) and the
+    bias gradient from the same read (Add.backward's unbroadcast, ops_cpu.py:12-18), ragged tiles."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    H.use_cuda_library()
+    lib = B.lib()
+    n, c, h, w = nchw
+    rng = np.random.RandomState(n + c)
+    a = rng.randn(n, c, h, w).astype(np.float32)
+    src, dst, sums = DeviceBuffer(a.shape, hostbuf=a), DeviceBuffer(a.shape), DeviceBuffer((c,))
+    lib.ng_conv2d_stage_nhwc_sum(dst.ptr, src.ptr, sums.ptr, n, c, h * w, 0)
+    H.assert_exact(dst.numpy().reshape(n, h * w, c), a.reshape(n, c, h * w).transpose(0, 2, 1), "staged copy")
+    H.assert_close(sums.numpy(), a.astype(np.float64).sum(axis=(0, 2, 3)), H.RTOL_FP32, "channel sums")
