@@ -112,6 +112,16 @@ int ng_binary(int op, uint64_t out, uint64_t a, uint64_t b, int ndim,
  * tensor.py:482-483; here the value rides in the launch arguments).  scalar_is_lhs selects
  * f(s, a) instead of f(a, s). */
 int ng_binary_scalar(int op, uint64_t out, uint64_t a, float s, int scalar_is_lhs, int64_t n);
+/* Fused activations the reference composes from primitives:
+ *   NG_ACT_LEAKY_RELU  relu(x) - alpha*relu(-x)          nn.LeakyReLU, module.py:744-772 (param = alpha)
+ *   NG_ACT_MISH        x * tanh(log(1 + exp(x)))         nn.Mish,      module.py:844-864
+ *   NG_ACT_SWISH       x * sigmoid(beta*x)               nn.Swish,     module.py:818-841 (param = beta)
+ * param_ptr (device, 1 float) overrides the immediate `param` when non-zero.  ng_act_bwd writes
+ * dx = dy * act'(x); ng_swish_dbeta writes the learnt beta's gradient sum(dy * x^2 * s(1-s)). */
+enum { NG_ACT_LEAKY_RELU = 0, NG_ACT_MISH = 1, NG_ACT_SWISH = 2 };
+int ng_act_fwd(int kind, uint64_t y, uint64_t x, uint64_t param_ptr, float param, int64_t n);
+int ng_act_bwd(int kind, uint64_t dx, uint64_t dy, uint64_t x, uint64_t param_ptr, float param, int64_t n);
+int ng_swish_dbeta(uint64_t dbeta1, uint64_t dy, uint64_t x, uint64_t beta_ptr, int64_t n);
 int ng_fill(uint64_t out, float value, int64_t n);
 /* out[i] += a[i]  (gradient accumulation, tensor.py:243) */
 int ng_accumulate(uint64_t out, uint64_t a, int64_t n);
@@ -199,6 +209,10 @@ int ng_logsoftmax_bwd(uint64_t dx, uint64_t dy, uint64_t logp, int64_t rows, int
 /* fused NLLLoss.forward = -(logp * onehot(labels)).mean() over rows*cols (module.py:684-686) */
 int ng_nll_fwd(uint64_t loss1, uint64_t logp, uint64_t labels, int64_t rows, int64_t cols);
 int ng_nll_bwd(uint64_t dlogp, uint64_t dloss1, uint64_t labels, int64_t rows, int64_t cols);
+/* nn.MSELoss fused: loss1[0] = mean((pred - target)^2) (module.py:689-712; deterministic two-pass sum);
+ * ng_mse_bwd writes dloss * 2 (pred - target) / n, negated when for_target != 0. */
+int ng_mse_fwd(uint64_t loss1, uint64_t pred, uint64_t target, int64_t n);
+int ng_mse_bwd(uint64_t d, uint64_t dloss1, uint64_t pred, uint64_t target, int64_t n, int for_target);
 
 /* device-side accuracy (replaces the per-step D2H of the logits + host argmax, tests/helpers.py:310-313):
  * out[r] = first argmax of row r as float32 ; out1[0] = #{i : a[i] == b[i]} */

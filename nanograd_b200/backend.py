@@ -80,6 +80,11 @@ _PROTOTYPES = {
     "ng_logsoftmax_bwd": [u64, u64, u64, i64, i64],
     "ng_nll_fwd": [u64, u64, u64, i64, i64],
     "ng_nll_bwd": [u64, u64, u64, i64, i64],
+    "ng_mse_fwd": [u64, u64, u64, i64],
+    "ng_mse_bwd": [u64, u64, u64, u64, i64, i32],
+    "ng_act_fwd": [i32, u64, u64, u64, f32, i64],
+    "ng_act_bwd": [i32, u64, u64, u64, u64, f32, i64],
+    "ng_swish_dbeta": [u64, u64, u64, u64, i64],
     "ng_bn2d_fwd_train": [u64] * 8 + [i64, i64, i64, f32, f32],
     "ng_bn2d_fwd_eval": [u64] * 6 + [i64, i64, i64, f32],
     "ng_bn2d_bwd": [u64] * 8 + [i64, i64, i64],
@@ -100,6 +105,7 @@ EXPORTED_SYMBOLS = sorted(list(_PROTOTYPES) + ["ng_last_error"])
 
 # op codes (mirrors the enums of include/nanograd_b200.h)
 U_COPY, U_NEG, U_EXP, U_LOG, U_RELU, U_SIGMOID, U_TANH, U_SQRT, U_RECIP = range(9)
+ACT_LEAKY_RELU, ACT_MISH, ACT_SWISH = range(3)
 (B_ADD, B_MUL, B_POW, B_DIV, B_SUB, B_EQ, B_RELU_BWD, B_EXP_BWD, B_LOG_BWD, B_SIGMOID_BWD,
  B_TANH_BWD, B_POW_DBASE, B_POW_DEXP) = range(13)
 R_SUM, R_MAX, R_MIN = range(3)

@@ -171,6 +171,73 @@ __global__ void __launch_bounds__(256) accumulate_kernel(float* out, const float
   }
 }
 
+// ---- fused activations: the reference composes them from primitives --------
+//   LeakyReLU  relu(x) - alpha * relu(-x)        module.py:744-772   (3 nodes fwd, 1 + alpha at x = 0 bwd)
+//   Mish       x * tanh(log(1 + exp(x)))         module.py:844-864   (6 nodes fwd)
+//   Swish      x * sigmoid(beta * x), learnt beta module.py:818-841   (3 nodes fwd; dbeta is a full reduction)
+// `pptr` (device, 1 float) overrides the immediate parameter when non-null (Swish's beta lives on the device).
+template <int KIND>
+__device__ __forceinline__ float act_f(float x, float p) {
+  if (KIND == NG_ACT_LEAKY_RELU) return fmaxf(x, 0.f) - p * fmaxf(-x, 0.f);
+  if (KIND == NG_ACT_MISH) return x * tanhf(logf(1.f + expf(x)));
+  return x / (1.f + expf(-p * x));  // NG_ACT_SWISH
+}
+// d act / dx
+template <int KIND>
+__device__ __forceinline__ float act_df(float x, float p) {
+  if (KIND == NG_ACT_LEAKY_RELU) return ((x >= 0.f) ? 1.f : 0.f) + ((x <= 0.f) ? p : 0.f);  // ReLU'(0) = 1 on both branches
+  if (KIND == NG_ACT_MISH) {
+    const float t = tanhf(logf(1.f + expf(x)));
+    const float sg = 1.f / (1.f + expf(-x));   // d softplus / dx
+    return t + x * (1.f - t * t) * sg;
+  }
+  const float sg = 1.f / (1.f + expf(-p * x));
+  return sg + x * p * sg * (1.f - sg);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) act_fwd_kernel(float* __restrict__ y, const float* __restrict__ x,
+                                                      const float* __restrict__ pptr, float pimm, int64_t n) {
+  const float p = pptr ? pptr[0] : pimm;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = act_f<KIND>(x[i], p);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) act_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy,
+                                                      const float* __restrict__ x, const float* __restrict__ pptr,
+                                                      float pimm, int64_t n) {
+  const float p = pptr ? pptr[0] : pimm;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * act_df<KIND>(x[i], p);
+}
+
+// Swish: partial[b] = sum over the block's elements of dy * x^2 * s(1 - s), s = sigmoid(beta x)
+__global__ void __launch_bounds__(256) swish_dbeta_kernel(float* __restrict__ partial, const float* __restrict__ dy,
+                                                          const float* __restrict__ x, const float* __restrict__ beta,
+                                                          int64_t n) {
+  __shared__ float scratch[32];
+  const float b = beta[0];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    const float sg = 1.f / (1.f + expf(-b * xv));
+    acc += dy[i] * xv * xv * sg * (1.f - sg);
+  }
+  const float t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// out[0] = scale * sum_i partial[i] (one block, fixed order)
+__global__ void __launch_bounds__(256) sum_partials_kernel(float* __restrict__ out, const float* __restrict__ partial,
+                                                           int m, float scale) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) acc += partial[i];
+  const float t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) out[0] = t * scale;
+}
+
 static inline int ew_grid(int64_t work_items) {
   // enough CTAs for >= 2 waves at 8 resident CTAs/SM, never more than the work needs
   int64_t want = ceil_div(work_items, 256);
@@ -290,6 +357,50 @@ int ng_binary_scalar(int op, uint64_t out, uint64_t a, float s, int scalar_is_lh
       return set_error("ng_binary_scalar: unknown op %d", op);
   }
   NG_CHECK_LAUNCH();
+  return 0;
+}
+
+#define NG_ACT_SWITCH(kind, STMT)                                         \
+  switch (kind) {                                                        \
+    case NG_ACT_LEAKY_RELU: { constexpr int KK = NG_ACT_LEAKY_RELU; STMT; break; } \
+    case NG_ACT_MISH: { constexpr int KK = NG_ACT_MISH; STMT; break; }   \
+    case NG_ACT_SWISH: { constexpr int KK = NG_ACT_SWISH; STMT; break; } \
+    default: return set_error("ng_act: unknown activation %d", kind);    \
+  }
+
+int ng_act_fwd(int kind, uint64_t y, uint64_t x, uint64_t param_ptr, float param, int64_t n) {
+  NG_ENSURE_INIT();
+  if (n <= 0) return 0;
+  const float* pp = param_ptr ? dptr<const float>(param_ptr) : nullptr;
+  NG_ACT_SWITCH(kind, NG_LAUNCH((act_fwd_kernel<KK>), ew_grid(n), 256, 0, dptr<float>(y), dptr<const float>(x), pp, param, n));
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_act_bwd(int kind, uint64_t dx, uint64_t dy, uint64_t x, uint64_t param_ptr, float param, int64_t n) {
+  NG_ENSURE_INIT();
+  if (n <= 0) return 0;
+  const float* pp = param_ptr ? dptr<const float>(param_ptr) : nullptr;
+  NG_ACT_SWITCH(kind, NG_LAUNCH((act_bwd_kernel<KK>), ew_grid(n), 256, 0, dptr<float>(dx), dptr<const float>(dy),
+                                dptr<const float>(x), pp, param, n));
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_swish_dbeta(uint64_t dbeta1, uint64_t dy, uint64_t x, uint64_t beta_ptr, int64_t n) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(beta_ptr != 0, "ng_swish_dbeta: beta must be a device pointer");
+  int blocks = ew_grid(n > 0 ? n : 1);
+  if (blocks > 1024) blocks = 1024;
+  float* partial = nullptr;
+  int r = pool_alloc((void**)&partial, (uint64_t)blocks * sizeof(float));
+  if (r) return r;
+  NG_LAUNCH(swish_dbeta_kernel, blocks, 256, 0, partial, dptr<const float>(dy), dptr<const float>(x),
+            dptr<const float>(beta_ptr), n);
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(sum_partials_kernel, 1, 256, 0, dptr<float>(dbeta1), (const float*)partial, blocks, 1.f);
+  NG_CHECK_LAUNCH();
+  pool_free(partial);
   return 0;
 }
 

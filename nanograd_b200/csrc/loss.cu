@@ -73,6 +73,37 @@ __global__ void __launch_bounds__(256) nll_bwd_kernel(float* __restrict__ dlogp,
   }
 }
 
+// ---- MSELoss fused: ((p - t)^2).mean()  (module.py:689-712: Add, Neg, Pow, Sum, Mul nodes) --------------
+__global__ void __launch_bounds__(256) mse_partial_kernel(float* __restrict__ partial, const float* __restrict__ p,
+                                                          const float* __restrict__ t, int64_t n) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = p[i] - t[i];
+    acc += d * d;
+  }
+  const float s = block_sum(acc, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) mse_finish_kernel(float* __restrict__ loss, const float* __restrict__ partial, int m,
+                                                         float inv_n) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) acc += partial[i];
+  const float s = block_sum(acc, scratch);
+  if (threadIdx.x == 0) loss[0] = s * inv_n;
+}
+
+// d = sign * dloss * 2 (p - t) / n   (sign = +1 for the prediction, -1 for the target)
+__global__ void __launch_bounds__(256) mse_bwd_kernel(float* __restrict__ d, const float* __restrict__ dloss,
+                                                      const float* __restrict__ p, const float* __restrict__ t, int64_t n,
+                                                      float sign) {
+  const float g = sign * dloss[0] * 2.f / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = g * (p[i] - t[i]);
+}
+
 static inline int row_grid(int64_t rows) {
   int64_t g = ceil_div(rows, 8);  // 8 warps per block
   const int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 8;
@@ -148,6 +179,35 @@ int ng_nll_bwd(uint64_t dlogp, uint64_t dloss1, uint64_t labels, int64_t rows, i
   if (g > cap) g = cap;
   NG_LAUNCH(nll_bwd_kernel, (int)g, 256, 0, dptr<float>(dlogp), dptr<const float>(dloss1),
             dptr<const float>(labels), rows, cols);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_mse_fwd(uint64_t loss1, uint64_t pred, uint64_t target, int64_t n) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(n > 0, "ng_mse_fwd: empty input");
+  int64_t blocks = ceil_div(n, 1024);
+  const int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 4;
+  if (blocks > cap) blocks = cap;
+  float* partial = nullptr;
+  int r = pool_alloc((void**)&partial, (uint64_t)blocks * sizeof(float));
+  if (r) return r;
+  NG_LAUNCH(mse_partial_kernel, (int)blocks, 256, 0, partial, dptr<const float>(pred), dptr<const float>(target), n);
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(mse_finish_kernel, 1, 256, 0, dptr<float>(loss1), (const float*)partial, (int)blocks, 1.f / (float)n);
+  NG_CHECK_LAUNCH();
+  pool_free(partial);
+  return 0;
+}
+
+int ng_mse_bwd(uint64_t d, uint64_t dloss1, uint64_t pred, uint64_t target, int64_t n, int for_target) {
+  NG_ENSURE_INIT();
+  if (n <= 0) return 0;
+  int64_t g = ceil_div(n, 256);
+  const int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 16;
+  if (g > cap) g = cap;
+  NG_LAUNCH(mse_bwd_kernel, (int)g, 256, 0, dptr<float>(d), dptr<const float>(dloss1), dptr<const float>(pred),
+            dptr<const float>(target), n, for_target ? -1.f : 1.f);
   NG_CHECK_LAUNCH();
   return 0;
 }

@@ -440,6 +440,8 @@ class MSELoss(Module):
         pass
 
     def forward(self, predicted: Tensor, target: Tensor) -> Tensor:
+        if _fused(predicted, 'mseloss') and predicted.shape == target.shape:
+            return predicted.mseloss(target)
         return ((predicted - target) ** 2).mean()
 
     __call__ = forward
@@ -462,8 +464,11 @@ class LeakyReLU(Module):
     def __init__(self, alpha=0.01) -> None:
         super().__init__()
         self.alpha = Tensor(alpha, is_parameter=False, name='alpha_relu')
+        self._alpha_value = float(alpha)
 
     def forward(self, x: Tensor) -> Tensor:
+        if _fused(x, 'leakyrelu'):
+            return x.leakyrelu(alpha=self._alpha_value)
         return x.relu() - self.alpha * (-x).relu()
 
 
@@ -495,6 +500,8 @@ class Swish(Module):
         self.beta = Tensor(beta, requires_grad=True, is_parameter=True, name='swish_beta')
 
     def forward(self, x: Tensor) -> Tensor:
+        if _fused(x, 'swish') and self.beta.device == x.device:
+            return x.swish(self.beta)
         return x * (self.beta * x).sigmoid()
 
 
@@ -505,4 +512,6 @@ class Mish(Module):
         super().__init__()
 
     def forward(self, x: Tensor) -> Tensor:
+        if _fused(x, 'mish'):
+            return x.mish()
         return x * (1 + x.exp()).log().tanh()

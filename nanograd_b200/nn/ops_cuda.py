@@ -42,8 +42,13 @@ def _numel(shape):
 
 
 def _needs(ctx, i):
-    """Does parent ``i`` need a gradient?"""
-    return i < len(ctx.parents) and ctx.parents[i].requires_grad
+    """Does parent ``i`` need a gradient?  The reference computes every parent's gradient
+    (tensor.py:236-243); here only tensors that ask for one — or are flagged is_parameter, like
+    Dropout's mask (module.py:650-652), whose .grad the reference's users can read — get one."""
+    if i >= len(ctx.parents):
+        return False
+    p = ctx.parents[i]
+    return bool(p.requires_grad or getattr(p, "is_parameter", False))
 
 
 def _unary(op, a):
@@ -847,6 +852,95 @@ class NLLLoss(Function):
         dlogp = DeviceBuffer((rows, cols))
         _lib().ng_nll_bwd(dlogp.ptr, grad_output.ptr, target.ptr, rows, cols)
         return dlogp, None
+
+
+class MSELoss(Function):
+    """nn.MSELoss.forward fused: ((predicted - target) ** 2).mean() (module.py:689-712).
+    Result has shape (1,) like Sum(axis=None)."""
+
+    @staticmethod
+    def forward(ctx, predicted, target):
+        if tuple(predicted.shape) != tuple(target.shape):
+            raise Exception(f"MSELoss: shapes {predicted.shape} and {target.shape} differ")
+        out = DeviceBuffer((1,))
+        _lib().ng_mse_fwd(out.ptr, predicted.ptr, target.ptr, predicted.size)
+        ctx.save_for_backward(predicted, target)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        predicted, target = ctx.saved_tensors
+        grads = []
+        for i in range(2):
+            if not _needs(ctx, i):
+                grads.append(None)
+                continue
+            d = DeviceBuffer(predicted.shape)
+            _lib().ng_mse_bwd(d.ptr, grad_output.ptr, predicted.ptr, target.ptr, predicted.size, i)
+            grads.append(d)
+        return tuple(grads)
+
+
+def _act_forward(kind, x, param_ptr=0, param=0.0):
+    out = DeviceBuffer(x.shape)
+    _lib().ng_act_fwd(kind, out.ptr, x.ptr, param_ptr, float(param), x.size)
+    return out
+
+
+def _act_backward(kind, grad, x, param_ptr=0, param=0.0):
+    dx = DeviceBuffer(x.shape)
+    _lib().ng_act_bwd(kind, dx.ptr, grad.ptr, x.ptr, param_ptr, float(param), x.size)
+    return dx
+
+
+class LeakyReLU(Function):
+    """nn.LeakyReLU.forward fused: relu(x) - alpha * relu(-x) (module.py:744-772); the gradient at
+    x = 0 is 1 + alpha, as the composition of two ReLU.backward's gives (ops_cpu.py:263)."""
+
+    @staticmethod
+    def forward(ctx, input, alpha=0.01):
+        ctx.save_for_backward(input, float(alpha))
+        return _act_forward(B.ACT_LEAKY_RELU, input, param=alpha)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, alpha = ctx.saved_tensors
+        return _act_backward(B.ACT_LEAKY_RELU, grad_output, input, param=alpha)
+
+
+class Mish(Function):
+    """nn.Mish.forward fused: x * tanh(log(1 + exp(x))) (module.py:844-864)."""
+
+    @staticmethod
+    def forward(ctx, input):
+        ctx.save_for_backward(input)
+        return _act_forward(B.ACT_MISH, input)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return _act_backward(B.ACT_MISH, grad_output, ctx.saved_tensors[0])
+
+
+class Swish(Function):
+    """nn.Swish.forward fused: x * sigmoid(beta * x) with the learnt scalar beta read on the device
+    (module.py:818-841); backward returns (dx, dbeta) with dbeta shaped like beta."""
+
+    @staticmethod
+    def forward(ctx, input, beta):
+        if beta.size != 1:
+            raise Exception(f"Swish: beta must hold one value, got shape {beta.shape}")
+        ctx.save_for_backward(input, beta)
+        return _act_forward(B.ACT_SWISH, input, param_ptr=beta.ptr)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, beta = ctx.saved_tensors
+        dx = _act_backward(B.ACT_SWISH, grad_output, input, param_ptr=beta.ptr) if _needs(ctx, 0) else None
+        dbeta = None
+        if _needs(ctx, 1):
+            dbeta = DeviceBuffer(tuple(beta.shape))
+            _lib().ng_swish_dbeta(dbeta.ptr, grad_output.ptr, input.ptr, beta.ptr, input.size)
+        return dx, dbeta
 
 
 class BatchNorm2d(Function):

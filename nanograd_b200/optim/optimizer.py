@@ -50,6 +50,15 @@ class Optimizer:
             tables.append(B.u64_array([states[i].data.ptr for i in active]))
         return len(params), tables, B.i64_array(numels), grad_scale
 
+    def _mirror_scalar_shapes(self):
+        """A 0-d parameter (Swish's beta) comes out of the reference's update with shape (1,): the
+        update multiplies by a Python scalar, which dispatch wraps in a 1-element tensor
+        (tensor.py:482-483), and () broadcasts to (1,).  The in-place kernels keep the storage, so
+        only the logical shape is adjusted."""
+        for p in self.params:
+            if p.grad is not None and tuple(p.data.shape) == ():
+                p.data.shape = (1,)
+
     def _reduced_grad_ptrs(self, params, numels):
         """Data parallel: pack -> one allreduce(sum) -> kernels read the bucket, scaled by 1/world."""
         from nanograd_b200 import dist
@@ -84,6 +93,7 @@ class SGD(Optimizer):
             n, (p, g, m), numels, scale = self._device_tables(self.momentums)
             if n:
                 B.lib().ng_multi_sgd(n, p, g, m, numels, float(self.lr), float(self.momentum), float(scale))
+            self._mirror_scalar_shapes()
             return
         for i, p in enumerate(self.params):
             self.momentums[i] = self.momentums[i] * self.momentum + self.lr * p.grad
@@ -111,6 +121,7 @@ class Adam(Optimizer):
                 B.lib().ng_multi_adam(n, p, g, m, v, numels, float(self.lr), float(self.beta1), float(self.beta2),
                                       float(self.eps), float(1. - self.beta1 ** self.t),
                                       float(1. - self.beta2 ** self.t), 0.0, 0, float(scale))
+            self._mirror_scalar_shapes()
             return
         for i, p in enumerate(self.params):
             self.exp_avg[i] = self.beta1 * self.exp_avg[i] + (1. - self.beta1) * p.grad
@@ -144,6 +155,7 @@ class AdamW(Optimizer):
                 B.lib().ng_multi_adam(n, p, g, m, v, numels, float(self.lr), float(self.beta1), float(self.beta2),
                                       float(self.eps), float(bias_correction1), float(bias_correction2),
                                       float(self.weight_decay), 1, float(scale))
+            self._mirror_scalar_shapes()
             return
         for i, p in enumerate(self.params):
             self.exp_avg[i] = self.beta1 * self.exp_avg[i] + (1. - self.beta1) * p.grad

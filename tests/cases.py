@@ -352,6 +352,19 @@ def case_linear_stack(fw, seed=0):
     return rec
 
 
+def case_activation_mlp(fw, opt_name="sgdm", batch=24, steps=2, seed=0):
+    """SURVEY §8-f row 2 layers in one net: LeakyReLU (module.py:744-772), Swish with its learnt beta
+    (:818-841), Mish (:844-864), Dropout (mask sampled once, :627-659), MSELoss (:689-712)."""
+    nn = fw.nn
+    np.random.seed(seed)
+    model = nn.Sequential(nn.Linear(20, 32), nn.LeakyReLU(0.1), nn.Linear(32, 32), nn.Swish(), nn.Dropout(0.3),
+                          nn.Linear(32, 16), nn.Mish())
+    X = np.random.randn(batch, 20).astype(np.float32) * 2
+    T = np.random.randn(batch, 16).astype(np.float32)
+    model.train()
+    return _train(fw, model, opt_name, X, T, steps, nn.MSELoss())
+
+
 def all_cases():
     """name -> (function, kwargs).  Names double as golden file names."""
     cases = {}
@@ -388,6 +401,8 @@ def all_cases():
     for o in ("sgd", "sgdm", "adam", "adamw1", "adamw2", "adamw3"):
         cases[f"tinynet_{o}"] = (case_tinynet_step, dict(opt_name=o))
     cases["linear_stack"] = (case_linear_stack, {})
+    cases["activation_mlp_sgdm"] = (case_activation_mlp, dict(opt_name="sgdm"))
+    cases["activation_mlp_adam"] = (case_activation_mlp, dict(opt_name="adam"))
     return cases
 
 
