@@ -960,7 +960,12 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
       q.dpitch = TR * OW + 4;
       const size_t smem = sizeof(float) * ((size_t)K * q.dpitch + (size_t)C * q.xrows * q.xpitch);
       if (smem <= 48 * 1024) {
-        const int ctas_per_sm = (K * G <= 256) ? 3 : 1;
+        // load and compute phases alternate inside a CTA, so several CTAs per SM overlap them:
+        // as many as shared memory (<= 48 KB each) and 2048 threads allow, at most 5
+        int ctas_per_sm = (int)((220u * 1024u) / (smem + 1024u));
+        if (ctas_per_sm > 2048 / (K * G)) ctas_per_sm = 2048 / (K * G);
+        if (ctas_per_sm > 5) ctas_per_sm = 5;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
         int grid = sms_all * ctas_per_sm;
         if (grid > q.tiles) grid = q.tiles;
         const long long out_elems = (long long)K * NR * 3;
