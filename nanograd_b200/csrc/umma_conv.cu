@@ -191,7 +191,12 @@ constexpr int G_THREADS = 224;       // TF32 mode: producer, MMA, 4 epilogue war
 constexpr int G_THREADS_X3 = 480;    // 3xTF32 mode: + 2 groups of 4 operand-split warps before the second producer
 constexpr int G_CCHUNK = 32;        // channels per pipeline stage (4 MMAs of K = 8)
 constexpr int G_MAX_STAGES = 8;
-constexpr int G_A_RING = 3;         // 3xTF32: A (hi, lo) buffers in TMEM, 64 columns each
+// Ring depths of the 3xTF32 hand-off.  The chain MMA commit -> slot free -> split warps -> MMA issue is
+// longer than one stage of MMAs, so two lo buffers / three A buffers left the tensor pipe idle between
+// stages: four of each (all 512 TMEM columns at n_tile = 128) measured 6-7 % faster, six lo buffers slower
+// again (they cost a TMA stage).
+constexpr unsigned G_LO_RING = 4;   // 3xTF32: B lo-part buffers in shared memory
+constexpr int G_A_RING = 4;         // 3xTF32: A (hi, lo) buffers in TMEM, 64 columns each
 
 struct GatherP {
   CUtensorMap tm_a;  // activations NHWC, dims (C, W, H, N)
@@ -223,18 +228,18 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // Shared memory: `stages` operand sets (A tile + B tile) filled by TMA, then — 3xTF32 mode only — a
-  // ring of 2 "lo" sets.  A lo set lives only from the split to the end of its MMAs, an operand set
+  // ring of G_LO_RING "lo" sets.  A lo set lives only from the split to the end of its MMAs, an operand set
   // from the TMA issue on, so most of the capacity stays available for loads in flight.
   // 3xTF32 mode: the split warps move the A tile into TMEM (hi and lo, G_A_RING buffers of 64 columns)
-  // and write only B's lo part back to shared memory (ring of 2), so the MMAs read just B from shared
+  // and write only B's lo part back to shared memory (ring of G_LO_RING), so the MMAs read just B from shared
   // memory: 32 KB of shared-memory traffic per K step of a 128x128 tile instead of 48 KB.
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
   uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;   // x3: 2 x stage_b_bytes (B lo)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (p.x3 ? 2u * p.stage_b_bytes : 0u));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (p.x3 ? G_LO_RING * p.stage_b_bytes : 0u));
   uint64_t* empty_bar = full_bar + G_MAX_STAGES;
   uint64_t* split_bar = empty_bar + G_MAX_STAGES;
-  uint64_t* lo_empty = split_bar + G_MAX_STAGES;   // [2]
-  uint64_t* a_empty = lo_empty + 2;                // [G_A_RING]
+  uint64_t* lo_empty = split_bar + G_MAX_STAGES;   // [G_LO_RING]
+  uint64_t* a_empty = lo_empty + G_LO_RING;        // [G_A_RING]
   uint64_t* tmem_full = a_empty + G_A_RING;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       mbar_init(&lo_empty[s], 1);
     }
     for (int s = 0; s < G_A_RING; ++s) mbar_init(&a_empty[s], 1);
+    for (int s = 2; s < (int)G_LO_RING; ++s) mbar_init(&lo_empty[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
         uint32_t a_lo = smem_desc_lo(sa, 16u), b_lo = smem_desc_lo(sa + p.stage_a_bytes, 16u);
         if (p.x3) {
-          uint32_t bl_lo = smem_desc_lo(lo0 + (lo_i & 1u) * p.stage_b_bytes, 16u);
+          uint32_t bl_lo = smem_desc_lo(lo0 + (lo_i % G_LO_RING) * p.stage_b_bytes, 16u);
           const uint32_t aj = lo_i % G_A_RING;
           uint32_t a_t = tmem_a0 + aj * 64u;   // hi: columns [0,32), lo: [32,64) of the A buffer
           if (elect_one()) {
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
               a_t += 8u; b_lo += 2; bl_lo += 2;   // 8 TMEM columns / 32 bytes along K
             }
             mma_commit(&empty_bar[s]);
-            mma_commit(&lo_empty[lo_i & 1u]);
+            mma_commit(&lo_empty[lo_i % G_LO_RING]);
             mma_commit(&a_empty[aj]);
           }
         } else {
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       const uint32_t ph = (lo_i / (uint32_t)p.stages) & 1u;
       const uint32_t aj = lo_i % G_A_RING;
       mbar_wait(&a_empty[aj], ((lo_i / G_A_RING) & 1u) ^ 1u, p.dbg, 0x700u + aj);
-      mbar_wait(&lo_empty[lo_i & 1u], ((lo_i >> 1) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i & 1u));
+      mbar_wait(&lo_empty[lo_i % G_LO_RING], ((lo_i / G_LO_RING) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i % G_LO_RING));
       mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
       tc_fence_after();
       if (!(p.exp_flags & 1)) {
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
         tmem_st_32x32(a_t + 32u, lo);
         // B: lo part to the shared-memory ring
         split_stage_hi_lo(smem + (size_t)s * stage_bytes + p.stage_a_bytes,
-                          lo_ring + (size_t)(lo_i & 1u) * p.stage_b_bytes, p.stage_b_bytes, t, p.exp_flags);
+                          lo_ring + (size_t)(lo_i % G_LO_RING) * p.stage_b_bytes, p.stage_b_bytes, t, p.exp_flags);
         tmem_st_wait();
       }
       tc_fence_before();
@@ -509,11 +515,11 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
   const uint32_t budget = 227u * 1024u - 2048u;
   // x3: two B-lo sets share the capacity
-  int stages = (int)((budget - (x3 ? 2u * p.stage_b_bytes : 0u)) / stage_bytes);
+  int stages = (int)((budget - (x3 ? G_LO_RING * p.stage_b_bytes : 0u)) / stage_bytes);
   if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
   if (stages < 2) return -1;
   p.stages = stages;
-  // TMEM: two accumulators (+ the A ring in x3 mode: 2*128 + 3*64 = 448 <= 512 columns)
+  // TMEM: two accumulators (+ the A ring in x3 mode: 2*128 + 4*64 = 512 columns)
   p.tmem_cols = (uint32_t)pow2_ceil(2 * n_tile + (x3 ? G_A_RING * 64 : 0) < 32 ? 32 : 2 * n_tile + (x3 ? G_A_RING * 64 : 0));
   p.relu = relu;
   { const char* e = getenv("NG_UMMA_EXP"); p.exp_flags = e ? atoi(e) : 0; }
@@ -553,7 +559,7 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
     }
   }
   if (rc == 0) {
-    const size_t smem_bytes = (size_t)stages * stage_bytes + (x3 ? 2u * p.stage_b_bytes : 0u) + 1024 + 512;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + (x3 ? G_LO_RING * p.stage_b_bytes : 0u) + 1024 + 512;
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_img * p.n_tiles;
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int grid = total_tiles < sms ? total_tiles : sms;
