@@ -380,9 +380,9 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
     const uint32_t total_iters = (uint32_t)my_tiles * (uint32_t)k_iters;
+    int s = grp % p.stages;   // stage index and phase are stepped: no division on the per-stage path
+    uint32_t ph = (uint32_t)(grp / p.stages) & 1u;
     for (uint32_t lo_i = (uint32_t)grp; lo_i < total_iters; lo_i += 2u) {
-      const int s = (int)(lo_i % (uint32_t)p.stages);
-      const uint32_t ph = (lo_i / (uint32_t)p.stages) & 1u;
       const uint32_t aj = lo_i % G_A_RING;
       mbar_wait(&a_empty[aj], ((lo_i / G_A_RING) & 1u) ^ 1u, p.dbg, 0x700u + aj);
       mbar_wait(&lo_empty[lo_i % G_LO_RING], ((lo_i / G_LO_RING) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i % G_LO_RING));
@@ -411,6 +411,8 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[s]);
+      s += 2;
+      if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -628,8 +630,9 @@ int conv_dgrad_tf32(float* dx_out, const float* dyv, const float* w, int N, int 
 // this kernel; issue scales linearly with the number of producer WARPS, so two warps alternate chunks.
 constexpr int W_THREADS = 224;      // producer, MMA, 4 epilogue warps, second producer
 constexpr int W_THREADS_X3 = 480;   // ... + 2 groups of 4 operand-split warps before the second producer
-constexpr int W_A_RING_MAX = 6;     // X3: x operand (hi, lo) buffers in TMEM, 64 columns each
-constexpr int W_LO_RING_MAX = 4;    // X3: dy lo-part buffers in shared memory
+constexpr unsigned W_RING = 4;      // X3: x (hi, lo) buffers in TMEM (64 columns each) and dy-lo buffers in shared memory
+constexpr int W_A_RING_MAX = 4;
+constexpr int W_LO_RING_MAX = 4;
 constexpr int W_MAX_STAGES = 6;
 
 struct WgradUP {
@@ -643,7 +646,6 @@ struct WgradUP {
   uint32_t idesc, stage_a_bytes, stage_b_bytes, tmem_cols;
   int stages;
   int x3;
-  int a_ring, lo_ring;   // X3 ring depths (TMEM x buffers, shared-memory dy-lo buffers)
   int exp_flags;         // experiments (NG_UMMA_EXP): 1 skip x split loads, 2 skip MMAs, 4 skip TMEM stores, 16 skip dy split, 32 skip promotion
   uint32_t* dbg;
 };
@@ -663,10 +665,10 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
-  // X3: the x operand (hi, lo) goes to TMEM (ring of p.a_ring buffers of 64 columns, written by the
-  // split warps), only dy's lo part goes back to shared memory (ring of p.lo_ring)
+  // X3: the x operand (hi, lo) goes to TMEM (ring of W_RING buffers of 64 columns, written by the
+  // split warps), only dy's lo part goes back to shared memory (ring of W_RING)
   uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? (uint32_t)p.lo_ring * p.stage_b_bytes : 0u));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? W_RING * p.stage_b_bytes : 0u));
   uint64_t* empty_bar = full_bar + W_MAX_STAGES;
   uint64_t* split_bar = empty_bar + W_MAX_STAGES;
   uint64_t* lo_empty = split_bar + W_MAX_STAGES;   // [W_LO_RING_MAX]
@@ -778,9 +780,9 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
         uint32_t a_lo = smem_desc_lo(sa, 4096u), b_lo = smem_desc_lo(sa + p.stage_a_bytes, 4096u);
         if (X3) {
-          const uint32_t lj = (uint32_t)ch % (uint32_t)p.lo_ring;
+          const uint32_t lj = (uint32_t)ch % W_RING;
           uint32_t bl_lo = smem_desc_lo(lo0 + lj * p.stage_b_bytes, 4096u);
-          const uint32_t aj = (uint32_t)ch % (uint32_t)p.a_ring;
+          const uint32_t aj = lj;
           uint32_t a_t = tmem_a0 + aj * 64u;   // hi: columns [0,32), lo: [32,64)
           if (elect_one()) {
 #pragma unroll
@@ -829,12 +831,14 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
       const uint32_t smem0 = smem_u32(smem);
       const uint32_t col_base = (uint32_t)(m >> 5) * 4096u + (uint32_t)(m & 7) * 4u;  // group, position in 32B chunk
       const uint32_t chunk32 = (uint32_t)((m & 31) >> 3);
+      // stage index and phase are stepped (no division on the per-chunk path); the rings are powers of two
+      int s = grp % p.stages;
+      uint32_t ph = (uint32_t)(grp / p.stages) & 1u;
       for (int ch = grp; ch < n_chunks; ch += 2) {
-        const int s = ch % p.stages;
-        const uint32_t ph = (uint32_t)(ch / p.stages) & 1u;
-        const uint32_t aj = (uint32_t)ch % (uint32_t)p.a_ring, lj = (uint32_t)ch % (uint32_t)p.lo_ring;
-        mbar_wait(&a_empty[aj], (uint32_t)((((uint32_t)ch / (uint32_t)p.a_ring) & 1u) ^ 1u), p.dbg, 0x700u + aj);
-        mbar_wait(&lo_empty[lj], (uint32_t)((((uint32_t)ch / (uint32_t)p.lo_ring) & 1u) ^ 1u), p.dbg, 0x600u + lj);
+        const uint32_t aj = (uint32_t)ch % W_RING, lj = aj;
+        const uint32_t ring_parity = (((uint32_t)ch / W_RING) & 1u) ^ 1u;
+        mbar_wait(&a_empty[aj], ring_parity, p.dbg, 0x700u + aj);
+        mbar_wait(&lo_empty[lj], ring_parity, p.dbg, 0x600u + lj);
         mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
         tc_fence_after();
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes + col_base;
@@ -858,6 +862,8 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[s]);
+        s += 2;
+        if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
       }
     }
   } else {
@@ -982,19 +988,12 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
   p.stage_a_bytes = 128u * 128u;
   p.stage_b_bytes = (uint32_t)p.n_tile * 128u;
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
-  p.a_ring = (512 - 2 * p.n_tile) / 64;
-  if (p.a_ring > W_A_RING_MAX) p.a_ring = W_A_RING_MAX;
-  p.lo_ring = W_LO_RING_MAX;
   { const char* e = getenv("NG_UMMA_EXP"); p.exp_flags = e ? atoi(e) : 0; }
-  if (const char* e = getenv("NG_UMMA_WRING")) {   // experiment: "a,lo"
-    int a = 0, l = 0;
-    if (sscanf(e, "%d,%d", &a, &l) == 2 && a >= 1 && a <= p.a_ring && l >= 1 && l <= W_LO_RING_MAX) { p.a_ring = a; p.lo_ring = l; }
-  }
-  int stages = (int)((227u * 1024u - 2048u - (x3 ? (uint32_t)p.lo_ring * p.stage_b_bytes : 0u)) / stage_bytes);
+  int stages = (int)((227u * 1024u - 2048u - (x3 ? W_RING * p.stage_b_bytes : 0u)) / stage_bytes);
   if (stages > W_MAX_STAGES) stages = W_MAX_STAGES;
   if (stages < 2) return -1;
   p.stages = stages;
-  p.tmem_cols = (uint32_t)pow2_ceil(x3 ? 2 * p.n_tile + p.a_ring * 64 : (p.n_tile < 32 ? 32 : p.n_tile));
+  p.tmem_cols = (uint32_t)pow2_ceil(x3 ? 2 * p.n_tile + (int)W_RING * 64 : (p.n_tile < 32 ? 32 : p.n_tile));
 
   float *x_t = nullptr, *dy_t = nullptr, *ws = nullptr;
   if (!x_is_nhwc && pool_alloc((void**)&x_t, (uint64_t)N * C * H * W * sizeof(float))) return 1;
@@ -1031,7 +1030,7 @@ int conv_wgrad_tf32(float* dw, const float* dyv, const float* x, int N, int C, i
     }
   }
   if (rc == 0) {
-    const size_t smem_bytes = (size_t)stages * stage_bytes + (x3 ? (uint32_t)p.lo_ring * p.stage_b_bytes : 0u) + 1024 + 512;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + (x3 ? W_RING * p.stage_b_bytes : 0u) + 1024 + 512;
     const int grid = items * splits;
     static uint32_t* dbg_host = nullptr;
     const bool debug = getenv("NG_UMMA_DEBUG") != nullptr;
