@@ -795,7 +795,6 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
               a_t += 8u; b_lo += 64; bl_lo += 64;   // 8 pixels: 8 TMEM columns / 1024 bytes
             }
             mma_commit(&empty_bar[s]);
-            mma_commit(&lo_empty[lj]);
             mma_commit(&a_empty[aj]);
           }
         } else {
@@ -838,7 +837,6 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
         const uint32_t aj = (uint32_t)ch % W_RING, lj = aj;
         const uint32_t ring_parity = (((uint32_t)ch / W_RING) & 1u) ^ 1u;
         mbar_wait(&a_empty[aj], ring_parity, p.dbg, 0x700u + aj);
-        mbar_wait(&lo_empty[lj], ring_parity, p.dbg, 0x600u + lj);
         mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
         tc_fence_after();
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes + col_base;
