@@ -334,12 +334,21 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
           const uint32_t aj = lo_i % G_A_RING;
           uint32_t a_t = tmem_a0 + aj * 64u;   // hi: columns [0,32), lo: [32,64) of the A buffer
           if (elect_one()) {
-            for (int k = 0; k < ksteps; ++k) {
-              mma_tf32_ts(d_tmem, a_t + 32u, desc64(b_lo, dhi), p.idesc, accumulate);
-              mma_tf32_ts(d_tmem, a_t, desc64(bl_lo, dhi), p.idesc, 1u);
-              mma_tf32_ts(d_tmem, a_t, desc64(b_lo, dhi), p.idesc, 1u);
-              accumulate = 1;
-              a_t += 8u; b_lo += 2; bl_lo += 2;   // 8 TMEM columns / 32 bytes along K
+            if (ksteps == 4) {   // the common case, fully unrolled: this thread's time per stage is the kernel's critical path
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma_tf32_ts(d_tmem, a_t + 32u + 8u * k, desc64(b_lo + 2u * k, dhi), p.idesc, k == 0 ? accumulate : 1u);
+                mma_tf32_ts(d_tmem, a_t + 8u * k, desc64(bl_lo + 2u * k, dhi), p.idesc, 1u);
+                mma_tf32_ts(d_tmem, a_t + 8u * k, desc64(b_lo + 2u * k, dhi), p.idesc, 1u);
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                mma_tf32_ts(d_tmem, a_t + 32u, desc64(b_lo, dhi), p.idesc, accumulate);
+                mma_tf32_ts(d_tmem, a_t, desc64(bl_lo, dhi), p.idesc, 1u);
+                mma_tf32_ts(d_tmem, a_t, desc64(b_lo, dhi), p.idesc, 1u);
+                accumulate = 1;
+                a_t += 8u; b_lo += 2; bl_lo += 2;   // 8 TMEM columns / 32 bytes along K
+              }
             }
             mma_commit(&empty_bar[s]);
             mma_commit(&lo_empty[lo_i % G_LO_RING]);
