@@ -21,6 +21,10 @@ LIB_PATH = os.path.join(LIB_DIR, "libnanograd_b200.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# NANOGRAD_B200_ABLATE=1 builds the tensor-core kernels with their NG_UMMA_EXP ablation switches
+# (development only: the switches cost time on the per-stage paths, so release builds leave them out)
+if os.environ.get("NANOGRAD_B200_ABLATE"):
+    NVCC_FLAGS.append("-DNG_UMMA_ABLATE")
 
 
 def find_nvcc():

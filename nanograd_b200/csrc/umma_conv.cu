@@ -186,6 +186,16 @@ int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
   return 0;
 }
 
+// Ablation switches (NG_UMMA_EXP=<bits>) exist only in builds with -DNG_UMMA_ABLATE:
+// even an always-false runtime test on the per-stage paths costs measurable time in these kernels.
+#ifdef NG_UMMA_ABLATE
+#define NG_EXP(bits) ((p.exp_flags & (bits)) != 0)
+#define NG_EXP_FLAGS (p.exp_flags)
+#else
+#define NG_EXP(bits) false
+#define NG_EXP_FLAGS 0
+#endif
+
 // ------------------------------------------------------------------ gather kernel (fprop / dgrad)
 constexpr int G_THREADS = 224;       // TF32 mode: producer, MMA, 4 epilogue warps, second producer
 constexpr int G_THREADS_X3 = 480;    // 3xTF32 mode: + 2 groups of 4 operand-split warps before the second producer
@@ -224,7 +234,8 @@ struct GatherP {
     if (p.dbg) { ((volatile uint32_t*)p.dbg)[i] = (v); __threadfence_system(); } \
   } while (0)
 
-__global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const __grid_constant__ GatherP p) {
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? G_THREADS_X3 : G_THREADS, 1) umma_conv_gather_kernel(const __grid_constant__ GatherP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // Shared memory: `stages` operand sets (A tile + B tile) filled by TMA, then — 3xTF32 mode only — a
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
   // memory: 32 KB of shared-memory traffic per K step of a 128x128 tile instead of 48 KB.
   const uint32_t stage_bytes = p.stage_a_bytes + p.stage_b_bytes;
   uint8_t* lo_ring = smem + (size_t)p.stages * stage_bytes;   // x3: 2 x stage_b_bytes (B lo)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (p.x3 ? G_LO_RING * p.stage_b_bytes : 0u));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lo_ring + (X3 ? G_LO_RING * p.stage_b_bytes : 0u));
   uint64_t* empty_bar = full_bar + G_MAX_STAGES;
   uint64_t* split_bar = empty_bar + G_MAX_STAGES;
   uint64_t* lo_empty = split_bar + G_MAX_STAGES;   // [G_LO_RING]
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
   const int total_tiles = m_tiles * p.n_tiles;
   const int k_iters = p.RS * p.c_chunks;
 
-  const int producer2 = p.x3 ? 14 : 6;   // two TMA-issuing warps alternate stages (see W_THREADS below)
+  const int producer2 = X3 ? 14 : 6;   // two TMA-issuing warps alternate stages (see W_THREADS below)
   if (warp == 0 || warp == producer2) {
     if (lane == 0) {
       const uint32_t pid = warp == 0 ? 0u : 1u;
@@ -324,12 +335,12 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       for (int it = 0; it < k_iters; ++it) {
         int ksteps = (p.KC - cc * G_CCHUNK + 7) >> 3;
         if (ksteps > 4) ksteps = 4;
-        if (p.exp_flags & 2) ksteps = 0;
-        mbar_wait(p.x3 ? &split_bar[s] : &full_bar[s], ph, p.dbg, 0x300u + s);
+        if (NG_EXP(2)) ksteps = 0;
+        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph, p.dbg, 0x300u + s);
         tc_fence_after();
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
         uint32_t a_lo = smem_desc_lo(sa, 16u), b_lo = smem_desc_lo(sa + p.stage_a_bytes, 16u);
-        if (p.x3) {
+        if (X3) {
           uint32_t bl_lo = smem_desc_lo(lo0 + (lo_i % G_LO_RING) * p.stage_b_bytes, 16u);
           const uint32_t aj = lo_i % G_A_RING;
           uint32_t a_t = tmem_a0 + aj * 64u;   // hi: columns [0,32), lo: [32,64) of the A buffer
@@ -397,7 +408,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
       mbar_wait(&lo_empty[lo_i % G_LO_RING], ((lo_i / G_LO_RING) & 1u) ^ 1u, p.dbg, 0x600u + (lo_i % G_LO_RING));
       mbar_wait(&full_bar[s], ph, p.dbg, 0x500u + s);
       tc_fence_after();
-      if (!(p.exp_flags & 1)) {
+      if (!NG_EXP(1)) {
         // A: own 128-byte row (32 channels), 16-byte chunks un-swizzled (chunk ^ (row & 7))
         const uint32_t row = smem0 + (uint32_t)s * stage_bytes + (uint32_t)m * 128u;
         uint32_t hi[32], lo[32];
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
         tmem_st_32x32(a_t + 32u, lo);
         // B: lo part to the shared-memory ring
         split_stage_hi_lo(smem + (size_t)s * stage_bytes + p.stage_a_bytes,
-                          lo_ring + (size_t)(lo_i % G_LO_RING) * p.stage_b_bytes, p.stage_b_bytes, t, p.exp_flags);
+                          lo_ring + (size_t)(lo_i % G_LO_RING) * p.stage_b_bytes, p.stage_b_bytes, t, NG_EXP_FLAGS);
         tmem_st_wait();
       }
       tc_fence_before();
@@ -449,7 +460,7 @@ __global__ void __launch_bounds__(G_THREADS_X3, 1) umma_conv_gather_kernel(const
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
         const int jbase = n_t * p.n_tile + j0;
-        if (valid && !(p.exp_flags & 4)) {
+        if (valid && !NG_EXP(4)) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int j = jbase + i;
@@ -563,8 +574,11 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   if (rc == 0) {
     static bool configured = false;
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(umma_conv_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(umma_conv_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(227 * 1024));
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(umma_conv_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(227 * 1024));
       if (e != cudaSuccess) rc = set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       configured = (e == cudaSuccess);
     }
@@ -583,7 +597,8 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
       fprintf(stderr, "[umma] gather: tiles %d grid %d n_tile %d stages %d w_tile %d rows %d imgs %d idesc %08x tmem %u\n",
               total_tiles, grid, p.n_tile, p.stages, p.w_tile, p.rows_tile, p.imgs_tile, p.idesc, p.tmem_cols);
     }
-    NG_LAUNCH(umma_conv_gather_kernel, grid, x3 ? G_THREADS_X3 : G_THREADS, smem_bytes, p);
+    if (x3) NG_LAUNCH(umma_conv_gather_kernel<true>, grid, G_THREADS_X3, smem_bytes, p);
+    else NG_LAUNCH(umma_conv_gather_kernel<false>, grid, G_THREADS, smem_bytes, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = set_error("umma_conv_gather_kernel launch failed: %s", cudaGetErrorString(e));
     if (debug) {
@@ -796,7 +811,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (p.exp_flags & 2) break;
+              if (NG_EXP(2)) break;
               mma_tf32_ts(d_tmem, a_t + 32u, desc64(b_lo, dhi), p.idesc, accumulate);
               mma_tf32_ts(d_tmem, a_t, desc64(bl_lo, dhi), p.idesc, 1u);
               mma_tf32_ts(d_tmem, a_t, desc64(b_lo, dhi), p.idesc, 1u);
@@ -853,18 +868,18 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           float v = 1.f;
-          if (!(p.exp_flags & 1))
+          if (!NG_EXP(1))
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa + (uint32_t)k * 128u + ((chunk32 ^ (uint32_t)(k & 3)) << 5)));
           hi[k] = __float_as_uint(v);
           lo[k] = __float_as_uint(tf32_lo(v));
         }
         const uint32_t a_t = tmem_a0 + aj * 64u + lane_addr;
-        if (!(p.exp_flags & 4)) {
+        if (!NG_EXP(4)) {
           tmem_st_32x32(a_t, hi);
           tmem_st_32x32(a_t + 32u, lo);
         }
         split_stage_hi_lo(smem + (size_t)s * stage_bytes + p.stage_a_bytes,
-                          lo_ring + (size_t)lj * p.stage_b_bytes, p.stage_b_bytes, t, p.exp_flags & 16);
+                          lo_ring + (size_t)lj * p.stage_b_bytes, p.stage_b_bytes, t, NG_EXP_FLAGS & 16);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -891,7 +906,7 @@ umma_conv_wgrad_kernel(const __grid_constant__ WgradUP p) {
         tc_fence_after();
 #pragma unroll
         for (int j0 = 0; j0 < W_X3_MAX_N; j0 += 32) {
-          if (j0 < p.n_tile && !(p.exp_flags & 32)) {
+          if (j0 < p.n_tile && !NG_EXP(32)) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.n_tile + j0), r);
             tmem_ld_wait();
