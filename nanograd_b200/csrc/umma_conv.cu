@@ -213,6 +213,7 @@ struct GatherP {
   CUtensorMap tm_b;  // filters [tap][j][kc], dims (KC, J, RS)
   float* out;
   const float* bias;
+  int bias_vec;   // bias is 16-byte aligned: the epilogue reads it four values at a time
   int n_img, J, KC, RS, OH, OW;
   int w_tile, rows_tile, imgs_tile;   // w_tile * rows_tile * imgs_tile == 128
   int tiles_w, tiles_h, tiles_img;
@@ -461,14 +462,43 @@ __global__ void __launch_bounds__(X3 ? G_THREADS_X3 : G_THREADS, 1) umma_conv_ga
         tmem_ld_wait();
         const int jbase = n_t * p.n_tile + j0;
         if (valid && !NG_EXP(4)) {
+          // These warps share issue slots with the split warps and the MMA thread, so the store loop is kept
+          // lean: one running pointer, no per-element bounds test on full chunks, bias as four-wide loads.
+          float* dst = out_pix + (long long)jbase * opix;
+          if (jbase + 32 <= p.J) {
+            if (p.bias_vec) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + jbase);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int j = jbase + i;
-            if (j < p.J) {
-              float v = __uint_as_float(r[i]);
-              if (p.bias) v += __ldg(p.bias + j);
-              if (p.relu) v = fmaxf(v, 0.f);
-              out_pix[(long long)j * opix] = v;
+              for (int i = 0; i < 8; ++i) {
+                const float4 bv = __ldg(b4 + i);
+                r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + bv.x);
+                r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + bv.y);
+                r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + bv.z);
+                r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + bv.w);
+              }
+            } else if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(p.bias + jbase + i));
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              *dst = __uint_as_float(r[i]);
+              dst += opix;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int j = jbase + i;
+              if (j < p.J) {
+                float v = __uint_as_float(r[i]);
+                if (p.bias) v += __ldg(p.bias + j);
+                if (p.relu) v = fmaxf(v, 0.f);
+                dst[(long long)i * opix] = v;
+              }
             }
           }
         }
@@ -512,6 +542,7 @@ static int launch_gather(float* out, const float* act, const float* filt, const 
   memset(&p, 0, sizeof(p));
   p.out = out;
   p.bias = bias;
+  p.bias_vec = (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) ? 1 : 0;
   p.n_img = n_img; p.J = J; p.KC = KC; p.RS = RS; p.OH = OH; p.OW = OW;
   int w_tile = pow2_ceil(OW);
   if (w_tile > 32) w_tile = 32;
