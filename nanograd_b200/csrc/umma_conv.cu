@@ -368,10 +368,16 @@ __global__ void __launch_bounds__(X3 ? G_THREADS_X3 : G_THREADS, 1) umma_conv_ga
           }
         } else {
           if (elect_one()) {
-            for (int k = 0; k < ksteps; ++k) {
-              mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(b_lo, dhi), p.idesc, accumulate);
-              accumulate = 1;
-              a_lo += 2; b_lo += 2;
+            if (ksteps == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_tf32(d_tmem, desc64(a_lo + 2u * k, dhi), desc64(b_lo + 2u * k, dhi), p.idesc, k == 0 ? accumulate : 1u);
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                mma_tf32(d_tmem, desc64(a_lo, dhi), desc64(b_lo, dhi), p.idesc, accumulate);
+                accumulate = 1;
+                a_lo += 2; b_lo += 2;
+              }
             }
             mma_commit(&empty_bar[s]);
           }
