@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
                                                         int64_t N, int64_t C, int64_t P, int64_t n_per_split,
                                                         int vec_ok, const float* __restrict__ gamma = nullptr,
                                                         const float* __restrict__ beta = nullptr,
-                                                        const float* __restrict__ invstd = nullptr) {
+                                                        const float* __restrict__ invstd = nullptr, FastDiv fp4 = FastDiv{0, 0, 0}) {
   __shared__ float scratch[32];
   const int64_t c = blockIdx.x, s = blockIdx.y;
   float za = 0.f, zb = 0.f;
@@ -40,8 +40,17 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
   if (vec_ok) {
     const int64_t P4 = P >> 2;
     const int64_t items = (n1 - n0) * P4;
+    const bool fast = fp4.d != 0 && items < (1LL << 31);
     for (int64_t i = threadIdx.x; i < items; i += blockDim.x) {
-      const int64_t n = n0 + i / P4, p4 = i % P4;
+      int64_t n, p4;
+      if (fast) {
+        const uint32_t q = fastdiv((uint32_t)i, fp4);
+        n = n0 + q;
+        p4 = (uint32_t)i - q * fp4.d;
+      } else {
+        n = n0 + i / P4;
+        p4 = i % P4;
+      }
       const int64_t off = (n * C + c) * P + (p4 << 2);
       const float4 xv = *reinterpret_cast<const float4*>(x + off);
       if (MODE == 0) {
@@ -118,13 +127,21 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, co
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ mean, const float* __restrict__ inv_or_var,
                                                        int64_t total, int64_t C, int64_t P, float eps, int use_var,
-                                                       int vec_ok, int relu) {
+                                                       int vec_ok, int relu, FastDiv fp4 = FastDiv{0, 0, 0},
+                                                       FastDiv fc = FastDiv{0, 0, 0}) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
     const int64_t n4 = total >> 2;
+    const bool fast = fp4.d != 0 && fc.d != 0 && n4 < (1LL << 31);
     for (int64_t i = tid; i < n4; i += nth) {
-      const int64_t c = ((i << 2) / P) % C;
+      int64_t c;
+      if (fast) {
+        const uint32_t plane = fastdiv((uint32_t)i, fp4);
+        c = plane - fastdiv(plane, fc) * fc.d;
+      } else {
+        c = ((i << 2) / P) % C;
+      }
       const float inv = use_var ? 1.f / sqrtf(inv_or_var[c] + eps) : inv_or_var[c];
       const float a = gamma[c] * inv, mu = mean[c], b = beta[c];
       float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -165,14 +182,22 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(float* __restrict__ dx, 
                                                         const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ sums, int64_t total, int64_t C, int64_t P,
-                                                        float inv_count, int vec_ok, const float* __restrict__ beta) {
+                                                        float inv_count, int vec_ok, const float* __restrict__ beta,
+                                                        FastDiv fp4 = FastDiv{0, 0, 0}, FastDiv fc = FastDiv{0, 0, 0}) {
   // beta != nullptr: fused ReLU, dy is masked by (z >= 0) with z recomputed from x
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
     const int64_t n4 = total >> 2;
+    const bool fast = fp4.d != 0 && fc.d != 0 && n4 < (1LL << 31);
     for (int64_t i = tid; i < n4; i += nth) {
-      const int64_t c = ((i << 2) / P) % C;
+      int64_t c;
+      if (fast) {
+        const uint32_t plane = fastdiv((uint32_t)i, fp4);
+        c = plane - fastdiv(plane, fc) * fc.d;
+      } else {
+        c = ((i << 2) / P) % C;
+      }
       const float inv = invstd[c], mu = mean[c];
       const float k0 = gamma[c] * inv, k1 = sums[c * 2] * inv_count, k2 = inv * inv * sums[c * 2 + 1] * inv_count;
       float4 g = reinterpret_cast<const float4*>(dy)[i];
@@ -238,7 +263,7 @@ int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
   NG_LAUNCH((bn_reduce_kernel<0>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
             (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr,
-            (const float*)nullptr, (const float*)nullptr);
+            (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
   NG_CHECK_LAUNCH();
   NG_LAUNCH(bn_fwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, dptr<const float>(x),
             dptr<float>(save_mean), dptr<float>(save_invstd), running_mean ? dptr<float>(running_mean) : nullptr,
@@ -247,7 +272,8 @@ int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
   const int64_t total = N * C * HW;
   NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
             dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(save_mean),
-            dptr<const float>(save_invstd), total, C, HW, eps, 0, vec, act);
+            dptr<const float>(save_invstd), total, C, HW, eps, 0, vec, act, make_fastdiv(vec ? HW / 4 : 0),
+            make_fastdiv(C));
   NG_CHECK_LAUNCH();
   pool_free(partial);
   return 0;
@@ -269,7 +295,8 @@ int ng_bn2d_act_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, 
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
   NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
             dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(running_mean),
-            dptr<const float>(running_var), total, C, HW, eps, 1, vec, act);
+            dptr<const float>(running_var), total, C, HW, eps, 1, vec, act, make_fastdiv(vec ? HW / 4 : 0),
+            make_fastdiv(C));
   NG_CHECK_LAUNCH();
   return 0;
 }
@@ -295,11 +322,11 @@ int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, u
   if (act) {
     NG_LAUNCH((bn_reduce_kernel<2>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
               dptr<const float>(dy), dptr<const float>(save_mean), N, C, HW, n_per, vec, dptr<const float>(gamma),
-              dptr<const float>(beta), dptr<const float>(save_invstd));
+              dptr<const float>(beta), dptr<const float>(save_invstd), make_fastdiv(vec ? HW / 4 : 0));
   } else {
     NG_LAUNCH((bn_reduce_kernel<1>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
               dptr<const float>(dy), dptr<const float>(save_mean), N, C, HW, n_per, vec, (const float*)nullptr,
-              (const float*)nullptr, (const float*)nullptr);
+              (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
   }
   NG_CHECK_LAUNCH();
   NG_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial,
@@ -309,7 +336,7 @@ int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, u
   NG_LAUNCH(bn_bwd_dx_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(dx), dptr<const float>(dy),
             dptr<const float>(x), dptr<const float>(gamma), dptr<const float>(save_mean),
             dptr<const float>(save_invstd), (const float*)sums, total, C, HW, 1.f / (float)(N * HW), vec,
-            act ? dptr<const float>(beta) : (const float*)nullptr);
+            act ? dptr<const float>(beta) : (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0), make_fastdiv(C));
   NG_CHECK_LAUNCH();
   pool_free(partial);
   return 0;

@@ -78,6 +78,29 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
   type* name = reinterpret_cast<type*>(name##_raw)
 #endif
 
+// Division of 0 <= n < 2^31 by a launch-invariant divisor as one wide multiply and a shift (the
+// memory-bound kernels otherwise spend more issue slots on 64-bit index divisions than on data):
+// m = ceil(2^s / d), s = 31 + ceil(log2 d)  =>  floor(n / d) == (n * m) >> s exactly for n < 2^31.
+struct FastDiv {
+  uint32_t d, m, s;   // d == 0: not set up (callers keep their generic path)
+};
+static inline FastDiv make_fastdiv(int64_t d) {
+  FastDiv f;
+  f.d = f.m = f.s = 0;
+  if (d < 1 || d >= (1LL << 31)) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < (uint64_t)d) ++l;
+  f.d = (uint32_t)d;
+  f.s = 31 + l;
+  f.m = (uint32_t)(((1ull << f.s) + (uint64_t)d - 1) / (uint64_t)d);
+  return f;
+}
+#if defined(__CUDACC__) || defined(NG_EMU)
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+  return (uint32_t)(((unsigned long long)n * f.m) >> f.s);
+}
+#endif
+
 // 16-byte aligned static shared array (float4 fragment reads)
 #ifdef NG_EMU
 #define NG_SHARED16 alignas(16) static
