@@ -373,6 +373,26 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(float* __restrict__ 
   }
 }
 
+// Many partials, few outputs (the direct first-layer wgrad writes one partial per CTA): 8 threads share
+// an output, each sums every 8th partial, shared memory adds the 8 in a fixed order.
+__global__ void __launch_bounds__(512) splitk_reduce_wide_kernel(float* __restrict__ out, const float* __restrict__ ws, int S,
+                                                                 long long n) {
+  __shared__ float red[8][64];
+  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const long long e = (long long)blockIdx.x * 64 + el;
+  float acc = 0.f;
+  if (e < n)
+    for (int s = g; s < S; s += 8) acc += ws[(long long)s * n + e];
+  red[g][el] = acc;
+  __syncthreads();
+  if (g == 0 && e < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][el];
+    out[e] = t;
+  }
+}
+
 // =====================================================================================
 // wgrad: dW[k][c][r][s] = sum_{n,oh,ow} dy[n,k,oh,ow] * x[n,c,oh*st+r-pt,ow*st+s-pl]
 //   I = flattened (c,r,s), J = k, reduction over (n, oh, ow) split across grid.z
@@ -979,9 +999,8 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
         else if (RPG == 2) NG_LAUNCH((conv_wgrad_smallc_kernel<2>), grid, K * G, smem, q);
         else NG_LAUNCH((conv_wgrad_smallc_kernel<3>), grid, K * G, smem, q);
         NG_CHECK_LAUNCH();
-        int g = (int)ceil_div(out_elems, 256);
-        NG_LAUNCH(splitk_reduce_kernel, g, 256, 0, dptr<float>(dw), (const float*)ws, grid, out_elems,
-                  (const float*)nullptr, 1, 0);
+        NG_LAUNCH(splitk_reduce_wide_kernel, (int)ceil_div(out_elems, 64), 512, 0, dptr<float>(dw), (const float*)ws, grid,
+                  out_elems);
         NG_CHECK_LAUNCH();
         pool_free(ws);
         prof_end(tok);

@@ -16,6 +16,7 @@ struct PoolP {
   int64_t NC;
   int H, W, ph, pw, OH, OW;
   int fast2;  // ph == pw == 2, W even and base pointers 8-byte aligned
+  FastDiv f_ow, f_oh;  // set when the output has fewer than 2^31 elements: index math without 64-bit divisions
 };
 
 template <bool IS_MAX>
@@ -23,10 +24,20 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(float* __restrict__ y, co
   const int64_t total = p.NC * p.OH * p.OW;
   const float scale = 1.f / (float)(p.ph * p.pw);
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int ow = (int)(o % p.OW);
-    const int64_t t = o / p.OW;
-    const int oh = (int)(t % p.OH);
-    const int64_t nc = t / p.OH;
+    int ow, oh;
+    int64_t nc;
+    if (p.f_ow.d) {
+      const uint32_t t = fastdiv((uint32_t)o, p.f_ow);
+      ow = (int)((uint32_t)o - t * p.f_ow.d);
+      const uint32_t u = fastdiv(t, p.f_oh);
+      oh = (int)(t - u * p.f_oh.d);
+      nc = u;
+    } else {
+      ow = (int)(o % p.OW);
+      const int64_t t = o / p.OW;
+      oh = (int)(t % p.OH);
+      nc = t / p.OH;
+    }
     const float* src = x + (nc * p.H + (int64_t)oh * p.ph) * p.W + (int64_t)ow * p.pw;
     float acc;
     if (p.fast2) {
@@ -54,10 +65,20 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(float* __restrict__ dx, c
   const int64_t total = p.NC * p.OH * p.OW;
   const float scale = 1.f / (float)(p.ph * p.pw);
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int ow = (int)(o % p.OW);
-    const int64_t t = o / p.OW;
-    const int oh = (int)(t % p.OH);
-    const int64_t nc = t / p.OH;
+    int ow, oh;
+    int64_t nc;
+    if (p.f_ow.d) {
+      const uint32_t t = fastdiv((uint32_t)o, p.f_ow);
+      ow = (int)((uint32_t)o - t * p.f_ow.d);
+      const uint32_t u = fastdiv(t, p.f_oh);
+      oh = (int)(t - u * p.f_oh.d);
+      nc = u;
+    } else {
+      ow = (int)(o % p.OW);
+      const int64_t t = o / p.OW;
+      oh = (int)(t % p.OH);
+      nc = t / p.OH;
+    }
     const int64_t base = (nc * p.H + (int64_t)oh * p.ph) * p.W + (int64_t)ow * p.pw;
     const float g = dy[o];
     if (IS_MAX) {
@@ -102,6 +123,8 @@ static int make_pool(PoolP& p, const char* who, int64_t NC, int H, int W, int ph
   p.NC = NC; p.H = H; p.W = W; p.ph = ph; p.pw = pw;
   p.OH = H / ph; p.OW = W / pw;
   p.fast2 = (ph == 2 && pw == 2 && (W % 2 == 0) && (a % 8 == 0) && (b % 8 == 0)) ? 1 : 0;
+  p.f_ow = p.f_oh = FastDiv{0, 0, 0};
+  if (p.OH > 0 && p.OW > 0 && NC * p.OH * p.OW < (1LL << 31)) { p.f_ow = make_fastdiv(p.OW); p.f_oh = make_fastdiv(p.OH); }
   return 0;
 }
 
