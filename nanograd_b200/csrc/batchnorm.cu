@@ -41,32 +41,48 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
     const int64_t P4 = P >> 2;
     const int64_t items = (n1 - n0) * P4;
     const bool fast = fp4.d != 0 && items < (1LL << 31);
-    for (int64_t i = threadIdx.x; i < items; i += blockDim.x) {
-      int64_t n, p4;
-      if (fast) {
-        const uint32_t q = fastdiv((uint32_t)i, fp4);
-        n = n0 + q;
-        p4 = (uint32_t)i - q * fp4.d;
-      } else {
-        n = n0 + i / P4;
-        p4 = i % P4;
-      }
-      const int64_t off = (n * C + c) * P + (p4 << 2);
-      const float4 xv = *reinterpret_cast<const float4*>(x + off);
-      if (MODE == 0) {
-        const float a0 = xv.x - ref, a1 = xv.y - ref, a2 = xv.z - ref, a3 = xv.w - ref;
-        sa += (a0 + a1) + (a2 + a3);
-        sb += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-      } else {
-        float4 g = *reinterpret_cast<const float4*>(dy + off);
-        if (MODE == 2) {
-          if (!(bn_affine(xv.x, ref, za, zb) >= 0.f)) g.x = 0.f;
-          if (!(bn_affine(xv.y, ref, za, zb) >= 0.f)) g.y = 0.f;
-          if (!(bn_affine(xv.z, ref, za, zb) >= 0.f)) g.z = 0.f;
-          if (!(bn_affine(xv.w, ref, za, zb) >= 0.f)) g.w = 0.f;
+    // Several iterations' loads are issued before any is consumed: with one 16-byte load in flight per thread
+    // the pass was latency-bound (3.7 TB/s measured).  Out-of-range slots read nothing and add zero.
+    constexpr int U = (MODE == 0) ? 4 : 2;   // the backward passes load two tensors: same bytes in flight
+    for (int64_t i0 = threadIdx.x; i0 < items; i0 += U * (int64_t)blockDim.x) {
+      float4 xv[U], gv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * (int64_t)blockDim.x;
+        xv[u].x = xv[u].y = xv[u].z = xv[u].w = ref;
+        gv[u].x = gv[u].y = gv[u].z = gv[u].w = 0.f;
+        if (i < items) {
+          int64_t n, p4;
+          if (fast) {
+            const uint32_t q = fastdiv((uint32_t)i, fp4);
+            n = n0 + q;
+            p4 = (uint32_t)i - q * fp4.d;
+          } else {
+            n = n0 + i / P4;
+            p4 = i % P4;
+          }
+          const int64_t off = (n * C + c) * P + (p4 << 2);
+          xv[u] = *reinterpret_cast<const float4*>(x + off);
+          if (MODE != 0) gv[u] = *reinterpret_cast<const float4*>(dy + off);
         }
-        sa += (g.x + g.y) + (g.z + g.w);
-        sb += (g.x * (xv.x - ref) + g.y * (xv.y - ref)) + (g.z * (xv.z - ref) + g.w * (xv.w - ref));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (MODE == 0) {
+          const float a0 = xv[u].x - ref, a1 = xv[u].y - ref, a2 = xv[u].z - ref, a3 = xv[u].w - ref;
+          sa += (a0 + a1) + (a2 + a3);
+          sb += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        } else {
+          float4 g = gv[u];
+          if (MODE == 2) {
+            if (!(bn_affine(xv[u].x, ref, za, zb) >= 0.f)) g.x = 0.f;
+            if (!(bn_affine(xv[u].y, ref, za, zb) >= 0.f)) g.y = 0.f;
+            if (!(bn_affine(xv[u].z, ref, za, zb) >= 0.f)) g.z = 0.f;
+            if (!(bn_affine(xv[u].w, ref, za, zb) >= 0.f)) g.w = 0.f;
+          }
+          sa += (g.x + g.y) + (g.z + g.w);
+          sb += (g.x * (xv[u].x - ref) + g.y * (xv[u].y - ref)) + (g.z * (xv[u].z - ref) + g.w * (xv[u].w - ref));
+        }
       }
     }
   } else {
