@@ -138,9 +138,9 @@ def cpu_oracle_images_per_sec(steps, warmup, batch=CPU_SAMPLE_BATCH):
     import nanograd_b200.nn.module as nn
     import nanograd_b200.optim.optimizer as optim
     from nanograd_b200.device import Device
-    from nanograd_b200.tensor import Tensor, register_ops
-    from oracle import cpu_namespace
-    register_ops(cpu_namespace, device=Device.CPU)
+    from nanograd_b200.tensor import Tensor
+    import oracle
+    oracle.register_host()
     X, Y = synthetic_batch(batch, seed=0)
     times = []
     for i in range(warmup + steps):

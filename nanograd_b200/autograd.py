@@ -4,8 +4,11 @@ Same contract as the reference (nanograd/autograd.py:7-41): an op is a class wit
 ``forward(ctx, *raw_buffers, **kwargs)`` / ``backward(ctx, grad_raw)``; ``apply`` creates the
 context, mirrors forward's keyword defaults and the call's kwargs onto it, runs forward on the
 raw ``.data`` of the argument tensors and wraps the result.  Additions: the signature lookup is
-cached per class (the reference calls inspect.signature on every apply) and the result
-records ``children`` / ``op`` so the graph visualiser has edges to draw.
+cached per class (the reference calls inspect.signature on every apply), the result
+records ``children`` / ``op`` so the graph visualiser has edges to draw, and the result is built
+with the *caller's* Tensor class (``type(args[0])``) — the op namespace therefore works
+unchanged under this package's Tensor and under the reference's own ``nanograd.tensor.Tensor``
+(``nanograd_b200.integrate``), whose ``Device`` enum is a different object.
 """
 import inspect
 
@@ -39,7 +42,7 @@ class Function:
 
     def apply(self, *args, **kwargs):
         # called as op.apply(op, *tensors, **kwargs): `self` is the op class (tensor.py:487)
-        from nanograd_b200.tensor import Tensor
+        tensor_cls = type(args[0])  # the host package's Tensor (this repo's or the reference's)
 
         ctx = self(*args)
         for name, default in self._forward_defaults():
@@ -49,9 +52,11 @@ class Function:
 
         out = self.forward(ctx, *[t.data for t in args], **kwargs)
         requires_grad = any(t.requires_grad for t in args)
-        ret = Tensor(out, device=ctx.device, requires_grad=requires_grad)
+        ret = tensor_cls(out, device=ctx.device, requires_grad=requires_grad)
         ret.op = self.__name__.lower()
-        ret.children = [t for t in args]
         if requires_grad:
+            # edges for the visualiser; a no-grad result keeps no reference to its inputs, so
+            # inference chains do not pin device buffers
+            ret.children = list(args)
             ret.ctx = ctx
         return ret

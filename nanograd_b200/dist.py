@@ -123,6 +123,42 @@ def all_reduce_host(array):
     return t.numpy()
 
 
+class GradBucket:
+    """One flat FP32 arena holding the gradients of an optimizer's parameters, the operand of the
+    data-parallel allreduce.  ``reduce(params)`` returns the per-parameter device pointers of
+    the cross-rank *sums* (the optimizer kernel folds in 1/world)."""
+
+    ALIGN = 32  # floats: every slot starts on a 128-byte boundary (vectorised optimizer loads)
+
+    def __init__(self, params):
+        from nanograd_b200.nn.buffer import DeviceBuffer
+        self.ids = [id(p) for p in params]
+        self.numels = [int(p.data.size) for p in params]
+        self.offsets, off = [], 0
+        for n in self.numels:
+            self.offsets.append(off)
+            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.total = off
+        self.flat = DeviceBuffer((max(self.total, 1),))
+        from nanograd_b200 import backend as B
+        B.lib().ng_memset_zero(self.flat.ptr, self.flat.size * 4)  # padding stays zero for ever
+
+    def matches(self, params):
+        return [id(p) for p in params] == self.ids and [int(p.data.size) for p in params] == self.numels
+
+    def slot_ptr(self, i):
+        return self.flat.ptr + 4 * self.offsets[i]
+
+    def reduce(self, params):
+        from nanograd_b200 import backend as B
+        lib = B.lib()
+        for i, p in enumerate(params):
+            if p.grad.data.ptr != self.slot_ptr(i):
+                lib.ng_d2d(self.slot_ptr(i), p.grad.data.ptr, 4 * self.numels[i])
+        lib.ng_nccl_allreduce_sum(self.flat.ptr, self.total)
+        return [self.slot_ptr(i) for i in range(len(params))]
+
+
 def shutdown():
     if not _state["initialized"]:
         return

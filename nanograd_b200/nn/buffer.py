@@ -87,7 +87,9 @@ class ScalarBuffer(DeviceBuffer):
     The reference wraps every non-Tensor positional argument into ``Tensor(np.array([x]))`` on
     the input's device (tensor.py:482-483) — a 4-byte host-to-device copy per ``x * 0.5``.  Here
     the value stays on the host and rides in the kernel arguments; device memory is only
-    materialised if some op really needs a pointer.
+    materialised if some op really needs a pointer.  Once a pointer has been handed out the
+    device copy is the truth (a kernel may have written through it): ``immediate`` turns False
+    and ``numpy()`` reads the device.
     """
 
     def __init__(self, value):
@@ -99,6 +101,11 @@ class ScalarBuffer(DeviceBuffer):
         self.value = float(value)
 
     @property
+    def immediate(self):
+        """True while the value only lives on the host (usable as a kernel immediate)."""
+        return self._ptr == 0
+
+    @property
     def ptr(self):
         if not self._ptr:
             self._ptr = backend.malloc(4)
@@ -107,8 +114,16 @@ class ScalarBuffer(DeviceBuffer):
         return self._ptr
 
     def numpy(self):
+        if self._ptr:
+            return DeviceBuffer.numpy(self)
         return np.array([self.value], dtype=np.float32)
 
 
-# the reference's name for the same role
-GPUBuffer = DeviceBuffer
+class GPUBuffer(DeviceBuffer):
+    """``DeviceBuffer`` under the reference's name and constructor signature
+    ``GPUBuffer(ctx, shape, hostbuf=None)`` (nanograd/nn/buffer.py:14-26) — what
+    ``nanograd/nn/buffer.py`` exports once the backend is bound.  ``ctx`` (the
+    PyOpenCL context in the reference) is ignored."""
+
+    def __init__(self, ctx, shape, hostbuf=None):
+        DeviceBuffer.__init__(self, shape, hostbuf=hostbuf)

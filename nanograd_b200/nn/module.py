@@ -4,7 +4,8 @@ Class names, constructor signatures, attribute names (``weight``, ``bias``, ``ru
 and numerical semantics follow the reference (module.py:10-863, cited per class).  Layers are
 device-agnostic compositions of Tensor methods; where the tensor's device namespace offers a
 fused op (``conv2dbias``, ``linear``, ``batchnorm2d``, ``nllloss`` — see nn/ops_cuda.py) the layer
-issues that single op, otherwise it composes primitives exactly as the reference does.
+issues that single op, otherwise it composes primitives exactly as the reference does
+(BatchNorm excepted: device op only, see ``set_host_forward``).
 """
 from typing import Union
 
@@ -38,6 +39,24 @@ def init_weights(shape: tuple, weight_initialization: str, fan_mode: str = "fan_
 
 def _fused(x: Tensor, name: str) -> bool:
     return name in Tensor.ops[x.device]
+
+
+# BatchNorm has no host arithmetic in this package (the device op is one fused kernel; CPU math
+# is the reference's job).  The test-suite plugs the reference's composition of primitives in
+# here to run the same model code on the NumPy oracle (oracle/host_layers.py).
+_HOST_FORWARD = {}
+
+
+def set_host_forward(layer_name: str, fn) -> None:
+    _HOST_FORWARD[layer_name] = fn
+
+
+def _host_forward(layer, x: Tensor) -> Tensor:
+    fn = _HOST_FORWARD.get(type(layer).__name__)
+    if fn is None:
+        raise Exception(f"nanograd_b200 ships the Device.GPU {type(layer).__name__} only; move the model and its "
+                        "input with .gpu() (or run the reference nanograd for CPU math).")
+    return fn(layer, x)
 
 
 class Module:
@@ -212,21 +231,7 @@ class BatchNorm1d(Module):
                                 training=bool(self.is_train))
             out.name = "bn_1d_res"
             return out
-        if self.is_train:
-            batch_mean = x.mean(0)
-            centered_sq = (x - batch_mean.reshape(shape=[1, -1])) ** 2
-            batch_var = centered_sq.mean(0)
-            batch_empirical_var = ((x - batch_mean.reshape(shape=[1, -1])) ** 2).sum(axis=0) / (x.shape[0] - 1)
-            self.running_mean = (1. - self.momentum) * self.running_mean + self.momentum * batch_mean
-            self.running_var = (1. - self.momentum) * self.running_var + self.momentum * batch_empirical_var
-            return self._normalize(x, batch_mean, batch_var)
-        return self._normalize(x, self.running_mean, self.running_var)
-
-    def _normalize(self, x: Tensor, mean: Tensor, var: Tensor) -> Tensor:
-        x_hat = (x - mean.reshape(shape=[1, -1])) / (var + self.eps).sqrt().reshape(shape=[1, -1])
-        out = self.weight.reshape(shape=[1, -1]) * x_hat + self.bias.reshape(shape=[1, -1])
-        out.name = "bn_1d_res"
-        return out
+        return _host_forward(self, x)
 
 
 class BatchNorm2d(Module):
@@ -251,21 +256,7 @@ class BatchNorm2d(Module):
             out.name = 'bn_2d_res'
             return out
         assert not relu, "the fused BatchNorm2d+ReLU path exists on the device namespace only"
-        if self.is_train:
-            batch_mean = x.mean(axis=(0, 2, 3))
-            batch_var = ((x - batch_mean.reshape(shape=[1, -1, 1, 1])) ** 2).mean(axis=(0, 2, 3))
-            batch_empirical_var = (((x - batch_mean.reshape(shape=[1, -1, 1, 1])) ** 2).sum(axis=(0, 2, 3)) /
-                                   (np.prod([x.shape[i] for i in [0, 2, 3]]) - 1))
-            self.running_mean = (1. - self.momentum) * self.running_mean + self.momentum * batch_mean
-            self.running_var = (1. - self.momentum) * self.running_var + self.momentum * batch_empirical_var
-            return self._normalize(x, batch_mean, batch_var)
-        return self._normalize(x, self.running_mean, self.running_var)
-
-    def _normalize(self, x: Tensor, mean: Tensor, var: Tensor) -> Tensor:
-        x_hat = (x - mean.reshape(shape=[1, -1, 1, 1])) * self.weight.reshape(shape=[1, -1, 1, 1])
-        out = x_hat / ((var + self.eps).reshape(shape=[1, -1, 1, 1]).sqrt()) + self.bias.reshape(shape=[1, -1, 1, 1])
-        out.name = 'bn_2d_res'
-        return out
+        return _host_forward(self, x)
 
 
 class Conv1d(Module):

@@ -90,7 +90,8 @@ def _collapse(out_shape, sa, sb):
 
 def _binary(op, a, b):
     """out = f(a, b) with NumPy broadcasting; Python scalars ride as kernel immediates."""
-    a_scalar, b_scalar = isinstance(a, ScalarBuffer), isinstance(b, ScalarBuffer)
+    a_scalar = isinstance(a, ScalarBuffer) and a.immediate
+    b_scalar = isinstance(b, ScalarBuffer) and b.immediate
     if b_scalar and not a_scalar:
         out = DeviceBuffer(a.shape if len(a.shape) >= 1 else (1,))
         _lib().ng_binary_scalar(op, out.ptr, a.ptr, b.value, 0, a.size)
@@ -178,7 +179,7 @@ def _broadcast_to(buf, shape):
 
 def _scalar_int(v):
     """Positional non-Tensor arguments arrive as 1-element buffers (tensor.py:482-483)."""
-    if isinstance(v, ScalarBuffer):
+    if isinstance(v, ScalarBuffer) and v.immediate:
         return int(v.value)
     if isinstance(v, DeviceBuffer):
         return int(v.numpy().reshape(-1)[0])

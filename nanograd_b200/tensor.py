@@ -26,7 +26,7 @@ from typing import Union
 import numpy as np
 
 from nanograd_b200.device import Device
-from nanograd_b200.nn.buffer import DeviceBuffer, GPUBuffer, ScalarBuffer
+from nanograd_b200.nn.buffer import DeviceBuffer, ScalarBuffer
 from nanograd_b200.viz.comp_graph import BackwardGraphVisualizer, ForwardGraphVisualizer
 
 
@@ -173,7 +173,15 @@ class Tensor:
                     tensor.grad = tensor.grad + Tensor(grad, device=self.device, requires_grad=False)
 
     def copy(self):
-        return Tensor(self.data, device=self.device)
+        """Independent snapshot of the values (tensor.py:245-246).  On Device.GPU the optimizers
+        update parameters in place, so the copy owns its own allocation (one d2d copy)."""
+        if isinstance(self.data, DeviceBuffer):
+            from nanograd_b200 import backend
+            dup = DeviceBuffer(self.data.shape)
+            if dup.size:
+                backend.lib().ng_d2d(dup.ptr, self.data.ptr, dup.size * 4)
+            return Tensor(dup, device=self.device)
+        return Tensor(np.array(self.data, copy=True), device=self.device)
 
     def __str__(self):
         return f"<NanoTensor({str(self.data)}, name={self.name}, device={self.device}>"

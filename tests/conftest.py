@@ -16,10 +16,8 @@ def pytest_configure(config):
 def _oracle_cpu_namespace():
     """Tests run identical model code on both devices: the NumPy oracle is registered as the
     Device.CPU operator namespace (test infrastructure only — the package ships GPU ops only)."""
-    from nanograd_b200.device import Device
-    from nanograd_b200.tensor import register_ops
-    from oracle import cpu_namespace
-    register_ops(cpu_namespace, device=Device.CPU)
+    import oracle
+    oracle.register_host()
     yield
 
 

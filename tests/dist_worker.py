@@ -21,10 +21,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import helpers as H  # noqa: E402
 from nanograd_b200 import dist  # noqa: E402
 from nanograd_b200.device import Device  # noqa: E402
-from nanograd_b200.tensor import Tensor, register_ops  # noqa: E402
+from nanograd_b200.tensor import Tensor  # noqa: E402
 import nanograd_b200.nn.module as nn  # noqa: E402
 import nanograd_b200.optim.optimizer as optim  # noqa: E402
-from oracle import cpu_namespace  # noqa: E402
+import oracle  # noqa: E402
 
 GLOBAL_BATCH = 32
 
@@ -48,7 +48,7 @@ def step(model, opt, X, Y, device):
 
 def main():
     mode = sys.argv[1]
-    register_ops(cpu_namespace, device=Device.CPU)  # the oracle: checker, never the measured path
+    oracle.register_host()  # the oracle: checker, never the measured path
     rng = np.random.RandomState(7)
     X = rng.rand(GLOBAL_BATCH, 784).astype(np.float32)
     Y = rng.randint(0, 10, GLOBAL_BATCH).astype(np.float32)

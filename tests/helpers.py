@@ -6,6 +6,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFERENCE_ROOT = "/root/reference"
+# the unmodified reference pip-installed by tools/make_oracle_ref.sh (git-ignored, shipped to the GPU box)
+REFERENCE_INSTALL = os.path.join(ROOT, "oracle", "_ref")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 # FP32 parity bar of BASELINE.json's north_star: rtol 1e-4 (1e-2 in TF32 mode), evaluated
@@ -40,15 +42,17 @@ _REF = None
 
 
 def load_reference():
-    """Import the real reference (read-only /root/reference) next to this repo's packages.
+    """Import the real reference next to this repo's packages: /root/reference (the build
+    container) or its pip-installed copy oracle/_ref (the GPU box; tools/make_oracle_ref.sh).
 
-    Returns a dict of its modules, or None when the reference is not present (the GPU box).
+    Returns a dict of its modules, or None when neither is present.
     The reference imports ``graphviz`` unconditionally; tests/_shim carries a stub.
     """
     global _REF
     if _REF is not None:
         return _REF or None
-    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "nanograd")):
+    root = next((r for r in (REFERENCE_ROOT, REFERENCE_INSTALL) if os.path.isdir(os.path.join(r, "nanograd"))), None)
+    if root is None:
         _REF = {}
         return None
     import importlib
@@ -59,10 +63,12 @@ def load_reference():
     sys.dont_write_bytecode = True  # /root/reference is read-only
     try:
         sys.path.insert(0, shim)
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.insert(0, root)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             mods = {
+                "root": root,
+                "package": importlib.import_module("nanograd"),
                 "tensor": importlib.import_module("nanograd.tensor"),
                 "module": importlib.import_module("nanograd.nn.module"),
                 "optim": importlib.import_module("nanograd.optim.optimizer"),
