@@ -230,6 +230,7 @@ def _train(fw, model, opt_name, X, Y, steps, criterion):
     fw.place(model)
     opt = _make_optimizer(fw, opt_name, model.parameters())
     rec = {}
+    history = []
     for step in range(steps):
         xb, yb = fw.tensor(X), fw.tensor(Y)
         out = model(xb)
@@ -242,7 +243,10 @@ def _train(fw, model, opt_name, X, Y, steps, criterion):
             for i, p in enumerate(model.parameters()):
                 rec[f"grad{i}"] = fw.numpy(p.grad)
         opt.step()
+        history.append(fw.numpy(loss))
     rec["loss_last"] = fw.numpy(loss)
+    if steps > 2:
+        rec["loss_history"] = np.concatenate([np.asarray(h, dtype=np.float64).reshape(-1) for h in history])
     for i, p in enumerate(model.parameters()):
         rec[f"param{i}"] = fw.numpy(p)
     return rec
@@ -387,6 +391,10 @@ def all_cases():
     cases["batchnorm1d"] = (case_batchnorm1d, {})
     for o in ("sgd", "sgdm", "adam", "adamw"):
         cases[f"mnist_cnn_{o}"] = (case_mnist_cnn, dict(opt_name=o))
+    # multi-step trajectories: bound how far rounding differences are amplified over 10 optimizer steps
+    cases["mnist_cnn_adam_10steps"] = (case_mnist_cnn, dict(opt_name="adam", steps=10))
+    cases["mnist_cnn_sgdm_10steps"] = (case_mnist_cnn, dict(opt_name="sgdm", steps=10))
+    cases["vgg_wide_adam_8steps"] = (case_vgg_bn, dict(opt_name="adam", widths=(32, 64), hw=16, batch=16, steps=8))
     cases["vgg_bn_adam"] = (case_vgg_bn, dict(opt_name="adam"))
     cases["vgg_bn_sgd"] = (case_vgg_bn, dict(opt_name="sgd"))
     # shapes that the tcgen05 TF32 path accepts (channel counts multiple of 32)
@@ -406,5 +414,22 @@ def all_cases():
     return cases
 
 
-# integer-valued results that must match bit-exactly
+# integer-valued / selection results that must match bit-exactly: one-hot labels, max-pool outputs (a
+# maximum of float32 inputs is one of them, whatever the evaluation order)
 EXACT_KEYS = {"logsoftmax_nll": ["onehot"]}
+# gradients whose *support* must match bit-exactly: max-pool's dx is mask * g / count with a dense random
+# g, so (dx != 0) is Max.backward's equality mask (ops_cpu.py:121-127) — the north-star's "argmax indices"
+MASK_KEYS = {}
+for _p in range(1, 5):
+    EXACT_KEYS[f"maxpool2d_p{_p}"] = ["y"]
+    MASK_KEYS[f"maxpool2d_p{_p}"] = ["dx"]
+for _p in range(1, 4):
+    EXACT_KEYS[f"maxpool1d_p{_p}"] = ["y"]
+    MASK_KEYS[f"maxpool1d_p{_p}"] = ["dx"]
+
+# Multi-step cases: gradients/outputs of step 0 keep the one-step bar; the end of the trajectory
+# (loss_history, loss_last, post-step parameters) is compared at this looser bar because every
+# implementation — the float64-drifting oracle included — amplifies 1e-7 rounding differences
+# through 8-10 optimizer steps (Adam divides by sqrt(v) ~ |g|).
+# Measured on the FP32 SIMT kernels: 7e-6 / 4e-7 / 1.0e-4 (profiles/README.md keeps the GPU numbers).
+TRAJECTORY_RTOL = {"mnist_cnn_adam_10steps": 2e-4, "mnist_cnn_sgdm_10steps": 1e-4, "vgg_wide_adam_8steps": 1e-3}

@@ -21,12 +21,15 @@ EMU_SUBSET = (
     + ["matmul", "maxpool2d_p2", "maxpool2d_p3", "avgpool2d_p2", "avgpool2d_p4", "maxpool1d_p2", "avgpool1d_p3",
        "logsoftmax_nll", "elementwise", "reductions", "shapes", "batchnorm2d", "batchnorm1d",
        "mnist_cnn_sgd", "vgg_bn_sgd", "attention_adamw", "tinynet_sgdm", "tinynet_adam", "tinynet_adamw2",
-       "linear_stack", "conv2d_wide_c64_k32_p1", "activation_mlp_sgdm", "activation_mlp_adam"]
+       "linear_stack", "conv2d_wide_c64_k32_p1", "activation_mlp_sgdm", "activation_mlp_adam",
+       "mnist_cnn_adam_10steps"]
 )
 
 # cases whose convolutions the tensor-core path accepts; run in TF32 mode at the north-star's TF32 bar
 TF32_CASES = ["conv2d_wide_c32_k64", "conv2d_wide_c64_k32_p1", "conv2d_wide_c128_k128_p1", "mnist_cnn_sgd",
               "mnist_cnn_sgdm", "vgg_wide_sgd", "vgg_wide_adam"]
+# multi-step trajectories in both FP32-accurate engines (bar: cases.TRAJECTORY_RTOL)
+TRAJECTORY_CASES = ["mnist_cnn_adam_10steps", "mnist_cnn_sgdm_10steps", "vgg_wide_adam_8steps"]
 
 
 def _run(name):
@@ -65,6 +68,26 @@ def test_case_matches_reference_golden_on_b200_fp32_engines(name, mode):
     keys = _keys_for_tensor_core_modes(name, want)
     H.compare_case(name, {k: got[k] for k in keys}, {k: want[k] for k in keys}, H.RTOL_FP32,
                    cases.EXACT_KEYS.get(name, ()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["simt", "tf32x3"])
+@pytest.mark.parametrize("name", TRAJECTORY_CASES)
+def test_multi_step_trajectory_matches_reference_on_b200(name, mode):
+    """8-10 optimizer steps: step-0 outputs and gradients at rtol 1e-4, the loss history and the final
+    parameters at cases.TRAJECTORY_RTOL, in both FP32-accurate engines (this bounds how far the two
+    engines can drift apart over a run)."""
+    from nanograd_b200 import backend
+    H.use_cuda_library()
+    backend.set_math_mode(mode)
+    try:
+        fn, kwargs = CASES[name]
+        with np.errstate(all="ignore"):
+            got = fn(H.device_framework(Device.GPU), **kwargs)
+    finally:
+        backend.set_math_mode("fp32")
+    want = H.golden(name)
+    H.compare_case(name, got, {k: want[k] for k in want.files}, H.RTOL_FP32)
 
 
 def _keys_for_tensor_core_modes(name, want):
