@@ -22,9 +22,14 @@ Printed JSON line (rank 0):
   conv2d_sweep BASELINE config 1 (Conv2d 3x3, 32x32, BS 256, C=K in 16..256): TFLOP/s per pass
   mnist_cnn    BASELINE config 0 (README MNIST CNN, BS 128, SGD) images/s on the device
 
---impl reference times the reference's CPU implementation of the same step (the oracle port:
-the reference is pure Python and /root/reference does not exist on the GPU box) on all host
-cores, each step a bounded sample (batch 64) of the workload.
+--impl reference times the UNMODIFIED reference (PABannier/nanograd pip-installed into the
+git-ignored oracle/_ref by tools/make_oracle_ref.sh, which travels to the GPU box; /root/reference
+in the build container; the oracle port only if neither exists) through its own public API —
+its Tensor / nn.Sequential / Adam / NLLLoss on Device.CPU — on all host cores, for the same model,
+optimizer and loss.  Each of the W + K steps is one full training step on a bounded sample of
+the workload's batch (64 of the 512 images: the NumPy path runs ~10 images/s, a 512-image step
+costs ~30-60 s and, through the lru_cache on Tensor.build_graph_topology, ~20 GB of host memory
+that is never released); images/s does not depend on the sample size to within a few percent.
 """
 import argparse
 import ctypes
@@ -130,24 +135,75 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arms
+def _import_reference():
+    """The unmodified reference as an importable package: oracle/_ref (pip-installed copy, present on
+    the GPU box) or /root/reference (build container).  Returns (modules, where) or (None, why)."""
+    import importlib
+    import warnings
+    for root in (os.path.join(ROOT, "oracle", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(root, "nanograd", "tensor.py")):
+            sys.path.insert(0, os.path.join(ROOT, "tests", "_shim"))   # 4-line graphviz stand-in
+            sys.path.insert(0, root)
+            sys.dont_write_bytecode = True
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                mods = {k: importlib.import_module(f"nanograd.{k}") for k in
+                        ("tensor", "nn.module", "optim.optimizer", "device")}
+            return mods, root
+    return None, "neither oracle/_ref nor /root/reference holds the reference"
+
+
+def reference_images_per_sec(steps, warmup, batch=CPU_SAMPLE_BATCH):
+    """The real reference, one continuous run: model and Adam built once, W + K training steps
+    (so the NumPy path's drift to float64 after its first optimizer step is part of what is timed,
+    as it is for any user of the reference).  The lru_cache of Tensor.build_graph_topology is cleared
+    between steps — it would otherwise keep every step's graph and activations alive."""
+    import warnings
+    warnings.simplefilter("ignore")      # the reference's Pow.backward takes log of negative bases (ops_cpu.py:251)
+    np.seterr(all="ignore")
+    mods, where = _import_reference()
+    if mods is None:
+        return None, where
+    T, nn, optim = mods["tensor"], mods["nn.module"], mods["optim.optimizer"]
+    np.random.seed(0)
+    model = build_model(nn)
+    opt = optim.Adam(model.parameters(), lr=LR)
+    crit = nn.NLLLoss()
+    rng = np.random.RandomState(0)
+    times = []
+    for i in range(warmup + steps):
+        X = rng.randn(batch, 3, 32, 32).astype(np.float32)
+        Y = rng.randint(0, 10, batch).astype(np.float32)
+        t0 = time.perf_counter()
+        loss = train_step(model, opt, crit, T.Tensor(X), T.Tensor(Y))
+        float(loss.data[0])
+        dt = time.perf_counter() - t0
+        cache_clear = getattr(T.Tensor.build_graph_topology, "cache_clear", None)
+        if cache_clear:
+            cache_clear()
+        if i >= warmup:
+            times.append(dt)
+    return (batch / float(np.mean(times)), float(np.mean(times))), where
+
+
 def cpu_oracle_images_per_sec(steps, warmup, batch=CPU_SAMPLE_BATCH):
-    """The oracle port of the reference's NumPy path: this repo's device-agnostic Tensor/Module/
-    Optimizer code on Device.CPU with oracle/cpu_namespace registered (composition of primitives,
-    exactly the reference's graph).  Parameters are re-created before each timed step so every
-    step starts in float32 like the reference's first step (it drifts to float64 afterwards)."""
+    """Fallback when the reference itself is not importable: the oracle port of its NumPy path (this
+    repo's host mirror on Device.CPU with oracle/ registered: the reference's graph, primitive by
+    primitive), one continuous run like reference_images_per_sec."""
     import nanograd_b200.nn.module as nn
     import nanograd_b200.optim.optimizer as optim
-    from nanograd_b200.device import Device
     from nanograd_b200.tensor import Tensor
     import oracle
     oracle.register_host()
-    X, Y = synthetic_batch(batch, seed=0)
+    np.random.seed(0)
+    model = build_model(nn)
+    opt = optim.Adam(model.parameters(), lr=LR)
+    crit = nn.NLLLoss()
+    rng = np.random.RandomState(0)
     times = []
     for i in range(warmup + steps):
-        np.random.seed(0)
-        model = build_model(nn)
-        opt = optim.Adam(model.parameters(), lr=LR)
-        crit = nn.NLLLoss()
+        X = rng.randn(batch, 3, 32, 32).astype(np.float32)
+        Y = rng.randint(0, 10, batch).astype(np.float32)
         t0 = time.perf_counter()
         loss = train_step(model, opt, crit, Tensor(X), Tensor(Y))
         float(loss.data[0])
@@ -157,11 +213,37 @@ def cpu_oracle_images_per_sec(steps, warmup, batch=CPU_SAMPLE_BATCH):
     return batch / float(np.mean(times)), float(np.mean(times))
 
 
+def cpu_arm(steps, warmup):
+    """(images/s, s per step, kind, description of what was run)."""
+    res, where = reference_images_per_sec(steps, warmup)
+    if res is not None:
+        return res[0], res[1], "reference", f"unmodified PABannier/nanograd 1.0.4 imported from {os.path.relpath(where, ROOT)}"
+    ips, sec = cpu_oracle_images_per_sec(steps, warmup)
+    return ips, sec, "port", f"oracle port ({where})"
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def workload_config(world, n_params=2198602, math_mode="fp32"):
+    """The `config` object of the JSON line — identical for both arms (the reference arm runs the same
+    workload definition; what it samples per step is said in cpu_baseline.sample)."""
+    return {"workload": WORKLOAD, "global_batch": PER_GPU_BATCH * world, "per_gpu_batch": PER_GPU_BATCH,
+            "image": "3x32x32", "optimizer": "Adam(lr=1e-3)", "loss": "log_softmax + NLLLoss",
+            "params": n_params, "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": "no flush: one step touches ~1.9 GB of activations, far larger than the 126 MB L2",
+            "math": MATH_TEXT[math_mode]}
+
+
+MATH_TEXT = {"fp32": "FP32-accurate: tcgen05 tensor-core conv with 3xTF32 error compensation where the shape is "
+                     "supported, FP32 SIMT (FFMA) elsewhere (first conv layer, GEMMs)",
+             "tf32x3": "FP32-accurate 3xTF32 tcgen05 conv forced for every supported shape",
+             "simt": "FP32 SIMT (FFMA) implicit-GEMM conv / GEMM only",
+             "tf32": "TF32 tcgen05 tensor-core conv (FP32 accumulate), FP32 SIMT elsewhere"}
 
 
 def run_reference_arm(args):
@@ -170,16 +252,16 @@ def run_reference_arm(args):
         return
     cores = host_threads()
     steps, warmup = max(args.steps, 1), max(args.warmup, 0)
-    # keep the whole run within a few minutes: ~3-6 s per sampled step
-    steps, warmup = min(steps, 20), min(warmup, 3)
-    ips, sec = cpu_oracle_images_per_sec(steps, warmup)
-    sample = f"{steps} steps of batch {CPU_SAMPLE_BATCH} (of {PER_GPU_BATCH}) of the same model/optimizer, float32 in"
+    ips, sec, kind, what = cpu_arm(steps, warmup)
+    sample = (f"{what}; {warmup} warm-up + {steps} timed training steps, each on {CPU_SAMPLE_BATCH} of the workload's "
+              f"{PER_GPU_BATCH} images (same model, Adam, log_softmax + NLLLoss), {sec:.2f} s per step, float32 inputs "
+              f"(the NumPy path computes in float64 from its first optimizer step on)")
     line = {
         "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (NumPy, drifts to f64)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "per_step_sample_batch": CPU_SAMPLE_BATCH},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -411,43 +493,70 @@ KERNEL_NAMES = {
 KERNEL_NAMES["tf32x3"] = KERNEL_NAMES["fp32"]
 
 
-def roofline_object(m, math_mode, peaks, peak_src):
+def pick_peak(peaks, clocks):
+    """Burst or sustained tensor peak?  MEASURED_PEAKS.json holds the dense bf16 cuBLAS rate measured
+    best-of-10 (burst: SM clock at its maximum) and back-to-back for 4 s (sustained: the clock has
+    dropped to ~1.3 GHz under the power cap).  The figure that applies is the one whose clock matches
+    the SM clock this run actually held during the timed region (nvidia-smi samples)."""
+    burst = float(peaks.get("bf16_tflops", 0.0))
+    sustained = float(peaks.get("bf16_tflops_sustained", burst))
+    sm, mx = (clocks or {}).get("sm_mhz"), (clocks or {}).get("sm_max_mhz")
+    if sm and mx and sm < 0.85 * mx:
+        return sustained, "sustained", burst, sustained
+    return burst, "burst", burst, sustained
+
+
+def roofline_object(m, math_mode, peaks, peak_src, clocks=None):
     """Roofline of the dominant contraction class.
     simt: the FFMA pipe bounds it (peak = FFMA-saturating microkernel measured in this run).
     tf32: the tensor pipe bounds it; dense TF32 peak = 1/2 of the measured dense BF16 GEMM rate of
-          MEASURED_PEAKS.json (sustained figure: the kernels are timed inside a long step).
+          MEASURED_PEAKS.json — the burst figure when the SM clock held its maximum over the timed
+          region, the sustained one when it did not (pick_peak).
     fp32 / tf32x3 (FP32-accurate 3xTF32 on tensor cores): three TF32 MMAs per useful FP32 MAC, so the
-          peak for useful FLOPs is the TF32 peak / 3."""
+          peak for useful FLOPs is the TF32 peak / 3.  Both fractions and the raw tensor-pipe fraction
+          (MMA FLOPs issued / dense TF32 peak) are printed next to `frac`."""
     prof, K = m["prof"], m["K"]
-    dominant = max(prof, key=lambda k: prof[k]["ms"])
+    contraction = {k: v for k, v in prof.items() if k in ("conv_fprop", "conv_dgrad", "conv_wgrad", "gemm")}
+    dominant = max(contraction, key=lambda k: contraction[k]["ms"])
     d = prof[dominant]
     achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
-    kernel_ms = sum(v["ms"] for v in prof.values())
-    bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)))
+    kernel_ms = sum(v["ms"] for v in contraction.values())
+    bf16, which, burst, sustained = pick_peak(peaks, clocks)
+    extra = {}
     if math_mode == "simt":
         bound, peak = "fp32_ffma", m["ffma_peak"]
         src = ("FFMA-saturating microkernel measured in this run (nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4); "
                "no FP32 tensor-core MMA exists, so the tensor peak of %s does not bound this mode" % peak_src)
-    elif math_mode == "tf32":
-        bound, peak = "tensor", 0.5 * bf16
-        src = "dense TF32 = 1/2 of the measured sustained dense bf16 GEMM rate in %s (%.1f TFLOP/s)" % (peak_src, bf16)
     else:
-        bound, peak = "tensor", 0.5 * bf16 / 3.0
-        src = ("useful-FLOP peak of the FP32-accurate 3xTF32 scheme = dense TF32 (1/2 of the measured sustained bf16 "
-               "rate in %s, %.1f TFLOP/s) / 3 MMAs per FP32 MAC; for scale, the measured FFMA peak of the SIMT "
-               "alternative is %.1f TFLOP/s" % (peak_src, bf16, m["ffma_peak"]))
-    return {
+        mma_per_mac = 1.0 if math_mode == "tf32" else 3.0
+        bound, peak = "tensor", 0.5 * bf16 / mma_per_mac
+        src = ("%s = dense TF32 (1/2 of the measured %s dense bf16 GEMM rate in %s, %.1f TFLOP/s: the SM clock held "
+               "%s of %s MHz over the timed region)%s" % (
+                   "dense TF32 peak" if mma_per_mac == 1 else "useful-FLOP peak of the FP32-accurate 3xTF32 scheme",
+                   which, peak_src, bf16, (clocks or {}).get("sm_mhz"), (clocks or {}).get("sm_max_mhz"),
+                   "" if mma_per_mac == 1 else " / 3 MMAs per FP32 MAC; for scale, the measured FFMA peak of the SIMT "
+                   "alternative is %.1f TFLOP/s" % m["ffma_peak"]))
+        extra = {"frac_vs_burst_peak": round(achieved / (0.5 * burst / mma_per_mac), 4) if burst else None,
+                 "frac_vs_sustained_peak": round(achieved / (0.5 * sustained / mma_per_mac), 4) if sustained else None,
+                 "tensor_pipe_frac_of_dense_tf32": round(achieved * mma_per_mac / (0.5 * bf16), 4) if bf16 else None,
+                 "useful_frac_of_dense_tf32": round(achieved / (0.5 * bf16), 4) if bf16 else None,
+                 "peak_kind": which}
+    out = {
         "kernel": KERNEL_NAMES[math_mode][dominant], "bound": bound, "achieved": round(achieved, 2),
         "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(achieved / peak, 4) if peak else None,
         "traffic": ncu_traffic(math_mode + ":" + dominant), "peak_source": src,
         "avg_launch_ms": round(d["ms"] / max(d["launches"], 1), 4), "launches": d["launches"],
+        "class_flops_per_step": d["flops"] / K, "class_ms_per_step": round(d["ms"] / K, 4),
         "share_of_step": round(d["ms"] / (m["ms_per_step"] * K), 4),
         "contraction_share_of_step": round(kernel_ms / (m["ms_per_step"] * K), 4),
         "per_class": {k: {"ms_per_step": round(v["ms"] / K, 4), "launches_per_step": v["launches"] / K,
-                          "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None}
-                      for k, v in prof.items()},
+                          "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 and v["flops"] > 0 else None,
+                          "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 and v["bytes"] > 0 else None}
+                      for k, v in prof.items() if v["launches"]},
         "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_src,
     }
+    out.update(extra)
+    return out
 
 
 def run_device_arm(args):
@@ -477,11 +586,6 @@ def run_device_arm(args):
         return
 
     K, W = m["K"], m["W"]
-    math_text = {"fp32": "FP32-accurate: tcgen05 tensor-core conv with 3xTF32 error compensation where the shape is "
-                         "supported, FP32 SIMT (FFMA) elsewhere (first conv layer, GEMMs)",
-                 "tf32x3": "FP32-accurate 3xTF32 tcgen05 conv forced for every supported shape",
-                 "simt": "FP32 SIMT (FFMA) implicit-GEMM conv / GEMM only",
-                 "tf32": "TF32 tcgen05 tensor-core conv (FP32 accumulate), FP32 SIMT elsewhere"}
     notes = {"simt_mode": "same workload restricted to the FP32 SIMT (FFMA) kernels (NANOGRAD_B200_MATH=simt)",
              "tf32_mode": "same workload with the opt-in plain-TF32 tensor-core convolutions (NANOGRAD_B200_MATH=tf32; "
                           "parity bar rtol 1e-2); reduced precision, hence not the headline value"}
@@ -489,22 +593,18 @@ def run_device_arm(args):
         "metric": "train_images_per_sec", "value": round(m["value"], 1), "unit": "images/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": round(m["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32" if main_mode == "tf32" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": PER_GPU_BATCH * world, "per_gpu_batch": PER_GPU_BATCH,
-                   "image": "3x32x32", "optimizer": "Adam(lr=1e-3)", "loss": "log_softmax + NLLLoss",
-                   "params": m["n_params"], "parallelism": f"dp{world}" if world > 1 else "single",
-                   "l2": "no flush: one step touches ~1.9 GB of activations, far larger than the 126 MB L2",
-                   "math": math_text[main_mode]},
+        "config": workload_config(world, m["n_params"], main_mode),
         "e2e": {"value": round(m["e2e_value"], 1), "unit": "images/s", "ms_per_step": round(m["e2e_ms"], 4),
                 "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4},
         "gpu_launches": m["launches"], "launches_per_step": m["launches"] / K, "loss": m["loss"],
-        "clocks": m["clocks"], "roofline": roofline_object(m, main_mode, peaks, peak_src),
+        "clocks": m["clocks"], "roofline": roofline_object(m, main_mode, peaks, peak_src, m["clocks"]),
     }
     for key, (mode, o) in others.items():
         line[key] = {
             "note": notes[key], "value": round(o["value"], 1), "unit": "images/s", "ms_per_step": round(o["ms_per_step"], 4),
             "e2e": {"value": round(o["e2e_value"], 1), "unit": "images/s", "ms_per_step": round(o["e2e_ms"], 4),
                     "h2d_bytes_per_step": o["h2d"], "d2h_bytes_per_step": 4},
-            "gpu_launches": o["launches"], "loss": o["loss"], "roofline": roofline_object(o, mode, peaks, peak_src)}
+            "gpu_launches": o["launches"], "loss": o["loss"], "roofline": roofline_object(o, mode, peaks, peak_src, m["clocks"])}
 
     if world == 1 and not args.no_extras:
         ffma = m["ffma_peak"]
@@ -513,11 +613,11 @@ def run_device_arm(args):
                                 "rows": conv2d_sweep(B, lib, ffma)}
         line["mnist_cnn"] = mnist_cnn_images_per_sec(B)
         t0 = time.perf_counter()
-        cpu_ips, cpu_sec = cpu_oracle_images_per_sec(steps=2, warmup=1)
+        cpu_ips, cpu_sec, kind, what = cpu_arm(steps=3, warmup=1)
         line["cpu_baseline"] = {
-            "value": round(cpu_ips, 2), "unit": "images/s", "cores": host_threads(), "kind": "port",
-            "sample": f"2 steps (+1 warm-up) of batch {CPU_SAMPLE_BATCH} (of {PER_GPU_BATCH}), same model/optimizer, "
-                      f"{cpu_sec:.2f} s per step, {time.perf_counter() - t0:.1f} s total"}
+            "value": round(cpu_ips, 2), "unit": "images/s", "cores": host_threads(), "kind": kind,
+            "sample": f"{what}; 3 training steps (+1 warm-up) on {CPU_SAMPLE_BATCH} of the workload's {PER_GPU_BATCH} images, "
+                      f"same model/optimizer, {cpu_sec:.2f} s per step, {time.perf_counter() - t0:.1f} s total"}
     print(json.dumps(line), flush=True)
     dist.shutdown()
 

@@ -77,3 +77,53 @@ def test_checkpoint_roundtrip_emulated_device(tmp_path):
 def test_checkpoint_roundtrip_on_b200(tmp_path):
     H.use_cuda_library()
     _roundtrip(Device.GPU, tmp_path)
+
+
+def _swish_net():
+    import nanograd_b200.nn.module as nn
+    np.random.seed(3)
+    return nn.Sequential(nn.Linear(6, 5), nn.Swish(), nn.Linear(5, 2))
+
+
+def test_checkpoint_with_a_0d_parameter_saved_after_a_step(tmp_path):
+    """Swish's learnt beta is 0-d at construction and (1,) after an optimizer step (the reference's
+    broadcasting quirk, mirrored by the device step): a save-after-step loads into a fresh model."""
+    import nanograd_b200.nn.module as nn
+    import nanograd_b200.optim.optimizer as optim
+    H.use_emulated_library()
+    net = _swish_net().gpu()
+    opt = optim.Adam(net.parameters(), lr=1e-2)
+    x = Tensor(np.random.randn(4, 6).astype(np.float32), device=Device.GPU)
+    nn.MSELoss()(net(x), Tensor(np.zeros((4, 2), dtype=np.float32), device=Device.GPU)).backward()
+    opt.step()
+    path = str(tmp_path / "swish.npz")
+    checkpoint.save(path, net, opt)
+    fresh = _swish_net().gpu()
+    fresh_opt = optim.Adam(fresh.parameters(), lr=1e-2)
+    checkpoint.load(path, fresh, fresh_opt)
+    for a, b in zip(net.parameters(), fresh.parameters()):
+        np.testing.assert_array_equal(a.numpy().reshape(-1), b.numpy().reshape(-1))
+    assert fresh_opt.t == 1
+
+
+def test_checkpoint_refuses_a_reordered_model(tmp_path):
+    import nanograd_b200.nn.module as nn
+    H.use_emulated_library()
+
+    class A(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.first = nn.Linear(4, 4)
+            self.second = nn.Linear(4, 4)
+
+    class B(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.second = nn.Linear(4, 4)
+            self.first = nn.Linear(4, 4)
+
+    path = str(tmp_path / "order.npz")
+    checkpoint.save(path, A())
+    with pytest.raises(Exception, match="parameter order differs"):
+        checkpoint.load(path, B())
+    checkpoint.load(path, A())

@@ -131,3 +131,41 @@ def test_graph_visualiser_draws_forward_and_backward_graphs():
     for g in (fwd, bwd):
         src = g.source if isinstance(g.source, str) else g.source()
         assert src.count("->") >= 3, src      # edges for mul, add, sum
+
+
+def test_graph_visualiser_on_device_tensors(device_lib):
+    """The same plots for a model on Device.GPU (host emulation in the CPU suite, the B200 under -m gpu):
+    node labels come from ``.shape`` / ``.op`` only, nothing is copied off the device, and a no-grad
+    inference chain keeps no edges (and therefore pins no device buffers)."""
+    import nanograd_b200.nn.module as nn
+    from nanograd_b200 import backend
+    from nanograd_b200.tensor import Tensor
+    np.random.seed(0)
+    model = H.build_mnist_cnn(nn).gpu()
+    x = Tensor(np.random.rand(4, 784).astype(np.float32), device=Device.GPU)
+    y = Tensor(np.random.randint(0, 10, 4).astype(np.float32), device=Device.GPU)
+    loss = nn.NLLLoss()(model(x), y)
+    loss.backward()
+    launches = backend.launch_count()
+    fwd, bwd = loss.plot_forward(), loss.plot_backward()
+    assert backend.launch_count() == launches            # drawing launches nothing on the device
+    for g in (fwd, bwd):
+        src = g.source if isinstance(g.source, str) else g.source()
+        assert src.count("->") >= 10, src                # conv, relu, pool, conv, relu, pool, reshape, linear, ...
+    ops = {n.op for n in _walk(loss)}
+    assert {"conv2dbias", "maxpool2d", "linear", "logsoftmax", "nllloss"} <= ops, ops
+    # inference chain: no requires_grad inputs -> no children retained
+    frozen = Tensor(np.random.rand(2, 5).astype(np.float32), device=Device.GPU)
+    out = (frozen * 2.0).relu().sum()
+    assert out.children == [] and out.ctx is None
+
+
+def _walk(root):
+    seen, stack = [], [root]
+    while stack:
+        n = stack.pop()
+        if any(n is s for s in seen):
+            continue
+        seen.append(n)
+        stack.extend(n.children)
+    return seen
