@@ -1,6 +1,6 @@
 // Multi-tensor optimizer steps (SGD / Adam / AdamW) and gradient-bucket pack / unpack.
 // One launch updates up to 48 parameter tensors; pointer tables ride in the kernel arguments
-// (no host->device copy per step).  HBM-bound: SGD 20 B/param (12 with momentum == 0 in the
+// (no host->device copy per step); 128-bit loads/stores, grid = exact chunk count.  HBM-bound: SGD 20 B/param (12 with momentum == 0 in the
 // reference's accounting), Adam/AdamW 28 B/param.
 //
 // The reference writes each step as 5-15 dispatched elementwise Tensor ops per parameter
@@ -13,6 +13,11 @@
 namespace ng {
 
 constexpr int kMT = 48;
+// One CTA updates one 4096-element chunk of one tensor: 256 threads x four 128-bit vectors per array,
+// all loads of a thread issued before the first use (Adam streams 4 arrays in, 3 out).  The CTA -> (tensor,
+// chunk) map is a prefix sum over per-tensor chunk counts carried in the kernel arguments, so the grid is
+// exactly the work (small bias vectors cost one CTA each instead of a full-width grid row).
+constexpr int kChunk = 256 * 4 * 4;
 
 struct MTArgs {
   float* p[kMT];
@@ -20,47 +25,96 @@ struct MTArgs {
   float* s1[kMT];
   float* s2[kMT];
   long long n[kMT];
+  int blk_start[kMT + 1];
 };
 
 struct SgdH { float lr, momentum, grad_scale; };
 struct AdamH { float lr, beta1, beta2, eps, bc1, bc2, decay_mul, step_size, grad_scale; int adamw; };
 
-__global__ void __launch_bounds__(256) multi_sgd_kernel(const __grid_constant__ MTArgs a, SgdH h) {
-  const int t = blockIdx.y;
-  float* p = a.p[t];
-  const float* g = a.g[t];
-  float* m = a.s1[t];
-  const long long n = a.n[t];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+struct SgdOp {
+  SgdH h;
+  static constexpr bool kTwoStates = false;
+  __device__ __forceinline__ void operator()(float& p, float g, float& m, float&) const {
     // optimizer.py:54-55: m = m*momentum + lr*g ; p = p - m
-    const float mi = m[i] * h.momentum + h.lr * (g[i] * h.grad_scale);
-    m[i] = mi;
-    p[i] = p[i] - mi;
+    const float mi = m * h.momentum + h.lr * (g * h.grad_scale);
+    m = mi;
+    p = p - mi;
   }
-}
+};
 
-__global__ void __launch_bounds__(256) multi_adam_kernel(const __grid_constant__ MTArgs a, AdamH h) {
-  const int t = blockIdx.y;
-  float* p = a.p[t];
-  const float* g = a.g[t];
-  float* m = a.s1[t];
-  float* v = a.s2[t];
-  const long long n = a.n[t];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * h.grad_scale;
-    const float mi = h.beta1 * m[i] + (1.f - h.beta1) * gi;
-    const float vi = h.beta2 * v[i] + (1.f - h.beta2) * (gi * gi);
-    m[i] = mi;
-    v[i] = vi;
+struct AdamOp {
+  AdamH h;
+  static constexpr bool kTwoStates = true;
+  __device__ __forceinline__ void operator()(float& p, float g, float& m, float& v) const {
+    const float gi = g * h.grad_scale;
+    const float mi = h.beta1 * m + (1.f - h.beta1) * gi;
+    const float vi = h.beta2 * v + (1.f - h.beta2) * (gi * gi);
+    m = mi;
+    v = vi;
     if (h.adamw) {
       // optimizer.py:125-128: p*(1 - lr*wd) - (lr/bc1) * (m / (sqrt(v/bc2) + eps))
       const float denom = sqrtf(vi / h.bc2) + h.eps;
-      p[i] = p[i] * h.decay_mul - h.step_size * (mi / denom);
+      p = p * h.decay_mul - h.step_size * (mi / denom);
     } else {
       // optimizer.py:86-89: p - lr * (m/bc1) / (sqrt(v/bc2) + eps)
-      p[i] = p[i] - h.lr * (mi / h.bc1) / (sqrtf(vi / h.bc2) + h.eps);
+      p = p - h.lr * (mi / h.bc1) / (sqrtf(vi / h.bc2) + h.eps);
     }
   }
+};
+
+template <class Op>
+__global__ void __launch_bounds__(256) multi_update_kernel(const __grid_constant__ MTArgs a, const Op op) {
+  int t = 0;
+  while ((int)blockIdx.x >= a.blk_start[t + 1]) ++t;   // <= 48 uniform steps over the argument bank
+  float* __restrict__ p = a.p[t];
+  const float* __restrict__ g = a.g[t];
+  float* __restrict__ m = a.s1[t];
+  float* __restrict__ v = Op::kTwoStates ? a.s2[t] : nullptr;
+  const long long n = a.n[t];
+  const long long base = (long long)((int)blockIdx.x - a.blk_start[t]) * kChunk;
+  const long long end = base + kChunk < n ? base + kChunk : n;
+  const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)(Op::kTwoStates ? v : p)) & 15) == 0);
+  if (aligned && end - base == kChunk) {
+    float4 P[4], G[4], M[4], V[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = base + 4 * ((long long)u * 256 + threadIdx.x);
+      P[u] = *reinterpret_cast<const float4*>(p + i);
+      G[u] = *reinterpret_cast<const float4*>(g + i);
+      M[u] = *reinterpret_cast<const float4*>(m + i);
+      if (Op::kTwoStates) V[u] = *reinterpret_cast<const float4*>(v + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = base + 4 * ((long long)u * 256 + threadIdx.x);
+      op(P[u].x, G[u].x, M[u].x, V[u].x);
+      op(P[u].y, G[u].y, M[u].y, V[u].y);
+      op(P[u].z, G[u].z, M[u].z, V[u].z);
+      op(P[u].w, G[u].w, M[u].w, V[u].w);
+      *reinterpret_cast<float4*>(m + i) = M[u];
+      if (Op::kTwoStates) *reinterpret_cast<float4*>(v + i) = V[u];
+      *reinterpret_cast<float4*>(p + i) = P[u];
+    }
+    return;
+  }
+  for (long long i = base + threadIdx.x; i < end; i += 256) {
+    float pi = p[i], mi = m[i], vi = Op::kTwoStates ? v[i] : 0.f;
+    op(pi, g[i], mi, vi);
+    m[i] = mi;
+    if (Op::kTwoStates) v[i] = vi;
+    p[i] = pi;
+  }
+}
+
+// Fills blk_start from the element counts; returns the grid size.
+static inline unsigned mt_plan(MTArgs& a, int c) {
+  int blocks = 0;
+  for (int i = 0; i < c; ++i) {
+    a.blk_start[i] = blocks;
+    blocks += (int)ceil_div(a.n[i], (long long)kChunk);
+  }
+  for (int i = c; i <= kMT; ++i) a.blk_start[i] = blocks;
+  return (unsigned)blocks;
 }
 
 // PACK: flat[off_t + i] = src_t[i];  UNPACK: dst_t[i] = flat[off_t + i]  (offsets in s2 slot as integers)
@@ -103,16 +157,15 @@ int ng_multi_sgd(int count, const uint64_t* params, const uint64_t* grads, const
     const int c = (count - base < kMT) ? count - base : kMT;
     MTArgs a;
     memset(&a, 0, sizeof(a));
-    long long max_n = 0;
     for (int i = 0; i < c; ++i) {
       a.p[i] = dptr<float>(params[base + i]);
       a.g[i] = dptr<const float>(grads[base + i]);
       a.s1[i] = dptr<float>(moms[base + i]);
       a.n[i] = numels[base + i];
-      if (a.n[i] > max_n) max_n = a.n[i];
     }
-    if (max_n == 0) continue;
-    NG_LAUNCH(multi_sgd_kernel, dim3(mt_grid_x(max_n), (unsigned)c), 256, 0, a, h);
+    const unsigned grid = mt_plan(a, c);
+    if (grid == 0) continue;
+    NG_LAUNCH((multi_update_kernel<SgdOp>), grid, 256, 0, a, SgdOp{h});
     NG_CHECK_LAUNCH();
   }
   return 0;
@@ -132,17 +185,16 @@ int ng_multi_adam(int count, const uint64_t* params, const uint64_t* grads, cons
     const int c = (count - base < kMT) ? count - base : kMT;
     MTArgs a;
     memset(&a, 0, sizeof(a));
-    long long max_n = 0;
     for (int i = 0; i < c; ++i) {
       a.p[i] = dptr<float>(params[base + i]);
       a.g[i] = dptr<const float>(grads[base + i]);
       a.s1[i] = dptr<float>(exp_avg[base + i]);
       a.s2[i] = dptr<float>(exp_avg_sq[base + i]);
       a.n[i] = numels[base + i];
-      if (a.n[i] > max_n) max_n = a.n[i];
     }
-    if (max_n == 0) continue;
-    NG_LAUNCH(multi_adam_kernel, dim3(mt_grid_x(max_n), (unsigned)c), 256, 0, a, h);
+    const unsigned grid = mt_plan(a, c);
+    if (grid == 0) continue;
+    NG_LAUNCH((multi_update_kernel<AdamOp>), grid, 256, 0, a, AdamOp{h});
     NG_CHECK_LAUNCH();
   }
   return 0;

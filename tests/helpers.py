@@ -178,7 +178,7 @@ def params_to_numpy(model):
 
 # ---------------------------------------------------------------------------- case comparison
 def compare_case(name, got, want, rtol, exact_keys=(), params_on_model_scale=False, mask_keys=None,
-                 trajectory_rtol=None):
+                 trajectory_rtol=None, grads_on_model_scale=False):
     """Compare one tests/cases.py result dict with its reference values.
 
     Tolerance: scale-relative allclose per array, each gradient on ITS OWN scale (see RTOL_FP32
@@ -190,6 +190,11 @@ def compare_case(name, got, want, rtol, exact_keys=(), params_on_model_scale=Fal
         the model's largest gradient instead of its own;
       * after an Adam/AdamW step such a parameter moves by lr*g/(|g|+eps), i.e. by amplified
         noise, on every implementation; those parameters are excluded from the post-step check.
+    ``grads_on_model_scale`` (opt-in TF32 mode, whole-model cases only): gradients are compared on the
+    scale of the model's largest gradient.  The 1e-2 bar is a per-operator bar; through four TF32
+    conv layers and their BatchNorm backward passes (which subtract means, i.e. cancel) the 3e-4
+    per-op rounding compounds to ~5 % of the first layer's small gradient (measured: 3.6e-4 absolute
+    against a first-layer maximum of 6.2e-3 and a model maximum of 0.19).
     ``mask_keys``: arrays whose support (!= 0) must match bit-exactly besides the value check.
     ``trajectory_rtol``: looser bar for the end of a multi-step trajectory (see cases.TRAJECTORY_RTOL).
     """
@@ -217,6 +222,8 @@ def compare_case(name, got, want, rtol, exact_keys=(), params_on_model_scale=Fal
             assert g.shape == w.shape, what
             own = float(np.max(np.abs(w)))
             scale = own if own >= 1e-6 * gmax else gmax  # analytically-zero gradients: see docstring
+            if grads_on_model_scale:
+                scale = max(own, gmax)
             np.testing.assert_allclose(g, w, rtol=rtol, atol=rtol * scale, err_msg=what)
             continue
         if trajectory_rtol is not None and (key.startswith("param") or key in ("loss_last", "loss_history")):
