@@ -194,7 +194,7 @@ def compare_case(name, got, want, rtol, exact_keys=(), params_on_model_scale=Fal
     scale of the model's largest gradient.  The 1e-2 bar is a per-operator bar; through four TF32
     conv layers and their BatchNorm backward passes (which subtract means, i.e. cancel) the 3e-4
     per-op rounding compounds to ~5 % of the first layer's small gradient (measured: 3.6e-4 absolute
-    against a first-layer maximum of 6.2e-3 and a model maximum of 0.19).
+    against a first-layer maximum of 6.2e-3 and a model maximum of 0.06).
     ``mask_keys``: arrays whose support (!= 0) must match bit-exactly besides the value check.
     ``trajectory_rtol``: looser bar for the end of a multi-step trajectory (see cases.TRAJECTORY_RTOL).
     """
