@@ -7,8 +7,12 @@ One "step" is one full training step (forward, NLL loss, backward, Adam) of BASE
 [Conv3x3(pad 1)-BatchNorm2d-ReLU]x2-MaxPool for 64/128/256 channels, Linear(4096,256)-ReLU-
 Linear(256,10), log_softmax + NLLLoss, Adam(lr 1e-3) — on a batch of 512 synthetic 3x32x32 images
 per GPU.  With N GPUs (launched by torchrun, one rank per GPU) every rank trains its own shard of
-the global batch 512*N and gradients are summed by one NCCL allreduce per step (N = 8 is
-BASELINE config 4, global batch 4096): weak scaling.
+the global batch and the gradients are summed with NCCL (chunks of the flat gradient arena on a
+communication stream while the backward pass is still running).  Default: weak scaling, 512 images
+per GPU (N = 8 is BASELINE config 4, global batch 4096), per-shard BatchNorm statistics.
+--scaling strong: the global batch stays 4096 (4096/2048/1024/512 images per GPU
+at N = 1/2/4/8); --sync-bn: BatchNorm statistics over the global batch (the reference's
+single-process semantics), at the price of two small exchanges per BatchNorm layer and direction.
 
 Printed JSON line (rank 0):
   value        images/s with inputs already resident in HBM, CUDA-event timed, max over ranks
@@ -47,6 +51,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 PER_GPU_BATCH = 512
+STRONG_GLOBAL_BATCH = 4096
 CPU_SAMPLE_BATCH = 64
 LR = 1e-3
 WORKLOAD = "cifar_vgg_bn_adam_bs512_per_gpu (BASELINE configs[2]; x8 GPUs = configs[4], global batch 4096)"
@@ -229,12 +234,18 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def workload_config(world, n_params=2198602, math_mode="fp32"):
+def workload_config(world, n_params=2198602, math_mode="fp32", batch=None, args=None):
     """The `config` object of the JSON line — identical for both arms (the reference arm runs the same
     workload definition; what it samples per step is said in cpu_baseline.sample)."""
-    return {"workload": WORKLOAD, "global_batch": PER_GPU_BATCH * world, "per_gpu_batch": PER_GPU_BATCH,
+    scaling = getattr(args, "scaling", "weak")
+    if batch is None:
+        batch = STRONG_GLOBAL_BATCH // world if scaling == "strong" else PER_GPU_BATCH
+    sync_bn = bool(getattr(args, "sync_bn", False)) and world > 1
+    return {"workload": WORKLOAD, "global_batch": batch * world, "per_gpu_batch": batch,
             "image": "3x32x32", "optimizer": "Adam(lr=1e-3)", "loss": "log_softmax + NLLLoss",
             "params": n_params, "parallelism": f"dp{world}" if world > 1 else "single",
+            "batchnorm": ("global-batch statistics (SyncBN: the single-process reference step at the global batch)"
+                          if sync_bn else "per-shard statistics" if world > 1 else "batch statistics"),
             "l2": "no flush: one step touches ~1.9 GB of activations, far larger than the 126 MB L2",
             "math": MATH_TEXT[math_mode]}
 
@@ -259,8 +270,8 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.gpus),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus, args=args),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -338,46 +349,91 @@ def conv2d_sweep(B, lib, ffma_peak):
     return rows
 
 
-def mnist_cnn_images_per_sec(B, steps=100, warmup=10):
+def mnist_cnn_images_per_sec(B, steps=200, warmup=10):
+    """BASELINE config 0: the README MNIST CNN, batch 128, SGD(lr 0.01), NLLLoss.
+    eager   — the reference's loop shape: every primitive dispatched from Python (device-resident batch);
+    graphed — nanograd_b200.graph.GraphedStep: the same step captured once, then per step one H2D copy of
+              a NEW host batch from pinned staging plus one cudaGraphLaunch (this is the end-to-end figure:
+              host batches in, loss read back at the end)."""
     import helpers
     import nanograd_b200.nn.module as nn
     import nanograd_b200.optim.optimizer as optim
     from nanograd_b200.device import Device
+    from nanograd_b200.graph import GraphedStep
     from nanograd_b200.tensor import Tensor
-    np.random.seed(0)
-    model = helpers.build_mnist_cnn(nn)
-    model.gpu()
-    opt = optim.SGD(model.parameters(), lr=0.01, momentum=0)
-    crit = nn.NLLLoss()
-    X = np.random.rand(128, 784).astype(np.float32)
-    Y = np.random.randint(0, 10, 128).astype(np.float32)
-    xb, yb = Tensor(X, device=Device.GPU), Tensor(Y, device=Device.GPU)
-
-    def step():
-        out = model(xb)
-        opt.zero_grad()
-        loss = crit(out, yb)
-        loss.backward()
-        opt.step()
-        return loss
-    for _ in range(warmup):
-        step()
-    B.sync()
     import gc
+
+    def setup():
+        np.random.seed(0)
+        model = helpers.build_mnist_cnn(nn)
+        model.gpu()
+        opt = optim.SGD(model.parameters(), lr=0.01, momentum=0)
+        crit = nn.NLLLoss()
+
+        def step(xb, yb):
+            out = model(xb)
+            opt.zero_grad()
+            loss = crit(out, yb)
+            loss.backward()
+            opt.step()
+            return loss
+        return step
+
+    rng = np.random.RandomState(0)
+    X = rng.rand(8, 128, 784).astype(np.float32)
+    Y = rng.randint(0, 10, (8, 128)).astype(np.float32)
+
+    # ---- eager
+    step = setup()
+    xb, yb = Tensor(X[0], device=Device.GPU), Tensor(Y[0], device=Device.GPU)
+    for _ in range(warmup):
+        step(xb, yb)
+    B.sync()
     gc.collect()  # garbage of the previous measurements would otherwise be collected inside the timed loop
+    launches0 = B.launch_count()
     e0, e1 = B.Event().record(), B.Event()
-    walls = []
+    t0 = time.perf_counter()
     for _ in range(steps):
-        t0 = time.perf_counter()
-        loss = step()
-        walls.append((time.perf_counter() - t0) * 1e3)
+        loss = step(xb, yb)
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps
     e1.record()
     e1.synchronize()
-    ms = e0.elapsed_ms(e1) / steps
-    if os.environ.get("NG_BENCH_DEBUG"):
-        print("mnist host ms per step:", " ".join("%.2f" % w for w in walls), "mem", B.mem_stats(), file=sys.stderr)
-    return {"workload": "README MNIST CNN, BS 128, SGD (BASELINE configs[0])", "images_per_sec": round(128 / (ms * 1e-3), 1),
-            "ms_per_step": round(ms, 4), "loss": float(loss.numpy()[0])}
+    eager_ms = e0.elapsed_ms(e1) / steps
+    eager_launches = (B.launch_count() - launches0) / steps
+    eager_loss = float(loss.numpy()[0])
+
+    # ---- graphed
+    fast = GraphedStep(setup(), X[0], Y[0], warmup=3)
+    for i in range(warmup):
+        fast(X[i % 8], Y[i % 8])
+    B.sync()
+    gc.collect()
+    e0, e1 = B.Event().record(), B.Event()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        out = fast(X[i % 8], Y[i % 8])
+    ghost_ms = (time.perf_counter() - t0) * 1e3 / steps
+    e1.record()
+    e1.synchronize()
+    graph_ms = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3) / steps
+    graph_loss = float(out.numpy()[0])
+    res = {"workload": "README MNIST CNN, BS 128, SGD (BASELINE configs[0])",
+           "images_per_sec": round(128 / (graph_ms * 1e-3), 1), "ms_per_step": round(graph_ms, 4),
+           "mode": "captured step (CUDA graph): per step one pinned H2D of a new host batch + one cudaGraphLaunch",
+           "kernels_per_step": fast.kernel_nodes, "host_ms_per_step": round(ghost_ms, 4), "loss": graph_loss,
+           "eager": {"images_per_sec": round(128 / (eager_ms * 1e-3), 1), "ms_per_step": round(eager_ms, 4),
+                     "launches_per_step": eager_launches, "host_ms_per_step": round(host_ms, 4),
+                     "host_us_per_launch": round(host_ms * 1e3 / max(eager_launches, 1), 2), "loss": eager_loss}}
+    fast.close()
+    return res
+
+
+def per_gpu_batch(args, world):
+    if args.scaling == "strong":
+        if STRONG_GLOBAL_BATCH % world:
+            raise SystemExit(f"--scaling strong needs a world size that divides {STRONG_GLOBAL_BATCH}")
+        return STRONG_GLOBAL_BATCH // world
+    return PER_GPU_BATCH
 
 
 def measure_training(args, B, dist, lib, math_mode, with_clocks):
@@ -391,6 +447,7 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
 
     B.set_math_mode(math_mode)
     rank, world = dist.rank(), dist.world_size()
+    batch = per_gpu_batch(args, world)
     # identical parameters on every rank: host-side NumPy init under the same seed
     np.random.seed(0)
     model = build_model(nn)
@@ -400,7 +457,7 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     n_params = sum(int(np.prod(p.shape)) for p in model.parameters())
 
     # this rank's shard of the global synthetic batch
-    Xh, Yh = synthetic_batch(PER_GPU_BATCH, seed=1000 + rank)
+    Xh, Yh = synthetic_batch(batch, seed=1000 + rank)
     x_res, y_res = Tensor(Xh, device=Device.GPU), Tensor(Yh, device=Device.GPU)
 
     W, K = max(args.warmup, 3), max(args.steps, 1)
@@ -441,7 +498,7 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
             (("conv_fprop", 0), ("conv_dgrad", 1), ("conv_wgrad", 2), ("gemm", 3))}
     lib.ng_prof_reset()
     ms_per_step = ms_total / K
-    value = PER_GPU_BATCH * world / (ms_per_step * 1e-3)
+    value = batch * world / (ms_per_step * 1e-3)
 
     # ---- e2e: the public input pipeline (nanograd_b200.data.BatchLoader) -----------------------
     # Every step draws a random mini-batch from a host-resident synthetic dataset (the reference's loop,
@@ -449,12 +506,12 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     # copy stream (overlapping the previous step) and reads the loss back to the host (blocking).
     from nanograd_b200.data import BatchLoader
     rng = np.random.RandomState(2000 + rank)
-    n_data = 4 * PER_GPU_BATCH
+    n_data = 4 * batch
     Xd = rng.randn(n_data, 3, 32, 32).astype(np.float32)
     Yd = rng.randint(0, 10, n_data).astype(np.float32)
     # one loader for 2 untimed + K timed steps (its pinned staging and thread exist before the clock starts)
     e0, e1, t0 = None, B.Event(), 0.0
-    for i, (xb, yb) in enumerate(BatchLoader(Xd, Yd, PER_GPU_BATCH, 2 + K, device=Device.GPU)):
+    for i, (xb, yb) in enumerate(BatchLoader(Xd, Yd, batch, 2 + K, device=Device.GPU)):
         if i == 2:
             dist.barrier()
             B.sync()
@@ -468,13 +525,14 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     dist.barrier()
     gc.enable()
     e2e_ms = dist.all_reduce_max(max(e0.elapsed_ms(e1), wall_ms)) / K
-    e2e_value = PER_GPU_BATCH * world / (e2e_ms * 1e-3)
+    e2e_value = batch * world / (e2e_ms * 1e-3)
+    checksum = dist.replica_checksum(list(model.parameters())) if world > 1 else None
     del loss, x_res, y_res, model, opt
     B.set_math_mode("fp32")
     return {"value": value, "ms_per_step": ms_per_step, "e2e_value": e2e_value, "e2e_ms": e2e_ms,
             "h2d": int(Xh.nbytes + Yh.nbytes), "launches": int(launches), "loss": loss_value, "prof": prof,
             "ffma_peak": float(ffma_peak.value), "clocks": clocks.summary() if clocks else None,
-            "n_params": n_params, "K": K, "W": W}
+            "n_params": n_params, "K": K, "W": W, "batch": batch, "replica_checksum": checksum}
 
 
 KERNEL_NAMES = {
@@ -568,7 +626,7 @@ def run_device_arm(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nnodes=1 "
                              f"--nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus}")
-    dist.init(use_device=True)
+    dist.init(use_device=True, sync_bn=args.sync_bn)
     rank, world = dist.rank(), dist.world_size()
     lib = B.lib()
     B.init(dist.local_rank())
@@ -591,12 +649,14 @@ def run_device_arm(args):
                           "parity bar rtol 1e-2); reduced precision, hence not the headline value"}
     line = {
         "metric": "train_images_per_sec", "value": round(m["value"], 1), "unit": "images/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": round(m["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
+        "steps": K, "warmup": W, "ms_per_step": round(m["ms_per_step"], 4), "higher_is_better": True,
+        "scaling": args.scaling,
         "vs_baseline": None, "dtype": "tf32" if main_mode == "tf32" else "f32", "data": "synthetic",
-        "config": workload_config(world, m["n_params"], main_mode),
+        "config": workload_config(world, m["n_params"], main_mode, m["batch"], args),
         "e2e": {"value": round(m["e2e_value"], 1), "unit": "images/s", "ms_per_step": round(m["e2e_ms"], 4),
                 "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4},
         "gpu_launches": m["launches"], "launches_per_step": m["launches"] / K, "loss": m["loss"],
+        "replica_checksum": m["replica_checksum"],
         "clocks": m["clocks"], "roofline": roofline_object(m, main_mode, peaks, peak_src, m["clocks"]),
     }
     for key, (mode, o) in others.items():
@@ -630,6 +690,10 @@ def main():
     ap.add_argument("--impl", default="device", choices=["device", "reference"])
     ap.add_argument("--math", default="fp32", choices=["fp32", "simt", "tf32x3", "tf32"],
                     help="math mode of the headline measurement (default fp32: FP32-accurate, engine picked per call)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 512 images per GPU; strong: global batch 4096 split over the GPUs (SURVEY 8-d cfg4)")
+    ap.add_argument("--sync-bn", action="store_true",
+                    help="BatchNorm statistics over the global batch (SyncBN) instead of per shard")
     ap.add_argument("--no-tf32", action="store_true", help="skip the secondary simt-mode and tf32-mode measurements")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the conv2d sweep / MNIST CNN / CPU baseline side measurements (profiling runs)")

@@ -266,13 +266,41 @@ int ng_multi_adam(int count, const uint64_t* params, const uint64_t* grads,
 int ng_multi_pack(int count, const uint64_t* srcs, const int64_t* numels, uint64_t dst_flat);
 int ng_multi_unpack(int count, const uint64_t* dsts, const int64_t* numels, uint64_t src_flat);
 
+/* --------------------------------------------------------- captured steps (graphs) --- */
+/* New functionality.  The reference's training loop (README.md:94-125) dispatches ~30 tiny device
+ * operations per README-CNN step from Python; here a step can be recorded once on the compute stream
+ * (ng_graph_begin ... the step's calls ... ng_graph_end) and replayed with one launch.  Memory allocated
+ * while capturing belongs to the graph (private pool), so replays never alias later allocations.  A
+ * captured step must not synchronise, read results back, or copy from pageable host memory. */
+int ng_graph_begin(void);
+int ng_graph_end(uint64_t* out_handle, uint64_t* out_kernel_nodes, uint64_t* out_private_bytes);
+int ng_graph_launch(uint64_t handle);
+int ng_graph_destroy(uint64_t handle);
+int ng_graph_capturing(int* out_flag);
+
 /* ---------------------------------------------------------- data-parallel (NCCL) --- */
 /* New functionality (the reference has no multi-device support, device.py:10-11).  One
- * process per GPU; libnccl is dlopen()ed on first use.  The allreduce runs on a dedicated
- * communication stream fenced against the compute stream with events. */
-int ng_nccl_unique_id(void* out_128_bytes);
-int ng_nccl_init(const void* id_128_bytes, int world_size, int rank);
+ * process per GPU; libnccl is dlopen()ed on first use.
+ * ng_nccl_unique_id fills 256 bytes (two ncclUniqueIds: the gradient-bucket communicator on the
+ * communication stream and the in-line communicator of the compute stream); rank 0 creates them
+ * and shares them with the other ranks (nanograd_b200/dist.py: a file under the run directory).
+ * ng_nccl_allreduce_begin launches the sum of buf[0..count) on the communication stream, ordered
+ * after the compute-stream work enqueued so far; several chunks may be in flight while the backward
+ * pass continues.  ng_nccl_allreduce_end makes the compute stream wait for all of them (before the
+ * optimizer kernel).  ng_nccl_allreduce_sum = begin + end.
+ * ng_nccl_sync_bn(1): BatchNorm training statistics and the backward's two per-channel sums are
+ * exchanged across ranks (allgather of per-rank (mean, M2), Chan's combination; allreduce of the
+ * backward sums), so a data-parallel step equals the single-process step on the global batch
+ * (module.py:356-391 computes statistics over the whole batch).
+ * ng_nccl_host_allreduce: up to 64 host doubles, op 0 = sum, 1 = max (barriers, timings, checksums). */
+int ng_nccl_unique_id(void* out_256_bytes);
+int ng_nccl_init(const void* id_256_bytes, int world_size, int rank);
+int ng_nccl_world(int* world_size, int* rank);
 int ng_nccl_allreduce_sum(uint64_t buf, int64_t count);
+int ng_nccl_allreduce_begin(uint64_t buf, int64_t count);
+int ng_nccl_allreduce_end(void);
+int ng_nccl_sync_bn(int on);
+int ng_nccl_host_allreduce(double* values, int count, int op);
 int ng_nccl_destroy(void);
 
 #ifdef __cplusplus

@@ -12,6 +12,8 @@ unchanged under this package's Tensor and under the reference's own ``nanograd.t
 """
 import inspect
 
+from nanograd_b200 import dist as _dist
+
 
 class Function:
     def __init__(self, *tensors):
@@ -52,6 +54,8 @@ class Function:
 
         out = self.forward(ctx, *[t.data for t in args], **kwargs)
         requires_grad = any(t.requires_grad for t in args)
+        if _dist._state["world"] > 1 and requires_grad:
+            _dist.note_use(args)
         ret = tensor_cls(out, device=ctx.device, requires_grad=requires_grad)
         ret.op = self.__name__.lower()
         if requires_grad:

@@ -95,9 +95,19 @@ _PROTOTYPES = {
     "ng_multi_adam": [i32, p_u64, p_u64, p_u64, p_u64, p_i64, f32, f32, f32, f32, f32, f32, f32, i32, f32],
     "ng_multi_pack": [i32, p_u64, p_i64, u64],
     "ng_multi_unpack": [i32, p_u64, p_i64, u64],
+    "ng_graph_begin": [],
+    "ng_graph_end": [p_u64, p_u64, p_u64],
+    "ng_graph_launch": [u64],
+    "ng_graph_destroy": [u64],
+    "ng_graph_capturing": [POINTER(c_int)],
     "ng_nccl_unique_id": [c_void_p],
     "ng_nccl_init": [c_void_p, i32, i32],
+    "ng_nccl_world": [POINTER(c_int), POINTER(c_int)],
     "ng_nccl_allreduce_sum": [u64, i64],
+    "ng_nccl_allreduce_begin": [u64, i64],
+    "ng_nccl_allreduce_end": [],
+    "ng_nccl_sync_bn": [i32],
+    "ng_nccl_host_allreduce": [POINTER(ctypes.c_double), i32, i32],
     "ng_nccl_destroy": [],
 }
 
@@ -236,6 +246,12 @@ def mem_stats():
     a, b, c = u64(0), u64(0), u64(0)
     lib().ng_mem_stats(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
     return {"live_bytes": a.value, "pooled_bytes": b.value, "device_allocs": c.value}
+
+
+def graph_capturing():
+    flag = c_int(0)
+    lib().ng_graph_capturing(ctypes.byref(flag))
+    return bool(flag.value)
 
 
 def device_info():

@@ -137,6 +137,55 @@ __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __res
   }
 }
 
+// ---- synchronised BatchNorm (data parallel, ng_nccl_sync_bn) ----------------------------------------
+// The reference computes the statistics over the whole batch (module.py:356-391); under data parallelism
+// the batch is sharded, so every rank folds its partials into (mean_r, M2_r = sum (x - mean_r)^2, n_r),
+// the triples are all-gathered ([2C + 4] floats per rank) and combined with Chan's pairwise update in
+// rank order on every rank — the same arithmetic everywhere, hence bit-identical replicas, and no
+// E[x^2] - E[x]^2 cancellation across ranks.
+__global__ void __launch_bounds__(256) bn_fwd_local_kernel(const float* __restrict__ partial, const float* __restrict__ x,
+                                                           float* __restrict__ send, int64_t C, int64_t P, int S,
+                                                           float count) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) send[2 * C] = count;
+  if (c >= C) return;
+  float sa = 0.f, sb = 0.f;
+  for (int s = 0; s < S; ++s) {
+    sa += partial[(s * C + c) * 2 + 0];
+    sb += partial[(s * C + c) * 2 + 1];
+  }
+  const float d = sa / count;
+  float m2 = sb - sa * d;
+  if (m2 < 0.f) m2 = 0.f;
+  send[2 * c + 0] = x[c * P] + d;
+  send[2 * c + 1] = m2;
+}
+
+__global__ void __launch_bounds__(256) bn_fwd_finalize_sync_kernel(const float* __restrict__ gathered, int world,
+                                                                   int64_t stride, float* __restrict__ save_mean,
+                                                                   float* __restrict__ save_invstd, float* running_mean,
+                                                                   float* running_var, int64_t C, float eps,
+                                                                   float momentum) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float* g = gathered + (int64_t)r * stride;
+    const float nr = g[2 * C], mr = g[2 * c], m2r = g[2 * c + 1];
+    const float tot = n + nr;
+    const float delta = mr - mean;
+    mean += delta * (nr / tot);
+    m2 += m2r + delta * delta * (n * nr / tot);
+    n = tot;
+  }
+  save_mean[c] = mean;
+  save_invstd[c] = 1.f / sqrtf(m2 / n + eps);
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (m2 / (n - 1.f));
+  }
+}
+
 // y = (x - mean[c]) * gamma[c] * invstd[c] + beta[c]
 // use_var: invstd is computed on the fly from a variance array (evaluation mode)
 __global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, const float* __restrict__ x,
@@ -179,8 +228,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, co
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial,
                                                               const float* __restrict__ invstd, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ sums, int64_t C,
-                                                              int S) {
+                                                              int S, float count) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) sums[2 * C] = count;  // summed across ranks with the two per-channel sums (synchronised BatchNorm)
   if (c >= C) return;
   float sa = 0.f, sb = 0.f;
   for (int s = 0; s < S; ++s) {
@@ -199,8 +249,11 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(float* __restrict__ dx, 
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ sums, int64_t total, int64_t C, int64_t P,
                                                         float inv_count, int vec_ok, const float* __restrict__ beta,
-                                                        FastDiv fp4 = FastDiv{0, 0, 0}, FastDiv fc = FastDiv{0, 0, 0}) {
+                                                        FastDiv fp4 = FastDiv{0, 0, 0}, FastDiv fc = FastDiv{0, 0, 0},
+                                                        int global_count = 0) {
   // beta != nullptr: fused ReLU, dy is masked by (z >= 0) with z recomputed from x
+  // global_count: the element count behind `sums` is sums[2C] (allreduced with them), not the local one
+  if (global_count) inv_count = 1.f / sums[2 * C];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
@@ -281,10 +334,26 @@ int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
             (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr,
             (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
   NG_CHECK_LAUNCH();
-  NG_LAUNCH(bn_fwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, dptr<const float>(x),
-            dptr<float>(save_mean), dptr<float>(save_invstd), running_mean ? dptr<float>(running_mean) : nullptr,
-            running_var ? dptr<float>(running_var) : nullptr, C, HW, S, (float)(N * HW), eps, momentum);
-  NG_CHECK_LAUNCH();
+  if (dp_sync_bn()) {
+    const int world = dp_world();
+    const int64_t stride = 2 * C + 4;
+    float* xchg = nullptr;  // [stride] to send, then [world][stride] gathered
+    if (pool_alloc((void**)&xchg, (uint64_t)(world + 1) * stride * sizeof(float))) return 1;
+    NG_LAUNCH(bn_fwd_local_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, dptr<const float>(x), xchg, C,
+              HW, S, (float)(N * HW));
+    NG_CHECK_LAUNCH();
+    if (dp_allgather_inline(xchg, xchg + stride, stride)) return 1;
+    NG_LAUNCH(bn_fwd_finalize_sync_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)(xchg + stride), world, stride,
+              dptr<float>(save_mean), dptr<float>(save_invstd), running_mean ? dptr<float>(running_mean) : nullptr,
+              running_var ? dptr<float>(running_var) : nullptr, C, eps, momentum);
+    NG_CHECK_LAUNCH();
+    pool_free(xchg);
+  } else {
+    NG_LAUNCH(bn_fwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, dptr<const float>(x),
+              dptr<float>(save_mean), dptr<float>(save_invstd), running_mean ? dptr<float>(running_mean) : nullptr,
+              running_var ? dptr<float>(running_var) : nullptr, C, HW, S, (float)(N * HW), eps, momentum);
+    NG_CHECK_LAUNCH();
+  }
   const int64_t total = N * C * HW;
   NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
             dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(save_mean),
@@ -332,8 +401,8 @@ int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, u
   int64_t n_per = 0;
   const int S = bn_split(N, C, HW, &n_per);
   float* partial = nullptr;
-  if (pool_alloc((void**)&partial, (uint64_t)(S + 1) * C * 2 * sizeof(float))) return 1;
-  float* sums = partial + (int64_t)S * C * 2;
+  if (pool_alloc((void**)&partial, ((uint64_t)(S + 1) * C * 2 + 4) * sizeof(float))) return 1;
+  float* sums = partial + (int64_t)S * C * 2;  // [C][2] sums, then the element count behind them
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0) && ((dx & 15u) == 0);
   if (act) {
     NG_LAUNCH((bn_reduce_kernel<2>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
@@ -346,13 +415,18 @@ int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, u
   }
   NG_CHECK_LAUNCH();
   NG_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial,
-            dptr<const float>(save_invstd), dptr<float>(dgamma), dptr<float>(dbeta), sums, C, S);
+            dptr<const float>(save_invstd), dptr<float>(dgamma), dptr<float>(dbeta), sums, C, S, (float)(N * HW));
   NG_CHECK_LAUNCH();
+  // synchronised BatchNorm: dgamma / dbeta stay this rank's sums (the gradient bucket adds them across
+  // ranks); dx needs the two sums, and the count, over the global batch
+  const int sync = dp_sync_bn() ? 1 : 0;
+  if (sync && dp_allreduce_inline(sums, 2 * C + 1)) return 1;
   const int64_t total = N * C * HW;
   NG_LAUNCH(bn_bwd_dx_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(dx), dptr<const float>(dy),
             dptr<const float>(x), dptr<const float>(gamma), dptr<const float>(save_mean),
             dptr<const float>(save_invstd), (const float*)sums, total, C, HW, 1.f / (float)(N * HW), vec,
-            act ? dptr<const float>(beta) : (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0), make_fastdiv(C));
+            act ? dptr<const float>(beta) : (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0), make_fastdiv(C),
+            sync);
   NG_CHECK_LAUNCH();
   pool_free(partial);
   return 0;

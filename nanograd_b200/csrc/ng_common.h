@@ -29,6 +29,14 @@ int ensure_init();
 // Workspace from the caching pool (freed with pool_free on the same stream → safe reuse).
 int pool_alloc(void** out, uint64_t bytes);
 int pool_free(void* p);
+// Data parallel (nccl_dp.cu): world size / rank of this process, and in-line collectives on the
+// compute stream used by synchronised BatchNorm.
+int dp_world();
+int dp_rank();
+bool dp_sync_bn();
+int dp_allreduce_inline(float* buf, int64_t count);
+int dp_allgather_inline(const float* send, float* recv, int64_t count_per_rank);
+
 // Optional per-class kernel timing (ng_prof_*): returns a token (< 0 when disabled).
 int prof_begin(int cls, double flops, double bytes);
 void prof_end(int token);

@@ -45,16 +45,32 @@ int ensure_init() {
 // the next request immediately: any kernel still reading it is ordered before any kernel the
 // new owner will launch.  Training repeats the same shapes every step → after the first step
 // no cudaMalloc is issued.
+struct Block { uint64_t size; uint64_t owner; };  // owner 0 = the global pool, else the id of a captured graph
 struct Pool {
   std::mutex mu;
   std::map<uint64_t, std::vector<void*>> free_by_size;
-  std::unordered_map<void*, uint64_t> size_of;  // every block we ever allocated and still own
+  std::unordered_map<void*, Block> size_of;  // every block we ever allocated and still own
   uint64_t live = 0, pooled = 0, n_allocs = 0;
 };
 static Pool& pool() {
   static Pool* p = new Pool();  // leaked on purpose: outlive Python's teardown order
   return *p;
 }
+
+// ---- captured steps (CUDA graphs) ----------------------------------------------------------------
+// A training step whose cost is host dispatch (the README MNIST CNN: ~30 launches of microseconds each)
+// is captured once into a CUDA graph and replayed with one cudaGraphLaunch.  The graph bakes device
+// addresses in, so everything allocated while capturing comes from — and returns to — a pool private
+// to that graph: replays can never collide with memory the regular pool hands out later.
+struct GraphRec {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::map<uint64_t, std::vector<void*>> free_by_size;  // private free list (reused within the capture)
+  uint64_t kernel_nodes = 0, bytes = 0;
+};
+static std::unordered_map<uint64_t, GraphRec*>* g_graphs = nullptr;
+static uint64_t g_capturing = 0;  // id of the graph being captured, 0 = none
+static uint64_t g_next_graph = 1;
 
 static uint64_t round_size(uint64_t b) {
   if (b == 0) b = 1;
@@ -77,29 +93,32 @@ int pool_alloc(void** out, uint64_t bytes) {
   Pool& P = pool();
   const uint64_t sz = round_size(bytes);
   std::lock_guard<std::mutex> lk(P.mu);
-  auto it = P.free_by_size.find(sz);
-  if (it != P.free_by_size.end() && !it->second.empty()) {
+  GraphRec* rec = g_capturing ? (*g_graphs)[g_capturing] : nullptr;
+  auto& free_list = rec ? rec->free_by_size : P.free_by_size;
+  auto it = free_list.find(sz);
+  if (it != free_list.end() && !it->second.empty()) {
     *out = it->second.back();
     it->second.pop_back();
-    P.pooled -= sz;
+    if (!rec) P.pooled -= sz;
     P.live += sz;
     return 0;
   }
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, sz);
-  if (e != cudaSuccess) {
+  if (e != cudaSuccess && !rec) {
     cudaGetLastError();
     cudaStreamSynchronize(g_stream);
     release_pooled_locked(P);
     e = cudaMalloc(&p, sz);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return set_error("device out of memory: %llu bytes requested (%llu live, pool emptied): %s",
-                       (unsigned long long)sz, (unsigned long long)P.live, cudaGetErrorString(e));
-    }
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error("device out of memory: %llu bytes requested (%llu live, pool emptied): %s",
+                     (unsigned long long)sz, (unsigned long long)P.live, cudaGetErrorString(e));
   }
   P.n_allocs++;
-  P.size_of[p] = sz;
+  P.size_of[p] = Block{sz, g_capturing};
+  if (rec) rec->bytes += sz;
   P.live += sz;
   *out = p;
   return 0;
@@ -111,9 +130,17 @@ int pool_free(void* p) {
   std::lock_guard<std::mutex> lk(P.mu);
   auto it = P.size_of.find(p);
   if (it == P.size_of.end()) return set_error("ng_free: pointer %p is not owned by the pool", p);
-  const uint64_t sz = it->second;
-  P.free_by_size[sz].push_back(p);
+  const uint64_t sz = it->second.size;
   P.live -= sz;
+  if (it->second.owner) {
+    auto g = g_graphs ? g_graphs->find(it->second.owner) : decltype(g_graphs->end()){};
+    if (g_graphs && g != g_graphs->end()) {
+      g->second->free_by_size[sz].push_back(p);  // stays with its graph: replays still use the address
+      return 0;
+    }
+    it->second.owner = 0;  // the graph is gone: the block joins the global pool
+  }
+  P.free_by_size[sz].push_back(p);
   P.pooled += sz;
   return 0;
 }
@@ -197,6 +224,98 @@ int ng_malloc(uint64_t* out_ptr, uint64_t bytes) {
 }
 
 int ng_free(uint64_t ptr) { return pool_free(dptr<void>(ptr)); }
+
+#ifndef NG_EMU
+int ng_graph_begin(void) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(g_capturing == 0, "ng_graph_begin: a capture is already in progress");
+  if (!g_graphs) g_graphs = new std::unordered_map<uint64_t, GraphRec*>();
+  const uint64_t id = g_next_graph++;
+  {
+    std::lock_guard<std::mutex> lk(pool().mu);
+    (*g_graphs)[id] = new GraphRec();
+    g_capturing = id;
+  }
+  // relaxed mode: the private pool may call cudaMalloc while capturing
+  cudaError_t e = cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) {
+    std::lock_guard<std::mutex> lk(pool().mu);
+    g_capturing = 0;
+    delete (*g_graphs)[id];
+    g_graphs->erase(id);
+    return set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int ng_graph_end(uint64_t* out_handle, uint64_t* out_kernel_nodes, uint64_t* out_private_bytes) {
+  NG_REQUIRE(g_capturing != 0, "ng_graph_end: no capture in progress");
+  const uint64_t id = g_capturing;
+  GraphRec* rec = (*g_graphs)[id];
+  cudaError_t e = cudaStreamEndCapture(g_stream, &rec->graph);
+  {
+    std::lock_guard<std::mutex> lk(pool().mu);
+    g_capturing = 0;
+  }
+  if (e != cudaSuccess || !rec->graph) {
+    cudaGetLastError();
+    return set_error("cudaStreamEndCapture failed: %s (a captured step must not synchronise, copy from pageable "
+                     "host memory or read results back)", cudaGetErrorString(e));
+  }
+  size_t n = 0;
+  NG_CHECK_CUDA(cudaGraphGetNodes(rec->graph, nullptr, &n));
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n) NG_CHECK_CUDA(cudaGraphGetNodes(rec->graph, nodes.data(), &n));
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) rec->kernel_nodes++;
+  }
+  NG_CHECK_CUDA(cudaGraphInstantiate(&rec->exec, rec->graph, 0));
+  *out_handle = id;
+  if (out_kernel_nodes) *out_kernel_nodes = rec->kernel_nodes;
+  if (out_private_bytes) *out_private_bytes = rec->bytes;
+  return 0;
+}
+
+int ng_graph_launch(uint64_t handle) {
+  NG_REQUIRE(g_graphs && g_graphs->count(handle), "ng_graph_launch: unknown graph %llu", (unsigned long long)handle);
+  NG_REQUIRE(g_capturing == 0, "ng_graph_launch: cannot replay while capturing");
+  GraphRec* rec = (*g_graphs)[handle];
+  NG_CHECK_CUDA(cudaGraphLaunch(rec->exec, g_stream));
+  g_launches += rec->kernel_nodes;
+  return 0;
+}
+
+int ng_graph_destroy(uint64_t handle) {
+  if (!g_graphs || !g_graphs->count(handle)) return 0;
+  NG_CHECK_CUDA(cudaStreamSynchronize(g_stream));
+  GraphRec* rec = (*g_graphs)[handle];
+  if (rec->exec) cudaGraphExecDestroy(rec->exec);
+  if (rec->graph) cudaGraphDestroy(rec->graph);
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  for (auto& kv : rec->free_by_size)
+    for (void* p : kv.second) {
+      cudaFree(p);
+      P.size_of.erase(p);
+    }
+  // blocks of this graph that are still held by live tensors join the global pool when they are freed
+  g_graphs->erase(handle);
+  delete rec;
+  return 0;
+}
+
+int ng_graph_capturing(int* out) {
+  *out = g_capturing != 0;
+  return 0;
+}
+#else
+int ng_graph_begin(void) { return set_error("CUDA graphs are not available in the emulation build"); }
+int ng_graph_end(uint64_t*, uint64_t*, uint64_t*) { return set_error("CUDA graphs are not available in the emulation build"); }
+int ng_graph_launch(uint64_t) { return set_error("CUDA graphs are not available in the emulation build"); }
+int ng_graph_destroy(uint64_t) { return 0; }
+int ng_graph_capturing(int* out) { *out = 0; return 0; }
+#endif
 
 int ng_mem_stats(uint64_t* live_bytes, uint64_t* pooled_bytes, uint64_t* n_device_allocs) {
   Pool& P = pool();

@@ -56,6 +56,20 @@ class DeviceBuffer:
         """Zero-copy alias with a new shape."""
         return DeviceBuffer(shape, hostbuf=self)
 
+    @classmethod
+    def alias_at(cls, base, offset_elems, shape):
+        """Zero-copy alias of ``numel(shape)`` elements of ``base`` starting at ``offset_elems`` (slots of
+        the data-parallel gradient arena)."""
+        out = cls.__new__(cls)
+        out.shape = tuple(int(s) for s in shape)
+        out.dtype = np.float32
+        out.size = _numel(out.shape)
+        if offset_elems < 0 or offset_elems + out.size > base.size:
+            raise Exception(f"alias of {out.size} elements at {offset_elems} does not fit a buffer of {base.size}")
+        out._base = base._base if base._base is not None else base
+        out._ptr = base.ptr + 4 * int(offset_elems)
+        return out
+
     def numpy(self):
         """Blocking device-to-host copy (the only synchronising operation besides sync())."""
         out = np.empty(self.shape, dtype=np.float32)

@@ -21,6 +21,7 @@ to float64 through Add.backward / OneHot / Max.backward, ops_cpu.py:43,126,174).
 import numpy as np
 
 from nanograd_b200 import backend as B
+from nanograd_b200 import dist as _dist
 from nanograd_b200.autograd import Function
 from nanograd_b200.nn.buffer import DeviceBuffer, ScalarBuffer
 
@@ -49,6 +50,17 @@ def _needs(ctx, i):
         return False
     p = ctx.parents[i]
     return bool(p.requires_grad or getattr(p, "is_parameter", False))
+
+
+def _param_out(ctx, i, shape):
+    """Output buffer for the gradient of parent ``i``.  Under data parallelism a parameter's gradient
+    is produced straight into its slot of the flat gradient arena (dist.GradBucket: no pack copy, and
+    the slot's chunk can go to NCCL while backward continues); otherwise a fresh buffer.  Returns
+    (buffer, token); call ``_dist.grad_slot_filled(token)`` once the kernel filling it is enqueued."""
+    buf, token = _dist.grad_slot(ctx, i, shape)
+    if buf is None:
+        return DeviceBuffer(shape), None
+    return buf, token
 
 
 def _unary(op, a):
@@ -124,13 +136,14 @@ def _norm_axes(axis, ndim):
     return sorted({int(a) % ndim for a in axis})
 
 
-def _reduce(op, x, axes, keepdims=False):
+def _reduce(op, x, axes, keepdims=False, out=None):
     """Reduce ``x`` over ``axes`` (list of non-negative ints)."""
     nd = len(x.shape)
     mask = [1 if i in axes else 0 for i in range(nd)]
     kept = [x.shape[i] for i in range(nd) if not mask[i]]
     full = [1 if mask[i] else x.shape[i] for i in range(nd)]
-    out = DeviceBuffer(kept if kept else (1,))
+    if out is None:
+        out = DeviceBuffer(kept if kept else (1,))
     _lib().ng_reduce(op, out.ptr, x.ptr, nd, B.i64_array(x.shape), B.i32_array(mask))
     if keepdims:
         return out.view(full)
@@ -497,7 +510,7 @@ class Tanh(Function):
 # ------------------------------------------------------------------------------------------
 # contractions
 # ------------------------------------------------------------------------------------------
-def _gemm(a, b, trans_a=False, trans_b=False, bias=None, flags=0):
+def _gemm(a, b, trans_a=False, trans_b=False, bias=None, flags=0, out=None):
     """(batched) row-major op(a) @ op(b) (+ bias over the last axis)."""
     if len(a.shape) < 2 or len(b.shape) < 2:
         raise Exception(f"matmul needs operands with at least 2 axes, got {a.shape} and {b.shape}")
@@ -510,7 +523,8 @@ def _gemm(a, b, trans_a=False, trans_b=False, bias=None, flags=0):
     bk, bn = (b.shape[-1], b.shape[-2]) if trans_b else (b.shape[-2], b.shape[-1])
     if ak != bk:
         raise Exception(f"matmul: inner dimensions differ ({a.shape} @ {b.shape}, trans_a={trans_a}, trans_b={trans_b})")
-    out = DeviceBuffer(tuple(batch_shape) + (am, bn))
+    if out is None:
+        out = DeviceBuffer(tuple(batch_shape) + (am, bn))
     _lib().ng_gemm(out.ptr, a.ptr, b.ptr, am, bn, ak, int(trans_a), int(trans_b), max(batch, 1),
                    bias.ptr if bias is not None else 0, flags | B.math_flags())
     return out
@@ -527,8 +541,15 @@ class MatMul(Function):
     @staticmethod
     def backward(ctx, grad_output):
         a, b = ctx.saved_tensors
-        ga = _gemm(grad_output, b, trans_b=True) if _needs(ctx, 0) else None
-        gb = _gemm(a, grad_output, trans_a=True) if _needs(ctx, 1) else None
+        ga = gb = None
+        if _needs(ctx, 0):
+            out, tok = _param_out(ctx, 0, a.shape)
+            ga = _gemm(grad_output, b, trans_b=True, out=out)
+            _dist.grad_slot_filled(tok)
+        if _needs(ctx, 1):
+            out, tok = _param_out(ctx, 1, b.shape)
+            gb = _gemm(a, grad_output, trans_a=True, out=out)
+            _dist.grad_slot_filled(tok)
         return ga, gb
 
 
@@ -562,7 +583,7 @@ def _tc_plan(geom, stride):
     return plan
 
 
-def _stage_nhwc(buf, channel_sums=False):
+def _stage_nhwc(buf, channel_sums=False, sums_out=None):
     """Channels-last staging copy of an NCHW buffer for the tensor-core kernels (made once, shared
     by the passes of one layer that read the same tensor).  channel_sums=True also returns the
     per-channel sums of `buf` from the same read (the bias gradient when `buf` is dy)."""
@@ -571,7 +592,7 @@ def _stage_nhwc(buf, channel_sums=False):
     out = DeviceBuffer(buf.shape)
     out.staged_flags = B.math_flags()
     if channel_sums and n <= 65535:
-        sums = DeviceBuffer((c,))
+        sums = sums_out if sums_out is not None else DeviceBuffer((c,))
         _lib().ng_conv2d_stage_nhwc_sum(out.ptr, buf.ptr, sums.ptr, n, c, hw, B.math_flags())
         return out, sums
     _lib().ng_conv2d_stage_nhwc(out.ptr, buf.ptr, n, c, hw, B.math_flags())
@@ -596,9 +617,9 @@ def _conv2d_dgrad(dy, w, x_shape, stride, padding, dy_nhwc=None):
     return dx
 
 
-def _conv2d_wgrad(dy, x, w_shape, stride, padding, x_nhwc=None, dy_nhwc=None):
+def _conv2d_wgrad(dy, x, w_shape, stride, padding, x_nhwc=None, dy_nhwc=None, out=None):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x.shape, w_shape, stride, padding)
-    dw = DeviceBuffer(w_shape)
+    dw = out if out is not None else DeviceBuffer(w_shape)
     xs, fx = (x_nhwc, B.F_X_NHWC) if x_nhwc is not None else (x, 0)
     ds, fd = (dy_nhwc, B.F_DY_NHWC) if dy_nhwc is not None else (dy, 0)
     _lib().ng_conv2d_wgrad(dw.ptr, ds.ptr, xs.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow,
@@ -626,22 +647,34 @@ def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding, want
     if x_nhwc is not None and (not w_tc or getattr(x_nhwc, "staged_flags", None) != B.math_flags()):
         x_nhwc = None  # math mode changed between forward and backward: restage inside the call
     dy_nhwc = db = None
+    db_out, db_tok = _param_out(ctx, 2, (weight.shape[0],)) if want_db else (None, None)
     if need_dx and need_dw and d_tc and w_tc:
         # one staging pass of dy serves dgrad and wgrad, and the bias gradient rides on its read
-        dy_nhwc, db = _stage_nhwc(grad_output, channel_sums=True) if want_db else (_stage_nhwc(grad_output), None)
-    dx = _conv2d_dgrad(grad_output, weight, input.shape, stride, padding, dy_nhwc=dy_nhwc) if need_dx else None
-    dw = _conv2d_wgrad(grad_output, input, weight.shape, stride, padding, x_nhwc=x_nhwc, dy_nhwc=dy_nhwc) \
-        if need_dw else None
+        dy_nhwc, db = _stage_nhwc(grad_output, channel_sums=True, sums_out=db_out) if want_db \
+            else (_stage_nhwc(grad_output), None)
+    # wgrad first: it is what the data-parallel gradient arena is waiting for (dgrad only feeds this rank)
+    dw = None
+    if need_dw:
+        dw_out, dw_tok = _param_out(ctx, 1, weight.shape)
+        dw = _conv2d_wgrad(grad_output, input, weight.shape, stride, padding, x_nhwc=x_nhwc, dy_nhwc=dy_nhwc, out=dw_out)
     if want_db:
-        return dx, dw, (db if db is not None else _channel_sum(grad_output))
+        if db is None:
+            db = _channel_sum(grad_output, out=db_out)
+        _dist.grad_slot_filled(db_tok)
+    if need_dw:
+        _dist.grad_slot_filled(dw_tok)
+    dx = _conv2d_dgrad(grad_output, weight, input.shape, stride, padding, dy_nhwc=dy_nhwc) if need_dx else None
+    if want_db:
+        return dx, dw, db
     return dx, dw
 
 
-def _channel_sum(dy):
+def _channel_sum(dy, out=None):
     """Bias gradient: sum over every axis but axis 1 (Add.backward's unbroadcast, ops_cpu.py:12-18)."""
     n, k = dy.shape[0], dy.shape[1]
     inner = _numel(dy.shape[2:])
-    out = DeviceBuffer((k,))
+    if out is None:
+        out = DeviceBuffer((k,))
     _lib().ng_channel_sum(out.ptr, dy.ptr, n, k, inner)
     return out
 
@@ -750,13 +783,18 @@ class Linear(Function):
     @staticmethod
     def backward(ctx, grad_output):
         input, weight = ctx.saved_tensors
+        dw = db = None
+        if _needs(ctx, 1):
+            out, tok = _param_out(ctx, 1, weight.shape)
+            dw = _gemm(grad_output, input, trans_a=True, out=out)                  # (out,B)@(B,in)
+            _dist.grad_slot_filled(tok)
+        if len(ctx.parents) >= 3 and _needs(ctx, 2):
+            out, tok = _param_out(ctx, 2, (grad_output.shape[1],))
+            db = _reduce(B.R_SUM, grad_output, [0], out=out)
+            _dist.grad_slot_filled(tok)
         dx = _gemm(grad_output, weight) if _needs(ctx, 0) else None               # (B,out)@(out,in)
-        dw = _gemm(grad_output, input, trans_a=True) if _needs(ctx, 1) else None   # (out,B)@(B,in)
         if len(ctx.parents) < 3:
             return dx, dw
-        db = None
-        if _needs(ctx, 2):
-            db = _reduce(B.R_SUM, grad_output, [0])
         return dx, dw, db
 
 
@@ -979,9 +1017,11 @@ class BatchNorm2d(Function):
         hw = _numel(input.shape[2:])
         if training:
             dx = DeviceBuffer(input.shape)
-            dgamma, dbeta = DeviceBuffer((c,)), DeviceBuffer((c,))
+            (dgamma, tok_g), (dbeta, tok_b) = _param_out(ctx, 1, (c,)), _param_out(ctx, 2, (c,))
             _lib().ng_bn2d_act_bwd(dx.ptr, dgamma.ptr, dbeta.ptr, grad_output.ptr, input.ptr, gamma.ptr, beta.ptr,
                                    save_mean.ptr, save_invstd.ptr, n, c, hw, act)
+            _dist.grad_slot_filled(tok_g)
+            _dist.grad_slot_filled(tok_b)
             return dx, dgamma, dbeta
         # constants statistics: y = (x - m) * g * inv + b
         bshape = (1, c) + (1,) * (len(input.shape) - 2)

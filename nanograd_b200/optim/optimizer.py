@@ -82,6 +82,9 @@ def device_sgd_step(opt):
 def device_adam_step(opt, decoupled_weight_decay=False):
     """Adam (optimizer.py:79-89) / AdamW (optimizer.py:115-128), one launch.  ``opt.t`` has
     already been advanced by the caller."""
+    if B.graph_capturing():
+        raise Exception("Adam/AdamW cannot be captured into a replayable step: the bias corrections 1 - beta^t are "
+                        "host scalars that change every step (capture SGD steps, or run Adam eagerly)")
     n, (p, g, m, v), numels, scale = _device_tables(opt, opt.exp_avg, opt.exp_avg_sq)
     if n:
         wd = float(opt.weight_decay) if decoupled_weight_decay else 0.0

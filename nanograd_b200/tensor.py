@@ -154,7 +154,14 @@ class Tensor:
         if self.shape != (1,):
             raise Exception("Can't initiate backprop from a non scalar-valued tensor.")
 
-        self.grad = Tensor.ones(self.shape, device=self.device, requires_grad=False)
+        if isinstance(self.data, DeviceBuffer):
+            # seed gradient written by a kernel (no host-to-device copy: the step stays capturable)
+            from nanograd_b200 import backend
+            seed = DeviceBuffer(self.shape)
+            backend.lib().ng_fill(seed.ptr, 1.0, seed.size)
+            self.grad = Tensor(seed, device=self.device, requires_grad=False)
+        else:
+            self.grad = Tensor.ones(self.shape, device=self.device, requires_grad=False)
 
         for node in reversed(self.build_graph_topology()):
             assert node.grad is not None, 'Got an unitialized gradient node'

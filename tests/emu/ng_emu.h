@@ -56,6 +56,8 @@ typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 typedef struct ng_emu_stream* cudaStream_t;
 typedef struct ng_emu_event* cudaEvent_t;
+typedef struct ng_emu_graph* cudaGraph_t;       // graphs are not emulated: the types exist so runtime.cu compiles
+typedef struct ng_emu_graph_exec* cudaGraphExec_t;
 struct ng_emu_event { std::chrono::steady_clock::time_point t; };
 enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaEventDisableTiming = 2 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };

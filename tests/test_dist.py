@@ -1,6 +1,7 @@
-"""Data-parallel path: sharding arithmetic, the gloo control plane at world size 2
-on CPU, and — on a box with >= 2 B200s — the NCCL gradient allreduce + fused optimizer step against
-the single-process oracle on the global batch."""
+"""Data-parallel path: sharding arithmetic; at world size 2 on CPU (gloo) the host-side
+gradient math and the full device code path on the emulated kernels (gradient arena, chunked allreduce,
+SyncBN, fused optimizer); and — on a box with >= 2 B200s (`gpurun --gpus 2`) — the same over NCCL against the
+single-process oracle on the global batch."""
 import os
 import socket
 import subprocess
@@ -39,6 +40,14 @@ def test_shard_bounds_partition_the_batch():
 
 def test_world2_gloo_control_plane_and_dp_gradient_math():
     res = _torchrun("cpu")
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "DIST_OK 0" in res.stdout and "DIST_OK 1" in res.stdout, res.stdout[-2000:]
+
+
+def test_world2_emulated_dp_path_matches_global_batch_oracle():
+    """The whole data-parallel code path (gradient arena with in-place slots and chunked allreduce,
+    synchronised BatchNorm, fused optimizer) on the host emulation of the kernels over gloo."""
+    res = _torchrun("emu", timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "DIST_OK 0" in res.stdout and "DIST_OK 1" in res.stdout, res.stdout[-2000:]
 
