@@ -721,6 +721,40 @@ static inline TileShape tile_shape(int t) {
   }
 }
 // `wide_ok`: the loader supports BM > 128 (gather and GEMM loaders do, wgrad's does not)
+// Tiny GEMMs (classifier heads, the README CNN's Linear(400, 10) and its backward products): the tiled
+// kernel runs them as one or a few CTAs whose K loop is a chain of exposed global-load latencies (70 us
+// for 128x10x400).  Here a thread owns one output element and walks K with four independent partial
+// sums; operands come through L1/L2 by their strides, so x @ W.T, dy @ W and dy.T @ x need no transpose.
+struct GemmSmallP {
+  const float* a;      // op(A)[m, k] = a[m * sam + k * sak]
+  const float* b;      // op(B)[k, n] = b[k * sbk + n * sbn]
+  float* c;
+  const float* bias;   // per output column n, or nullptr
+  int M, N, K, relu;
+  long long sam, sak, sbk, sbn;
+};
+
+__global__ void __launch_bounds__(128) gemm_small_kernel(const GemmSmallP p) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)p.M * p.N) return;
+  const int m = (int)(e / p.N), n = (int)(e - (long long)m * p.N);
+  const float* __restrict__ a = p.a + m * p.sam;
+  const float* __restrict__ b = p.b + n * p.sbn;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= p.K; k += 4) {
+    s0 = fmaf(a[(k + 0) * p.sak], b[(k + 0) * p.sbk], s0);
+    s1 = fmaf(a[(k + 1) * p.sak], b[(k + 1) * p.sbk], s1);
+    s2 = fmaf(a[(k + 2) * p.sak], b[(k + 2) * p.sbk], s2);
+    s3 = fmaf(a[(k + 3) * p.sak], b[(k + 3) * p.sbk], s3);
+  }
+  for (; k < p.K; ++k) s0 = fmaf(a[k * p.sak], b[k * p.sbk], s0);
+  float v = (s0 + s1) + (s2 + s3);
+  if (p.bias) v += p.bias[n];
+  if (p.relu) v = fmaxf(v, 0.f);
+  p.c[e] = v;
+}
+
 static inline int pick_tile(long long I, int J, bool wide_ok) {
   if (J > 64) return TILE_A;
   if (J > 32) return (wide_ok && I >= 256) ? TILE_B : TILE_D;
@@ -1023,8 +1057,19 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
   const int sms = g_sm_count > 0 ? g_sm_count : 148;
   // split the reduction so that the grid fills whole waves of 2 CTAs per SM (a ragged last wave
   // is the dominant loss for these small-output problems); every split at least 64 K-tiles deep
-  const long long max_splits = total_kt / 64 > 0 ? total_kt / 64 : 1;
-  long long splits = pick_splits(tiles, 2 * sms, max_splits < 512 ? max_splits : 512);
+  // Tiny layers (the README CNN: < 64 MFLOP per pass) are a chain of exposed load latencies per CTA, not
+  // FFMA work: cut them into many short splits (>= 8 K-tiles) and oversubscribe the SMs so that several
+  // CTAs hide each other's latency; the partials are folded by the wide (8 threads per output) reduce.
+  const bool tiny = 2.0 * N * K * C * R * S * (double)OH * OW < 64.0e6;
+  const long long min_depth = tiny ? 8 : 64;
+  const long long max_splits = total_kt / min_depth > 0 ? total_kt / min_depth : 1;
+#ifdef NG_EMU
+  const long long tiny_cap = 4;    // the host emulation runs every CUDA thread as a host thread
+#else
+  const long long tiny_cap = 2048;
+#endif
+  long long splits = tiny ? pick_splits(tiles, 6 * sms, max_splits < tiny_cap ? max_splits : tiny_cap)
+                          : pick_splits(tiles, 2 * sms, max_splits < 512 ? max_splits : 512);
   p.kt_per_split = (int)ceil_div(total_kt, splits);
   splits = ceil_div(total_kt, p.kt_per_split);
   const long long out_elems = (long long)K * p.CRS;
@@ -1044,10 +1089,15 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
   NG_TILE_SWITCH_NARROW(tile, NG_LAUNCH((conv_wgrad_kernel<TT>), grid, CT_THREADS, 0, p));
   NG_CHECK_LAUNCH();
   if (splits > 1) {
-    int g = (int)ceil_div(out_elems, 256);
-    if (g > sms * 8) g = sms * 8;
-    NG_LAUNCH(splitk_reduce_kernel, g, 256, 0, dptr<float>(dw), (const float*)ws, (int)splits, out_elems,
-              (const float*)nullptr, 1, 0);
+    if (splits >= 32 && out_elems <= 65536) {
+      NG_LAUNCH(splitk_reduce_wide_kernel, (int)ceil_div(out_elems, 64), 512, 0, dptr<float>(dw), (const float*)ws,
+                (int)splits, out_elems);
+    } else {
+      int g = (int)ceil_div(out_elems, 256);
+      if (g > sms * 8) g = sms * 8;
+      NG_LAUNCH(splitk_reduce_kernel, g, 256, 0, dptr<float>(dw), (const float*)ws, (int)splits, out_elems,
+                (const float*)nullptr, 1, 0);
+    }
     NG_CHECK_LAUNCH();
     pool_free(ws);
   }
@@ -1072,6 +1122,28 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
     if (rc >= 0) return rc;
   }
 #endif
+  // tiny problems: one thread per output (see gemm_small_kernel)
+#ifdef NG_EMU
+  const long long small_out_cap = 4096;   // the host emulation runs every CUDA thread as a host thread
+#else
+  const long long small_out_cap = 262144;
+#endif
+  if (batch == 1 && K > 0 && (double)M * N * K <= 4.0e6 && M * N <= small_out_cap && (M * N >= 256 || K <= 4096)) {
+    GemmSmallP q;
+    q.a = dptr<const float>(a);
+    q.b = dptr<const float>(b);
+    q.c = dptr<float>(c);
+    q.bias = bias ? dptr<const float>(bias) : nullptr;
+    q.M = (int)M; q.N = (int)N; q.K = (int)K;
+    q.relu = (flags & NG_F_RELU) ? 1 : 0;
+    q.sam = trans_a ? 1 : K; q.sak = trans_a ? M : 1;
+    q.sbk = trans_b ? 1 : N; q.sbn = trans_b ? K : 1;
+    const int tok = prof_begin(NG_PROF_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N));
+    NG_LAUNCH(gemm_small_kernel, (int)ceil_div(M * N, 128), 128, 0, q);
+    NG_CHECK_LAUNCH();
+    prof_end(tok);
+    return 0;
+  }
   // Row-major C[M,N]: the contiguous output index is n → I = N, J = M.
   //   a(i=n, k) = B[k, n]  → !trans_b: B is [K,N], sai = 1,  sak = N ; trans_b: B is [N,K], sai = K, sak = 1
   //   b(k, j=m) = A[m, k]  → !trans_a: A is [M,K], sbj = K,  sbk = 1 ; trans_a: A is [K,M], sbj = 1, sbk = M

@@ -176,6 +176,9 @@ static int run_reduce(float* out, const float* in, ReduceDesc d, bool inner_redu
 }
 
 // out[s][c] = sum over n in split s, p of in[n][c][p]; grid = (C, S)
+// A warp walks whole (image, channel) planes, its lanes the contiguous pixels: coalesced, and no index
+// division anywhere (the per-element 64-bit div/mod of a flat loop cost 36 us on the 11x11 planes of the
+// README CNN's bias gradient).  Two planes in flight per warp.
 __global__ void __launch_bounds__(256) channel_sum_kernel(float* __restrict__ partial, const float* __restrict__ in,
                                                           int64_t N, int64_t C, int64_t P, int64_t n_per_split,
                                                           int vec_ok) {
@@ -184,23 +187,28 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(float* __restrict__ pa
   const int64_t n0 = s * n_per_split;
   int64_t n1 = n0 + n_per_split;
   if (n1 > N) n1 = N;
-  float acc = 0.f;
-  if (vec_ok) {
-    const int64_t P4 = P >> 2;
-    const int64_t items = (n1 - n0) * P4;
-    for (int64_t i = threadIdx.x; i < items; i += blockDim.x) {
-      const int64_t n = n0 + i / P4, p4 = i % P4;
-      const float4 v = *reinterpret_cast<const float4*>(in + (n * C + c) * P + (p4 << 2));
-      acc += (v.x + v.y) + (v.z + v.w);
-    }
-  } else {
-    const int64_t items = (n1 - n0) * P;
-    for (int64_t i = threadIdx.x; i < items; i += blockDim.x) {
-      const int64_t n = n0 + i / P, p = i % P;
-      acc += in[(n * C + c) * P + p];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int64_t n = n0 + warp; n < n1; n += 2 * nwarps) {
+    const float* r0 = in + (n * C + c) * P;
+    const bool two = n + nwarps < n1;
+    const float* r1 = two ? in + ((n + nwarps) * C + c) * P : r0;
+    if (vec_ok) {
+      const int64_t P4 = P >> 2;
+      for (int64_t q = lane; q < P4; q += 32) {
+        const float4 v = reinterpret_cast<const float4*>(r0)[q];
+        const float4 w = two ? reinterpret_cast<const float4*>(r1)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc0 += (v.x + v.y) + (v.z + v.w);
+        acc1 += (w.x + w.y) + (w.z + w.w);
+      }
+    } else {
+      for (int64_t q = lane; q < P; q += 32) {
+        acc0 += r0[q];
+        if (two) acc1 += r1[q];
+      }
     }
   }
-  const float t = block_sum(acc, scratch);
+  const float t = block_sum(acc0 + acc1, scratch);
   if (threadIdx.x == 0) partial[s * C + c] = t;
 }
 

@@ -37,6 +37,7 @@
 
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
   unsigned x, y, z;

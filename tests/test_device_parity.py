@@ -21,8 +21,7 @@ EMU_SUBSET = (
     + ["matmul", "maxpool2d_p2", "maxpool2d_p3", "avgpool2d_p2", "avgpool2d_p4", "maxpool1d_p2", "avgpool1d_p3",
        "logsoftmax_nll", "elementwise", "reductions", "shapes", "batchnorm2d", "batchnorm1d",
        "mnist_cnn_sgd", "vgg_bn_sgd", "attention_adamw", "tinynet_sgdm", "tinynet_adam", "tinynet_adamw2",
-       "linear_stack", "conv2d_wide_c64_k32_p1", "activation_mlp_sgdm", "activation_mlp_adam",
-       "mnist_cnn_adam_10steps"]
+       "linear_stack", "conv2d_wide_c64_k32_p1", "activation_mlp_sgdm", "activation_mlp_adam"]
 )
 
 # cases whose convolutions the tensor-core path accepts; run in TF32 mode at the north-star's TF32 bar

@@ -22,10 +22,10 @@ CASES = cases.all_cases()
 
 EMU_FUSED = ["conv2d_k3_s1", "conv1d_k3_s2", "matmul", "maxpool2d_p2", "avgpool2d_p2", "maxpool1d_p2",
              "logsoftmax_nll", "elementwise", "reductions", "shapes", "batchnorm2d", "batchnorm1d", "mnist_cnn_sgd",
-             "mnist_cnn_adam", "vgg_bn_adam", "attention_adamw", "tinynet_sgdm", "tinynet_adamw2", "linear_stack",
+             "vgg_bn_adam", "attention_adamw", "tinynet_sgdm", "tinynet_adamw2", "linear_stack",
              "activation_mlp_sgdm", "conv2d_wide_c64_k32_p1"]
-EMU_PRIMITIVES = ["maxpool2d_p3", "avgpool2d_p4", "logsoftmax_nll", "batchnorm2d", "batchnorm1d", "mnist_cnn_sgdm",
-                  "vgg_bn_sgd", "tinynet_adam", "activation_mlp_adam"]
+EMU_PRIMITIVES = ["maxpool2d_p3", "avgpool2d_p4", "logsoftmax_nll", "batchnorm2d", "batchnorm1d", "vgg_bn_sgd",
+                  "tinynet_adam", "activation_mlp_adam", "conv2d_wide_c64_k32_p1"]
 
 
 def _bound_reference(fused):

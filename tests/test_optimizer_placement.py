@@ -36,9 +36,9 @@ def test_train_helper_with_optimizer_built_on_the_host(device_lib):
     np.random.seed(1)
     model = H.build_mnist_cnn(nn)
     opt = optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
-    X = np.random.rand(64, 784).astype(np.float32)
-    Y = np.random.randint(0, 10, 64).astype(np.float32)
-    data.train(model, X, Y, opt, steps=3, batch_size=16, device=Device.GPU)
+    X = np.random.rand(16, 784).astype(np.float32)
+    Y = np.random.randint(0, 10, 16).astype(np.float32)
+    data.train(model, X, Y, opt, steps=2, batch_size=4, device=Device.GPU)
     assert all(m.device == Device.GPU for m in opt.momentums)
 
 
