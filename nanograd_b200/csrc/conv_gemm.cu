@@ -393,6 +393,80 @@ __global__ void __launch_bounds__(512) splitk_reduce_wide_kernel(float* __restri
   }
 }
 
+// ---- direct wgrad for tiny layers (the README CNN: C*R*S*K <= 2048 filter taps, one image's x and dy fit
+// shared memory).  The implicit-GEMM kernel runs these as hundreds of 8-tile splits whose every step is
+// an exposed load latency (32 us for conv1 at batch 128).  Here a CTA stages whole images, thread
+// (group g, tap o) accumulates dW[o] over the output rows oh = g (mod G) in registers — dy is a warp
+// broadcast, x a conflict-free shifted read — and one partial per CTA goes to the fixed-order reduce.
+struct WgradTinyP {
+  const float* x;
+  const float* dy;
+  float* ws;      // [grid][K*C*R*S]
+  int N, C, H, W, K, R, S, OH, OW, stride, pad_t, pad_l;
+  int O, G;       // O = K*C*R*S taps, G = row groups sharing a tap
+};
+
+__global__ void __launch_bounds__(256) conv_wgrad_tiny_kernel(const __grid_constant__ WgradTinyP p) {
+  NG_DYN_SMEM(float, sm);
+  float* xs = sm;                                // [C][H][W]
+  float* ds = sm + p.C * p.H * p.W;              // [K][OH][OW]
+  float* red = ds + p.K * p.OH * p.OW;           // [G][O] (G > 1 only)
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int x_elems = p.C * p.H * p.W, d_elems = p.K * p.OH * p.OW;
+  constexpr int kMaxPer = 8;                     // taps per thread when O > blockDim.x
+  float acc[kMaxPer];
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) acc[j] = 0.f;
+  const int g = p.G > 1 ? tid / p.O : 0;
+  const bool active = p.G > 1 ? (tid < p.G * p.O) : true;
+  for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+    __syncthreads();
+    const float* xg = p.x + (long long)n * x_elems;
+    const float* dg = p.dy + (long long)n * d_elems;
+    for (int i = tid; i < x_elems; i += T) xs[i] = xg[i];
+    for (int i = tid; i < d_elems; i += T) ds[i] = dg[i];
+    __syncthreads();
+    if (!active) continue;
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {
+      const int o = p.G > 1 ? tid - g * p.O : tid + j * T;
+      if (o >= p.O || (p.G > 1 && j > 0)) break;
+      const int s = o % p.S, r = (o / p.S) % p.R, c = (o / (p.S * p.R)) % p.C, k = o / (p.S * p.R * p.C);
+      const float* dk = ds + k * p.OH * p.OW;
+      const float* xc = xs + c * p.H * p.W;
+      float a = 0.f;
+      for (int oh = g; oh < p.OH; oh += p.G) {
+        const int ih = oh * p.stride + r - p.pad_t;
+        if (ih < 0 || ih >= p.H) continue;
+        const float* drow = dk + oh * p.OW;
+        const float* xrow = xc + ih * p.W + (s - p.pad_l);
+        for (int ow = 0; ow < p.OW; ++ow) {
+          const int iw = ow * p.stride + s - p.pad_l;
+          if (iw >= 0 && iw < p.W) a = fmaf(drow[ow], xrow[ow * p.stride], a);
+        }
+      }
+      acc[j] += a;
+    }
+  }
+  float* out = p.ws + (long long)blockIdx.x * p.O;
+  if (p.G > 1) {
+    __syncthreads();
+    if (active) red[g * p.O + (tid - g * p.O)] = acc[0];
+    __syncthreads();
+    if (tid < p.O) {
+      float t = 0.f;
+      for (int q = 0; q < p.G; ++q) t += red[q * p.O + tid];
+      out[tid] = t;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {
+      const int o = tid + j * T;
+      if (o < p.O) out[o] = acc[j];
+    }
+  }
+}
+
 // =====================================================================================
 // wgrad: dW[k][c][r][s] = sum_{n,oh,ow} dy[n,k,oh,ow] * x[n,c,oh*st+r-pt,ow*st+s-pl]
 //   I = flattened (c,r,s), J = k, reduction over (n, oh, ow) split across grid.z
@@ -734,25 +808,56 @@ struct GemmSmallP {
   long long sam, sak, sbk, sbn;
 };
 
+// LANES = 1: a thread owns an output and walks K (short reductions).  LANES = 32: a warp owns an output,
+// its lanes take every 32nd k (coalesced when the operand is k-contiguous) and a shuffle tree adds them in
+// a fixed order (long reductions: 13 steps instead of 400 for the README CNN's Linear(400, 10)).
+template <int LANES>
 __global__ void __launch_bounds__(128) gemm_small_kernel(const GemmSmallP p) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)p.M * p.N) return;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = LANES == 1 ? t : t >> 5;
+  if (e >= (long long)p.M * p.N) return;   // LANES = 32: whole warps leave together
+  const int lane = LANES == 1 ? 0 : (int)(threadIdx.x & 31);
   const int m = (int)(e / p.N), n = (int)(e - (long long)m * p.N);
   const float* __restrict__ a = p.a + m * p.sam;
   const float* __restrict__ b = p.b + n * p.sbn;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int k = 0;
-  for (; k + 4 <= p.K; k += 4) {
-    s0 = fmaf(a[(k + 0) * p.sak], b[(k + 0) * p.sbk], s0);
-    s1 = fmaf(a[(k + 1) * p.sak], b[(k + 1) * p.sbk], s1);
-    s2 = fmaf(a[(k + 2) * p.sak], b[(k + 2) * p.sbk], s2);
-    s3 = fmaf(a[(k + 3) * p.sak], b[(k + 3) * p.sbk], s3);
+  int k = lane;
+  for (; k + 3 * LANES < p.K; k += 4 * LANES) {
+    s0 = fmaf(a[(long long)(k + 0 * LANES) * p.sak], b[(long long)(k + 0 * LANES) * p.sbk], s0);
+    s1 = fmaf(a[(long long)(k + 1 * LANES) * p.sak], b[(long long)(k + 1 * LANES) * p.sbk], s1);
+    s2 = fmaf(a[(long long)(k + 2 * LANES) * p.sak], b[(long long)(k + 2 * LANES) * p.sbk], s2);
+    s3 = fmaf(a[(long long)(k + 3 * LANES) * p.sak], b[(long long)(k + 3 * LANES) * p.sbk], s3);
   }
-  for (; k < p.K; ++k) s0 = fmaf(a[k * p.sak], b[k * p.sbk], s0);
+  for (; k < p.K; k += LANES) s0 = fmaf(a[(long long)k * p.sak], b[(long long)k * p.sbk], s0);
   float v = (s0 + s1) + (s2 + s3);
+  if (LANES == 32) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane != 0) return;
+  }
   if (p.bias) v += p.bias[n];
   if (p.relu) v = fmaxf(v, 0.f);
   p.c[e] = v;
+}
+
+// out[e] = sum_s ws[s][e], one warp per output: lanes take every 32nd partial, fixed-order shuffle tree
+// (hundreds of short wgrad splits folded into a few dozen filter taps)
+__global__ void __launch_bounds__(256) splitk_reduce_warp_kernel(float* __restrict__ out, const float* __restrict__ ws,
+                                                                 int S, long long n) {
+  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= n) return;
+  const int lane = threadIdx.x & 31;
+  float a0 = 0.f, a1 = 0.f;
+  int s = lane;
+  for (; s + 32 < S; s += 64) {
+    a0 += ws[(long long)s * n + e];
+    a1 += ws[(long long)(s + 32) * n + e];
+  }
+  if (s < S) a0 += ws[(long long)s * n + e];
+  float v = a0 + a1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) out[e] = v;
 }
 
 static inline int pick_tile(long long I, int J, bool wide_ok) {
@@ -993,6 +1098,42 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
              "ng_conv2d_wgrad: staged NHWC operands given but this shape does not take the tensor-core kernel");
   const int sms_all = g_sm_count > 0 ? g_sm_count : 148;
   {
+    // tiny layer: direct kernel over whole images in shared memory (see conv_wgrad_tiny_kernel)
+    const long long O = (long long)K * C * R * S;
+    const long long img_floats = (long long)C * H * W + (long long)K * OH * OW;
+    const int G = O < 256 ? (int)(256 / O) : 1;
+    const size_t smem = sizeof(float) * (size_t)(img_floats + (G > 1 ? G * O : 0));
+    if (2.0 * N * K * C * R * S * (double)OH * OW < 64.0e6 && O <= 2048 && smem <= 48 * 1024) {
+      WgradTinyP q;
+      memset(&q, 0, sizeof(q));
+      q.x = dptr<const float>(x);
+      q.dy = dptr<const float>(dy);
+      q.N = N; q.C = C; q.H = H; q.W = W; q.K = K; q.R = R; q.S = S; q.OH = OH; q.OW = OW;
+      q.stride = stride; q.pad_t = pad_t; q.pad_l = pad_l;
+      q.O = (int)O;
+      q.G = G < OH ? G : (OH > 0 ? OH : 1);
+      int grid = N < 2 * sms_all ? N : 2 * sms_all;
+      float* ws = nullptr;
+      int r = pool_alloc((void**)&ws, (uint64_t)((long long)grid * O) * sizeof(float));
+      if (r) return r;
+      q.ws = ws;
+      const int tok = prof_begin(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
+                                 4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
+      NG_LAUNCH(conv_wgrad_tiny_kernel, grid, 256, smem, q);
+      NG_CHECK_LAUNCH();
+      if (grid >= 64 && O <= 4096) {
+        NG_LAUNCH(splitk_reduce_warp_kernel, (int)ceil_div(O * 32, 256), 256, 0, dptr<float>(dw), (const float*)ws, grid, O);
+      } else {
+        NG_LAUNCH(splitk_reduce_kernel, (int)ceil_div(O, 256), 256, 0, dptr<float>(dw), (const float*)ws, grid, O,
+                  (const float*)nullptr, 1, 0);
+      }
+      NG_CHECK_LAUNCH();
+      pool_free(ws);
+      prof_end(tok);
+      return 0;
+    }
+  }
+  {
     // image-facing layer: direct kernel (see conv_wgrad_smallc_kernel)
     const int NR = C * R, RPG = NR < 3 ? NR : 3, G = (NR + RPG - 1) / RPG;
     const int px_budget = (40 * 1024 / 4) / K - 4;
@@ -1068,7 +1209,7 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
 #else
   const long long tiny_cap = 2048;
 #endif
-  long long splits = tiny ? pick_splits(tiles, 6 * sms, max_splits < tiny_cap ? max_splits : tiny_cap)
+  long long splits = tiny ? pick_splits(tiles, 4 * sms, max_splits < tiny_cap ? max_splits : tiny_cap)
                           : pick_splits(tiles, 2 * sms, max_splits < 512 ? max_splits : 512);
   p.kt_per_split = (int)ceil_div(total_kt, splits);
   splits = ceil_div(total_kt, p.kt_per_split);
@@ -1089,7 +1230,10 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
   NG_TILE_SWITCH_NARROW(tile, NG_LAUNCH((conv_wgrad_kernel<TT>), grid, CT_THREADS, 0, p));
   NG_CHECK_LAUNCH();
   if (splits > 1) {
-    if (splits >= 32 && out_elems <= 65536) {
+    if (splits >= 64 && out_elems <= 4096) {
+      NG_LAUNCH(splitk_reduce_warp_kernel, (int)ceil_div(out_elems * 32, 256), 256, 0, dptr<float>(dw), (const float*)ws,
+                (int)splits, out_elems);
+    } else if (splits >= 32 && out_elems <= 65536) {
       NG_LAUNCH(splitk_reduce_wide_kernel, (int)ceil_div(out_elems, 64), 512, 0, dptr<float>(dw), (const float*)ws,
                 (int)splits, out_elems);
     } else {
@@ -1139,7 +1283,8 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
     q.sam = trans_a ? 1 : K; q.sak = trans_a ? M : 1;
     q.sbk = trans_b ? 1 : N; q.sbn = trans_b ? K : 1;
     const int tok = prof_begin(NG_PROF_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N));
-    NG_LAUNCH(gemm_small_kernel, (int)ceil_div(M * N, 128), 128, 0, q);
+    if (K >= 64) NG_LAUNCH((gemm_small_kernel<32>), (int)ceil_div(M * N * 32, 128), 128, 0, q);
+    else NG_LAUNCH((gemm_small_kernel<1>), (int)ceil_div(M * N, 128), 128, 0, q);
     NG_CHECK_LAUNCH();
     prof_end(tok);
     return 0;
