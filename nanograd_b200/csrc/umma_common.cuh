@@ -159,6 +159,19 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// FP16 inputs (kind::f16, K = 16 per instruction, twice the TF32 rate), FP32 accumulation, both operands
+// from shared memory.
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // registers -> TMEM: this warp's 32 lanes x 32 consecutive columns
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -236,6 +249,17 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a
   return d;
 }
 
+// kind::f16 with FP16 inputs (A/B format 0) and FP32 accumulation
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
 // Round-to-nearest (ties away) FP32 -> TF32.  The tensor core would otherwise truncate the 13 low
 // mantissa bits (a biased, twice larger error); the staging copies round once, for free.
 __device__ __forceinline__ float tf32_round(float v) {
@@ -292,7 +316,7 @@ __device__ __forceinline__ void split_stage_hi_lo(const uint8_t* stage_raw, uint
 // Encodes a tiled FP32 tensor map.  dims/box are innermost-first; strides_bytes[i] is the byte
 // stride of dimension i+1 (dimension 0 is contiguous).  swizzle is one of the SWZ_* codes.
 int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle, int fp16 = 0);
 
 
 // ---------------------------------------------------------------- host: tensor-core convolution
@@ -307,6 +331,9 @@ int conv_dgrad_tf32(float* dx, const float* dy, const float* w, int N, int C, in
 int conv_wgrad_tf32(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int x3, int x_is_nhwc, int dy_is_nhwc);
 int to_nhwc(float* out, const float* in, int N, int C, int HW, int round);
+// FP16x3 mode: stage as the (hi, lo) FP16 NHWC pair with a power-of-two scale (umma_conv.cu); `staged`
+// holds N*C*HW*4 + 64 bytes; sums (optional) receives the per-channel sums of `in`.
+int to_nhwc_f16(void* staged, const float* in, float* sums, int N, int C, int HW);
 // to_nhwc plus sums[c] = sum over (n, p) of in[n][c][p] (the bias gradient when `in` is dy)
 int to_nhwc_sum(float* out, const float* in, float* sums, int N, int C, int HW, int round);
 // C[M,N] = op(A) @ op(B) (+ bias[N]) (ReLU), row-major FP32 (umma_gemm.cu)
