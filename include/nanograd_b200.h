@@ -158,7 +158,13 @@ int ng_onehot(uint64_t out, uint64_t labels, int64_t rows, int64_t classes);
  *                channels-last copy made by ng_conv2d_stage_nhwc with the same flags: forward and
  *                backward of one layer then share two staging passes instead of running four.  Only
  *                legal when ng_conv2d_tc_plan says that pass takes the tensor-core kernel. */
-enum { NG_F_RELU = 1, NG_F_TF32 = 2, NG_F_TF32X3 = 4, NG_F_TC_FORCE = 8, NG_F_X_NHWC = 16, NG_F_DY_NHWC = 32 };
+/*   NG_F_F16X3  FP32-accurate convolutions on tcgen05 with operands staged once per tensor as scaled
+ *                (hi, lo) FP16 pairs (11 + 11 significant bits, the precision of 3xTF32) and kind::f16 MMAs
+ *                at twice the TF32 rate; taken for stride-1 layers whose channel counts are both multiples
+ *                of 64, other layers follow NG_F_TF32X3 when that is set as well.
+ *   NG_F_STAGE_F16  (ng_conv2d_stage_nhwc*) make the FP16x3 staged copy: dst holds N*C*HW*4 + 64 bytes. */
+enum { NG_F_RELU = 1, NG_F_TF32 = 2, NG_F_TF32X3 = 4, NG_F_TC_FORCE = 8, NG_F_X_NHWC = 16, NG_F_DY_NHWC = 32,
+       NG_F_F16X3 = 64, NG_F_STAGE_F16 = 128 };
 /* C[M,N] = op(A) @ op(B) (+ bias[N]) ; row-major; op = transpose when the flag is set.
  * replaces matmul_op, ops_gpu.py:214-232, and the perm+matmul chain in MatMul.backward,
  * ops_gpu.py:452-459.  batch > 1: equally strided batches of A, B and C.
@@ -183,10 +189,13 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x,
                     int stride, int pad_t, int pad_l, int OH, int OW, int flags);
 
 /* Which of fprop / dgrad / wgrad (out[0..2]) will run on the tensor-core kernels for this geometry
- * and these flags (so a caller knows whether staging an NHWC copy pays off). */
+ * and these flags (so a caller knows whether staging an NHWC copy pays off), and out[3] = the engine:
+ * 0 none, 1 TF32 family (FP32 NHWC staging), 2 FP16x3 (stage with NG_F_STAGE_F16). */
 int ng_conv2d_tc_plan(int N, int C, int H, int W, int K, int R, int S, int stride, int OH, int OW,
-                      int flags, int* out_fprop_dgrad_wgrad);
-/* dst[n][p][c] = src[n][c][p] (p = h*W + w); rounds to TF32 when flags has NG_F_TF32. */
+                      int flags, int* out_fprop_dgrad_wgrad_engine);
+/* dst[n][p][c] = src[n][c][p] (p = h*W + w); rounds to TF32 when flags has NG_F_TF32.  With
+ * NG_F_STAGE_F16 (C % 64 == 0): dst[n][p][c / 64][hi | lo][c % 64] in FP16, scaled by a power of two,
+ * followed by 64 bytes of metadata (float 1/scale, uint32 bits of max|src|). */
 int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64_t HW, int flags);
 /* The same copy for dy that also returns the bias gradient sums[c] = sum_{n,p} src[n][c][p]
  * (Add.backward's unbroadcast of the conv bias, ops_cpu.py:12-18, module.py:476) from the one read. */

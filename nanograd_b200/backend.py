@@ -131,8 +131,9 @@ F_RELU, F_TF32, F_TF32X3 = 1, 2, 4
 #   "tf32x3"          like "fp32" but tensor cores for every supported shape, whatever its size.
 #   "tf32"  (opt-in)  tensor cores with plain TF32 inputs / FP32 accumulation (parity bar rtol 1e-2).
 # Selected with NANOGRAD_B200_MATH (or the reference-survey spelling NANOGRAD_TF32=1) or set_math_mode().
-F_TC_FORCE, F_X_NHWC, F_DY_NHWC = 8, 16, 32
-_MATH_MODES = {"fp32": F_TF32X3, "simt": 0, "tf32x3": F_TF32X3 | F_TC_FORCE, "tf32": F_TF32}
+F_TC_FORCE, F_X_NHWC, F_DY_NHWC, F_F16X3, F_STAGE_F16 = 8, 16, 32, 64, 128
+_MATH_MODES = {"fp32": F_TF32X3, "simt": 0, "tf32x3": F_TF32X3 | F_TC_FORCE, "tf32": F_TF32,
+               "fp32_f16": F_F16X3 | F_TF32X3, "f16x3": F_F16X3 | F_TF32X3 | F_TC_FORCE}
 _math_flags = _MATH_MODES["tf32" if os.environ.get("NANOGRAD_TF32", "0") == "1"
                           else os.environ.get("NANOGRAD_B200_MATH", "fp32").lower()]
 

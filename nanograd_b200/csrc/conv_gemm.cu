@@ -925,11 +925,19 @@ static int launch_conv_gather(const ConvGatherP& p, bool strided) {
   return 0;
 }
 
-// Engine selection for one convolution pass: 0 = FP32 SIMT, else the tensor-core kernel.
-static inline bool want_tensor_core(int flags, double flops) {
-  if (flags & NG_F_TF32) return true;
-  if (!(flags & NG_F_TF32X3)) return false;
-  return (flags & NG_F_TC_FORCE) || flops >= 2.0e8;
+// Engine selection for one convolution layer: 0 = FP32 SIMT, 1 = the TF32-family tensor-core kernels
+// (umma_conv.cu: TF32 or 3xTF32), 2 = the FP16x3 tensor-core kernels (umma_conv_f16.cu).  The staged
+// channels-last copies of the two families differ, so all three passes of a layer use the same family.
+static inline int conv_engine(int flags, double flops, int C, int K, int RS, int stride) {
+  if (flags & NG_F_TF32) return 1;
+  if (!(flags & (NG_F_TF32X3 | NG_F_F16X3))) return 0;
+  if (!((flags & NG_F_TC_FORCE) || flops >= 2.0e8)) return 0;
+#ifndef NG_EMU
+  if ((flags & NG_F_F16X3) && stride == 1 && umma::f16x3_supported(C, K, RS)) return 2;
+#else
+  (void)C; (void)K; (void)RS; (void)stride;
+#endif
+  return (flags & NG_F_TF32X3) ? 1 : 0;
 }
 
 static int check_conv_dims(const char* who, int N, int C, int H, int W, int K, int R, int S, int stride, int pad_t,
@@ -984,7 +992,11 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
   const int tok = prof_begin(NG_PROF_CONV_FPROP, flops, bytes);
   int rc = -1;
 #ifndef NG_EMU
-  if (want_tensor_core(flags, flops))
+  const int engine = conv_engine(flags, flops, C, K, R * S, stride);
+  if (engine == 2)
+    rc = umma::conv_fprop_f16(p.out, p.a, p.b, p.bias, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW, p.relu,
+                              (flags & NG_F_X_NHWC) ? 1 : 0);
+  else if (engine == 1)
     rc = umma::conv_fprop_tf32(p.out, p.a, p.b, p.bias, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW, p.relu,
                                (flags & NG_F_TF32) ? 0 : 1, (flags & NG_F_X_NHWC) ? 1 : 0);
 #endif
@@ -1033,7 +1045,11 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
   const int tok = prof_begin(NG_PROF_CONV_DGRAD, flops, bytes);
   int rc = -1;
 #ifndef NG_EMU
-  if (want_tensor_core(flags, flops))
+  const int engine = conv_engine(flags, flops, C, K, R * S, stride);
+  if (engine == 2)
+    rc = umma::conv_dgrad_f16(p.out, p.a, p.b, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW,
+                              (flags & NG_F_DY_NHWC) ? 1 : 0);
+  else if (engine == 1)
     rc = umma::conv_dgrad_tf32(p.out, p.a, p.b, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW,
                                (flags & NG_F_TF32) ? 0 : 1, (flags & NG_F_DY_NHWC) ? 1 : 0);
 #endif
@@ -1045,12 +1061,15 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
 }
 
 int ng_conv2d_tc_plan(int N, int C, int H, int W, int K, int R, int S, int stride, int OH, int OW, int flags,
-                      int* out_fprop_dgrad_wgrad) {
+                      int* out_fprop_dgrad_wgrad_engine) {
   (void)H; (void)W;
   const double flops = 2.0 * N * K * C * R * S * (double)OH * OW;
-  int f = 0, d = 0, w = 0;
+  int f = 0, d = 0, w = 0, engine = 0;
 #ifndef NG_EMU
-  if (stride == 1 && want_tensor_core(flags, flops)) {
+  if (stride == 1) engine = conv_engine(flags, flops, C, K, R * S, stride);
+  if (engine == 2) {
+    f = d = w = 1;
+  } else if (engine == 1) {
     f = umma::gather_supported(C, K, R * S) ? 1 : 0;
     d = umma::gather_supported(K, C, R * S) ? 1 : 0;
     w = umma::wgrad_supported(C, K, R * S) ? 1 : 0;
@@ -1058,9 +1077,10 @@ int ng_conv2d_tc_plan(int N, int C, int H, int W, int K, int R, int S, int strid
 #else
   (void)flops;
 #endif
-  out_fprop_dgrad_wgrad[0] = f;
-  out_fprop_dgrad_wgrad[1] = d;
-  out_fprop_dgrad_wgrad[2] = w;
+  out_fprop_dgrad_wgrad_engine[0] = f;
+  out_fprop_dgrad_wgrad_engine[1] = d;
+  out_fprop_dgrad_wgrad_engine[2] = w;
+  out_fprop_dgrad_wgrad_engine[3] = engine;
   return 0;
 }
 
@@ -1068,6 +1088,8 @@ int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64
   NG_ENSURE_INIT();
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL, "ng_conv2d_stage_nhwc: bad dimensions");
+  if (flags & NG_F_STAGE_F16)
+    return umma::to_nhwc_f16(dptr<void>(dst), dptr<const float>(src), nullptr, (int)N, (int)C, (int)HW);
   return umma::to_nhwc(dptr<float>(dst), dptr<const float>(src), (int)N, (int)C, (int)HW, (flags & NG_F_TF32) ? 1 : 0);
 #else
   (void)dst; (void)src; (void)N; (void)C; (void)HW; (void)flags;
@@ -1079,6 +1101,8 @@ int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t 
   NG_ENSURE_INIT();
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL && N <= 65535, "ng_conv2d_stage_nhwc_sum: bad dimensions");
+  if (flags & NG_F_STAGE_F16)
+    return umma::to_nhwc_f16(dptr<void>(dst), dptr<const float>(src), dptr<float>(sums), (int)N, (int)C, (int)HW);
   return umma::to_nhwc_sum(dptr<float>(dst), dptr<const float>(src), dptr<float>(sums), (int)N, (int)C, (int)HW,
                            (flags & NG_F_TF32) ? 1 : 0);
 #else
@@ -1092,12 +1116,17 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
   NG_ENSURE_INIT();
   if (check_conv_dims("ng_conv2d_wgrad", N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW)) return 1;
 #ifndef NG_EMU
-  if (want_tensor_core(flags, 2.0 * N * K * C * R * S * (double)OH * OW)) {
-    const int tok = prof_begin(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
+  const double wflops = 2.0 * N * K * C * R * S * (double)OH * OW;
+  const int engine = conv_engine(flags, wflops, C, K, R * S, stride);
+  if (engine) {
+    const int tok = prof_begin(NG_PROF_CONV_WGRAD, wflops,
                                4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
-    const int rc = umma::conv_wgrad_tf32(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R,
-                                         S, stride, pad_t, pad_l, OH, OW, (flags & NG_F_TF32) ? 0 : 1,
-                                         (flags & NG_F_X_NHWC) ? 1 : 0, (flags & NG_F_DY_NHWC) ? 1 : 0);
+    const int rc = engine == 2
+        ? umma::conv_wgrad_f16(dptr<float>(dw), dptr<const void>(dy), dptr<const void>(x), N, C, H, W, K, R, S, stride,
+                               pad_t, pad_l, OH, OW, (flags & NG_F_X_NHWC) ? 1 : 0, (flags & NG_F_DY_NHWC) ? 1 : 0)
+        : umma::conv_wgrad_tf32(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R,
+                                S, stride, pad_t, pad_l, OH, OW, (flags & NG_F_TF32) ? 0 : 1,
+                                (flags & NG_F_X_NHWC) ? 1 : 0, (flags & NG_F_DY_NHWC) ? 1 : 0);
     prof_end(tok);
     if (rc >= 0) return rc;
   }
@@ -1267,7 +1296,7 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
              "ng_gemm: dimension too large");
   if (M == 0 || N == 0) return 0;
 #ifndef NG_EMU
-  if (batch == 1 && K > 0 && want_tensor_core(flags, 2.0 * (double)M * N * K)) {
+  if (batch == 1 && K > 0 && conv_engine(flags & ~NG_F_F16X3, 2.0 * (double)M * N * K, 0, 0, 0, 1) == 1) {
     const int tok = prof_begin(NG_PROF_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N));
     const int rc = umma::gemm_tf32(dptr<float>(c), dptr<const float>(a), dptr<const float>(b),
                                    bias ? dptr<const float>(bias) : nullptr, M, N, K, trans_a, trans_b,

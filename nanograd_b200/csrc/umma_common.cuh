@@ -331,9 +331,19 @@ int conv_dgrad_tf32(float* dx, const float* dy, const float* w, int N, int C, in
 int conv_wgrad_tf32(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int x3, int x_is_nhwc, int dy_is_nhwc);
 int to_nhwc(float* out, const float* in, int N, int C, int HW, int round);
-// FP16x3 mode: stage as the (hi, lo) FP16 NHWC pair with a power-of-two scale (umma_conv.cu); `staged`
-// holds N*C*HW*4 + 64 bytes; sums (optional) receives the per-channel sums of `in`.
+// sums[c] = sum_n partial[n][c] in a fixed order (second pass of the staging kernels' channel sums)
+int channel_partial_sum(float* sums, const float* partial, int N, int C);
+// FP16x3 (FP32-accurate) engine, umma_conv_f16.cu: operands staged once per tensor as scaled (hi, lo) FP16
+// pairs, channels-last; `staged` holds N*C*HW*4 + 64 bytes; sums (optional) receives the per-channel sums of
+// `in`.  *_is_staged: that argument already is the to_nhwc_f16 copy.  Same return convention as above.
+bool f16x3_supported(int C, int K, int RS);
 int to_nhwc_f16(void* staged, const float* in, float* sums, int N, int C, int HW);
+int conv_fprop_f16(float* y, const void* x, const float* w, const float* bias, int N, int C, int H, int W, int K, int R,
+                   int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x_is_staged);
+int conv_dgrad_f16(float* dx, const void* dy, const float* w, int N, int C, int H, int W, int K, int R, int S,
+                   int stride, int pad_t, int pad_l, int OH, int OW, int dy_is_staged);
+int conv_wgrad_f16(float* dw, const void* dy, const void* x, int N, int C, int H, int W, int K, int R, int S,
+                   int stride, int pad_t, int pad_l, int OH, int OW, int x_is_staged, int dy_is_staged);
 // to_nhwc plus sums[c] = sum over (n, p) of in[n][c][p] (the bias gradient when `in` is dy)
 int to_nhwc_sum(float* out, const float* in, float* sums, int N, int C, int HW, int round);
 // C[M,N] = op(A) @ op(B) (+ bias[N]) (ReLU), row-major FP32 (umma_gemm.cu)

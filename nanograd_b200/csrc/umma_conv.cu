@@ -23,7 +23,6 @@
 #include "umma_common.cuh"
 
 #ifndef NG_EMU
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
@@ -168,6 +167,12 @@ __global__ void __launch_bounds__(1024) channel_partial_sum_kernel(float* __rest
   }
 }
 
+int channel_partial_sum(float* sums, const float* partial, int N, int C) {
+  NG_LAUNCH(channel_partial_sum_kernel, (int)ceil_div(C, 32), 1024, 0, sums, partial, N, C);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
 int to_nhwc_sum(float* out, const float* in, float* sums, int N, int C, int HW, int round) {
   float* partial = nullptr;
   if (pool_alloc((void**)&partial, (uint64_t)N * C * sizeof(float))) return 1;
@@ -184,170 +189,6 @@ int to_nhwc(float* out, const float* in, int N, int C, int HW, int round) {
   dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N);
   NG_LAUNCH(nchw_to_nhwc_kernel, grid, 256, 0, out, in, C, HW, round);
   NG_CHECK_LAUNCH();
-  return 0;
-}
-
-// ================================================================== FP16x3 (FP32-accurate) operands
-// v * 2^k = hi + lo with hi, lo in FP16 (11 + 11 significant bits; the dropped remainder is < 2^-22 |v|),
-// and  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  on kind::f16 MMAs at twice the TF32 rate: the same
-// error-compensated scheme as 3xTF32 at half the tensor-pipe time.  FP16 has a 5-bit exponent, so each
-// tensor is scaled by a power of two that puts its largest magnitude in [2^14, 2^15) (exact, undone in the
-// epilogue): an element 2^-18 of the maximum still has a normal lo part, and anything smaller is below
-// the 1e-4 * max|.| parity bar by orders of magnitude.  The split is done ONCE per tensor by the staging
-// pass that the tensor-core path needs anyway (NCHW -> NHWC), not per tile inside the MMA kernel.
-// Staged buffer layout: [hi plane][lo plane] of N*HW*C halves each (= the bytes of the FP32 tensor),
-// then 64 bytes of metadata: float inv_scale, uint absmax bits.
-__global__ void __launch_bounds__(256) absmax_kernel(unsigned int* __restrict__ out_bits, const float* __restrict__ in,
-                                                     long long n) {
-  float m = 0.f;
-  const long long n4 = n >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(in)[i];
-    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-  }
-  if (blockIdx.x == 0)
-    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(in[i]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __shared__ float red[8];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-    if (m > 0.f && m < 3.0e38f) atomicMax(out_bits, __float_as_uint(m));   // positive floats order like their bits
-  }
-}
-
-// scale = 2^(15 - e) with max = f * 2^e, f in [0.5, 1)
-__device__ __forceinline__ float f16_scale(unsigned int max_bits) {
-  const float mx = __uint_as_float(max_bits);
-  if (!(mx > 0.f)) return 1.f;
-  int e;
-  frexpf(mx, &e);
-  return ldexpf(1.f, 15 - e);
-}
-__device__ __forceinline__ void f16_split(float v, float scale, __half& hi, __half& lo) {
-  const float sv = v * scale;
-  hi = __float2half_rn(sv);
-  lo = __float2half_rn(sv - __half2float(hi));
-}
-
-// out_hi/out_lo[n][p][c] = split(in[n][c][p]); optionally partial[n][c] = sum_p in[n][c][p] (bias gradient)
-template <bool SUM>
-__global__ void __launch_bounds__(256) nchw_to_nhwc_f16_kernel(__half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                                               const float* __restrict__ in, float* __restrict__ partial,
-                                                               int C, int HW, const unsigned int* __restrict__ max_bits,
-                                                               float* __restrict__ inv_scale_out) {
-  __shared__ float tile[32][33];
-  const float scale = f16_scale(*max_bits);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  if (SUM) {
-    // grid = (C/32, N): the block walks every pixel tile of one (image, 32-channel group)
-    const int c0 = blockIdx.x * 32;
-    const long long img = (long long)blockIdx.y * C * HW;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int p0 = 0; p0 < HW; p0 += 32) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + 8 * i, p = p0 + tx;
-        const float v = (c < C && p < HW) ? in[img + (long long)c * HW + p] : 0.f;
-        tile[ty + 8 * i][tx] = v;
-        acc[i] += v;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int p = p0 + ty + 8 * i, c = c0 + tx;
-        if (p < HW && c < C) {
-          __half h, l;
-          f16_split(tile[tx][ty + 8 * i], scale, h, l);
-          out_hi[img + (long long)p * C + c] = h;
-          out_lo[img + (long long)p * C + c] = l;
-        }
-      }
-      __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float v = acc[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      const int c = c0 + ty + 8 * i;
-      if (tx == 0 && c < C) partial[(long long)blockIdx.y * C + c] = v;
-    }
-  } else {
-    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const long long img = (long long)blockIdx.z * C * HW;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = c0 + ty + 8 * i, p = p0 + tx;
-      tile[ty + 8 * i][tx] = (c < C && p < HW) ? in[img + (long long)c * HW + p] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = p0 + ty + 8 * i, c = c0 + tx;
-      if (p < HW && c < C) {
-        __half h, l;
-        f16_split(tile[tx][ty + 8 * i], scale, h, l);
-        out_hi[img + (long long)p * C + c] = h;
-        out_lo[img + (long long)p * C + c] = l;
-      }
-    }
-  }
-}
-
-// dst_hi/lo[(rs*J + j)*KC + kc] = split(w[j*sj + kc*sc + rs])
-__global__ void __launch_bounds__(256) filter_relayout_f16_kernel(__half* __restrict__ dst_hi, __half* __restrict__ dst_lo,
-                                                                  const float* __restrict__ w, int J, int KC, int RS,
-                                                                  long long sj, long long sc,
-                                                                  const unsigned int* __restrict__ max_bits,
-                                                                  float* __restrict__ inv_scale_out) {
-  const float scale = f16_scale(*max_bits);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
-  const long long n = (long long)J * KC * RS;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int kc = (int)(e % KC);
-    const long long t = e / KC;
-    const int j = (int)(t % J);
-    const int rs = (int)(t / J);
-    __half h, l;
-    f16_split(w[(long long)j * sj + (long long)kc * sc + rs], scale, h, l);
-    dst_hi[e] = h;
-    dst_lo[e] = l;
-  }
-}
-
-// Stage an NCHW FP32 tensor as the FP16 (hi, lo) NHWC pair.  `staged` must hold N*C*HW*4 + 64 bytes.
-int to_nhwc_f16(void* staged, const float* in, float* sums, int N, int C, int HW) {
-  const long long n = (long long)N * C * HW;
-  __half* hi = reinterpret_cast<__half*>(staged);
-  __half* lo = hi + n;
-  float* meta = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(staged) + n * 4);
-  unsigned int* bits = reinterpret_cast<unsigned int*>(meta + 1);
-  if (cudaMemsetAsync(bits, 0, 4, g_stream) != cudaSuccess) return set_error("cudaMemsetAsync failed");
-  const int sms = g_sm_count > 0 ? g_sm_count : 148;
-  long long g = ceil_div(n, 256 * 16);
-  if (g > sms * 8) g = sms * 8;
-  if (g < 1) g = 1;
-  NG_LAUNCH(absmax_kernel, (int)g, 256, 0, bits, in, n);
-  NG_CHECK_LAUNCH();
-  if (sums) {
-    float* partial = nullptr;
-    if (pool_alloc((void**)&partial, (uint64_t)N * C * sizeof(float))) return 1;
-    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)N);
-    NG_LAUNCH((nchw_to_nhwc_f16_kernel<true>), grid, 256, 0, hi, lo, in, partial, C, HW, (const unsigned int*)bits, meta);
-    NG_CHECK_LAUNCH();
-    NG_LAUNCH(channel_partial_sum_kernel, (int)ceil_div(C, 32), 1024, 0, sums, (const float*)partial, N, C);
-    NG_CHECK_LAUNCH();
-    pool_free(partial);
-  } else {
-    dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N);
-    NG_LAUNCH((nchw_to_nhwc_f16_kernel<false>), grid, 256, 0, hi, lo, in, (float*)nullptr, C, HW,
-              (const unsigned int*)bits, meta);
-    NG_CHECK_LAUNCH();
-  }
   return 0;
 }
 

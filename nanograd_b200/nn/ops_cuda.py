@@ -577,25 +577,27 @@ def _tc_plan(geom, stride):
     if plan is None:
         import ctypes
         n, c, h, wd, k, r, s, oh, ow, pt, pl = geom
-        out = (ctypes.c_int * 3)()
+        out = (ctypes.c_int * 4)()
         _lib().ng_conv2d_tc_plan(n, c, h, wd, k, r, s, stride, oh, ow, B.math_flags(), out)
-        plan = _PLAN_CACHE[key] = (bool(out[0]), bool(out[1]), bool(out[2]))
+        plan = _PLAN_CACHE[key] = (bool(out[0]), bool(out[1]), bool(out[2]), int(out[3]))
     return plan
 
 
-def _stage_nhwc(buf, channel_sums=False, sums_out=None):
+def _stage_nhwc(buf, engine, channel_sums=False, sums_out=None):
     """Channels-last staging copy of an NCHW buffer for the tensor-core kernels (made once, shared
-    by the passes of one layer that read the same tensor).  channel_sums=True also returns the
+    by the passes of one layer that read the same tensor).  engine 1: FP32 NHWC; engine 2 (FP16x3):
+    scaled (hi, lo) FP16 pairs plus 64 bytes of metadata.  channel_sums=True also returns the
     per-channel sums of `buf` from the same read (the bias gradient when `buf` is dy)."""
     n, c = buf.shape[0], buf.shape[1]
     hw = _numel(buf.shape[2:])
-    out = DeviceBuffer(buf.shape)
-    out.staged_flags = B.math_flags()
+    flags = B.math_flags() | (B.F_STAGE_F16 if engine == 2 else 0)
+    out = DeviceBuffer((n * c * hw + 16,)) if engine == 2 else DeviceBuffer(buf.shape)
+    out.staged_flags = (B.math_flags(), engine)
     if channel_sums and n <= 65535:
         sums = sums_out if sums_out is not None else DeviceBuffer((c,))
-        _lib().ng_conv2d_stage_nhwc_sum(out.ptr, buf.ptr, sums.ptr, n, c, hw, B.math_flags())
+        _lib().ng_conv2d_stage_nhwc_sum(out.ptr, buf.ptr, sums.ptr, n, c, hw, flags)
         return out, sums
-    _lib().ng_conv2d_stage_nhwc(out.ptr, buf.ptr, n, c, hw, B.math_flags())
+    _lib().ng_conv2d_stage_nhwc(out.ptr, buf.ptr, n, c, hw, flags)
     return (out, None) if channel_sums else out
 
 
@@ -631,27 +633,27 @@ def _conv_forward_shared(ctx, input, weight, bias, stride, padding):
     """Forward of Conv2d / Conv2dBias.  When both fprop and wgrad will run on tensor cores the NHWC
     staging copy of the input is made once here and kept for the backward."""
     geom = _conv_geometry(input.shape, weight.shape, stride, padding)
-    f_tc, d_tc, w_tc = _tc_plan(geom, stride)
+    f_tc, d_tc, w_tc, engine = _tc_plan(geom, stride)
     x_nhwc = None
     if f_tc and w_tc and _needs(ctx, 1):
-        x_nhwc = _stage_nhwc(input)
+        x_nhwc = _stage_nhwc(input, engine)
     ctx.conv_nhwc = x_nhwc
     return _conv2d_forward(input, weight, bias, stride, padding, x_nhwc=x_nhwc)
 
 
 def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding, want_db=False):
     geom = _conv_geometry(input.shape, weight.shape, stride, padding)
-    f_tc, d_tc, w_tc = _tc_plan(geom, stride)
+    f_tc, d_tc, w_tc, engine = _tc_plan(geom, stride)
     need_dx, need_dw = _needs(ctx, 0), _needs(ctx, 1)
     x_nhwc = getattr(ctx, "conv_nhwc", None)
-    if x_nhwc is not None and (not w_tc or getattr(x_nhwc, "staged_flags", None) != B.math_flags()):
+    if x_nhwc is not None and (not w_tc or getattr(x_nhwc, "staged_flags", None) != (B.math_flags(), engine)):
         x_nhwc = None  # math mode changed between forward and backward: restage inside the call
     dy_nhwc = db = None
     db_out, db_tok = _param_out(ctx, 2, (weight.shape[0],)) if want_db else (None, None)
     if need_dx and need_dw and d_tc and w_tc:
         # one staging pass of dy serves dgrad and wgrad, and the bias gradient rides on its read
-        dy_nhwc, db = _stage_nhwc(grad_output, channel_sums=True, sums_out=db_out) if want_db \
-            else (_stage_nhwc(grad_output), None)
+        dy_nhwc, db = _stage_nhwc(grad_output, engine, channel_sums=True, sums_out=db_out) if want_db \
+            else (_stage_nhwc(grad_output, engine), None)
     # wgrad first: it is what the data-parallel gradient arena is waiting for (dgrad only feeds this rank)
     dw = None
     if need_dw:

@@ -112,7 +112,7 @@ def test_conv_engines_elementwise_and_against_float64_at_full_size(shape):
     w = (rng.standard_normal((k, c, 3, 3), dtype=np.float32) / np.float32(np.sqrt(9 * c)))
     dy = rng.standard_normal((n, k, oh, oh), dtype=np.float32)
     xd, wd, dyd = DeviceBuffer(x.shape, hostbuf=x), DeviceBuffer(w.shape, hostbuf=w), DeviceBuffer(dy.shape, hostbuf=dy)
-    plan = (ctypes.c_int * 3)()
+    plan = (ctypes.c_int * 4)()
     lib.ng_conv2d_tc_plan(n, c, hw, hw, k, 3, 3, 1, oh, oh, B.F_TF32X3 | B.F_TC_FORCE, plan)
     plan = dict(zip(("fprop", "dgrad", "wgrad"), map(bool, plan)))
 

@@ -74,10 +74,13 @@ def main():
     ap.add_argument("--passes", default="fprop,dgrad,wgrad")
     ap.add_argument("--set", default="small")
     ap.add_argument("--x3", action="store_true", help="check the FP32-accurate 3xTF32 mode instead of TF32")
+    ap.add_argument("--f16", action="store_true", help="check the FP32-accurate FP16x3 mode (channels % 64 == 0)")
     args = ap.parse_args()
     global TF32
     if args.x3:
         TF32 = B.F_TF32X3 | B.F_TC_FORCE
+    if args.f16:
+        TF32 = B.F_F16X3 | B.F_TC_FORCE
     B.init()
     passes = args.passes.split(",")
     small = [(2, 32, 32, 32, 32, 3, 3, 1), (2, 64, 32, 32, 64, 3, 3, 1), (4, 64, 16, 16, 128, 3, 3, 1),
@@ -88,7 +91,11 @@ def main():
     vgg = [(512, 64, 32, 32, 64, 3, 3, 1), (512, 64, 16, 16, 128, 3, 3, 1), (512, 128, 16, 16, 128, 3, 3, 1),
            (512, 128, 8, 8, 256, 3, 3, 1), (512, 256, 8, 8, 256, 3, 3, 1)]
     sweep = [(256, c, 32, 32, c, 3, 3, 0) for c in (16, 32, 64, 128, 256)]
-    for shp in {"small": small, "vgg": vgg, "sweep": sweep, "odd": odd}[args.set]:
+    f16 = [(2, 64, 32, 32, 64, 3, 3, 1), (4, 64, 16, 16, 128, 3, 3, 1), (4, 128, 8, 8, 256, 3, 3, 1),
+           (2, 64, 64, 64, 64, 3, 3, 1), (3, 64, 9, 13, 320, 3, 3, 1), (2, 256, 20, 36, 64, 3, 3, 0),
+           (130, 64, 2, 2, 64, 1, 1, 0), (1, 64, 33, 65, 192, 3, 3, 2), (5, 128, 12, 12, 64, 5, 5, 2),
+           (2, 192, 7, 7, 128, 3, 3, 1), (9, 64, 1, 37, 64, 1, 5, 2)]
+    for shp in {"small": small, "vgg": vgg, "sweep": sweep, "odd": odd, "f16": f16}[args.set]:
         run(*shp, perf=args.perf, passes=passes)
     if args.set == "odd":   # conv1d-shaped problems (H = R = 1), as Conv1d issues them
         run(5, 32, 1, 100, 48, 1, 3, 0, perf=args.perf, passes=passes, pad_h=0)
