@@ -250,8 +250,12 @@ def workload_config(world, n_params=2198602, math_mode="fp32", batch=None, args=
             "math": MATH_TEXT[math_mode]}
 
 
-MATH_TEXT = {"fp32": "FP32-accurate: tcgen05 tensor-core conv with 3xTF32 error compensation where the shape is "
-                     "supported, FP32 SIMT (FFMA) elsewhere (first conv layer, GEMMs)",
+MATH_TEXT = {"fp32": "FP32-accurate: tcgen05 tensor-core conv with error-compensated FP16x3 operand pairs (channel "
+                     "counts multiples of 64) or the 3xTF32 split (other supported shapes), FP32 SIMT (FFMA) "
+                     "elsewhere (first conv layer, small GEMMs)",
+             "fp32_tf32x3": "FP32-accurate: tcgen05 tensor-core conv with 3xTF32 error compensation where the shape is "
+                            "supported, FP32 SIMT (FFMA) elsewhere",
+             "f16x3": "FP32-accurate FP16x3 / 3xTF32 tcgen05 conv forced for every supported shape",
              "tf32x3": "FP32-accurate 3xTF32 tcgen05 conv forced for every supported shape",
              "simt": "FP32 SIMT (FFMA) implicit-GEMM conv / GEMM only",
              "tf32": "TF32 tcgen05 tensor-core conv (FP32 accumulate), FP32 SIMT elsewhere"}
@@ -329,7 +333,10 @@ def conv2d_sweep(B, lib, ffma_peak):
         flops = 2.0 * N * K * C * R * S * OH * OW
         row = {"C=K": ch}
         iters = 20 if ch <= 64 else 5
-        for mode, flag in (("", 0), ("tf32x3_", B.F_TF32X3 | B.F_TC_FORCE), ("tf32_", B.F_TF32)):
+        modes = [("", 0), ("tf32x3_", B.F_TF32X3 | B.F_TC_FORCE), ("tf32_", B.F_TF32)]
+        if ch % 64 == 0:
+            modes.insert(2, ("f16x3_", B.F_F16X3 | B.F_TC_FORCE))
+        for mode, flag in modes:
             total = 0.0
             for name, fn in calls.items():
                 for _ in range(3):
@@ -543,12 +550,17 @@ KERNEL_NAMES = {
              "conv_dgrad": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05, dgrad)",
              "conv_wgrad": "2x nchw_to_nhwc + umma_conv_wgrad_kernel<false> (tcgen05) + wgrad_reduce_kernel",
              "gemm": "gemm_kernel (FP32 SIMT)"},
-    "fp32": {"conv_fprop": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05 3xTF32, fprop)",
-             "conv_dgrad": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05 3xTF32, dgrad)",
-             "conv_wgrad": "2x nchw_to_nhwc + umma_conv_wgrad_kernel<true> (tcgen05 3xTF32) + wgrad_reduce_kernel",
-             "gemm": "gemm_kernel (FP32 SIMT)"},
+    "tf32x3": {"conv_fprop": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05 3xTF32, fprop)",
+               "conv_dgrad": "nchw_to_nhwc + filter_relayout + umma_conv_gather_kernel (tcgen05 3xTF32, dgrad)",
+               "conv_wgrad": "2x nchw_to_nhwc + umma_conv_wgrad_kernel<true> (tcgen05 3xTF32) + wgrad_reduce_kernel",
+               "gemm": "gemm_kernel (FP32 SIMT)"},
+    "fp32": {"conv_fprop": "filter_relayout_f16 + umma_conv_gather_f16_kernel (tcgen05 FP16x3, fprop; x staged once per layer)",
+             "conv_dgrad": "filter_relayout_f16 + umma_conv_gather_f16_kernel (tcgen05 FP16x3, dgrad; dy staged once per layer)",
+             "conv_wgrad": "umma_conv_wgrad_f16_kernel (tcgen05 FP16x3) + wgrad_reduce_scaled_kernel",
+             "gemm": "umma_gemm_kernel (3xTF32) / gemm_kernel (FP32 SIMT)"},
 }
-KERNEL_NAMES["tf32x3"] = KERNEL_NAMES["fp32"]
+KERNEL_NAMES["fp32_tf32x3"] = KERNEL_NAMES["tf32x3"]
+KERNEL_NAMES["f16x3"] = KERNEL_NAMES["fp32"]
 
 
 def pick_peak(peaks, clocks):
@@ -587,16 +599,22 @@ def roofline_object(m, math_mode, peaks, peak_src, clocks=None):
                "no FP32 tensor-core MMA exists, so the tensor peak of %s does not bound this mode" % peak_src)
     else:
         mma_per_mac = 1.0 if math_mode == "tf32" else 3.0
-        bound, peak = "tensor", 0.5 * bf16 / mma_per_mac
-        src = ("%s = dense TF32 (1/2 of the measured %s dense bf16 GEMM rate in %s, %.1f TFLOP/s: the SM clock held "
+        # dense rate of the MMA kind the mode issues: kind::f16 (the measured bf16 GEMM rate) for FP16x3,
+        # kind::tf32 (half of it) for TF32 / 3xTF32
+        f16 = math_mode in ("fp32", "f16x3")
+        dense_frac = 1.0 if f16 else 0.5
+        bound, peak = "tensor", dense_frac * bf16 / mma_per_mac
+        src = ("%s = dense %s (%sthe measured %s dense bf16 GEMM rate in %s, %.1f TFLOP/s: the SM clock held "
                "%s of %s MHz over the timed region)%s" % (
-                   "dense TF32 peak" if mma_per_mac == 1 else "useful-FLOP peak of the FP32-accurate 3xTF32 scheme",
+                   "dense TF32 peak" if mma_per_mac == 1 else
+                   "useful-FLOP peak of the FP32-accurate %s scheme" % ("FP16x3" if f16 else "3xTF32"),
+                   "FP16" if f16 else "TF32", "" if f16 else "1/2 of ",
                    which, peak_src, bf16, (clocks or {}).get("sm_mhz"), (clocks or {}).get("sm_max_mhz"),
                    "" if mma_per_mac == 1 else " / 3 MMAs per FP32 MAC; for scale, the measured FFMA peak of the SIMT "
                    "alternative is %.1f TFLOP/s" % m["ffma_peak"]))
-        extra = {"frac_vs_burst_peak": round(achieved / (0.5 * burst / mma_per_mac), 4) if burst else None,
-                 "frac_vs_sustained_peak": round(achieved / (0.5 * sustained / mma_per_mac), 4) if sustained else None,
-                 "tensor_pipe_frac_of_dense_tf32": round(achieved * mma_per_mac / (0.5 * bf16), 4) if bf16 else None,
+        extra = {"frac_vs_burst_peak": round(achieved / (dense_frac * burst / mma_per_mac), 4) if burst else None,
+                 "frac_vs_sustained_peak": round(achieved / (dense_frac * sustained / mma_per_mac), 4) if sustained else None,
+                 "tensor_pipe_frac_of_dense": round(achieved * mma_per_mac / (dense_frac * bf16), 4) if bf16 else None,
                  "useful_frac_of_dense_tf32": round(achieved / (0.5 * bf16), 4) if bf16 else None,
                  "peak_kind": which}
     out = {
@@ -688,7 +706,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="device", choices=["device", "reference"])
-    ap.add_argument("--math", default="fp32", choices=["fp32", "simt", "tf32x3", "tf32"],
+    ap.add_argument("--math", default="fp32", choices=["fp32", "simt", "tf32x3", "tf32", "fp32_tf32x3", "f16x3"],
                     help="math mode of the headline measurement (default fp32: FP32-accurate, engine picked per call)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 512 images per GPU; strong: global batch 4096 split over the GPUs (SURVEY 8-d cfg4)")

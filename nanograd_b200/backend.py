@@ -122,18 +122,21 @@ R_SUM, R_MAX, R_MIN = range(3)
 F_RELU, F_TF32, F_TF32X3 = 1, 2, 4
 
 # Math mode of the convolution kernels (fprop, dgrad, wgrad):
-#   "fp32" (default)  FP32-accurate results (parity bar rtol 1e-4).  Per call the library picks the
-#                     faster FP32-accurate engine: the tcgen05 tensor-core kernel with the
-#                     error-compensated 3xTF32 operand split (measured 2e-6 .. 1.4e-5 from a float64
-#                     reference) when the shape is supported and the problem is large enough to pay
-#                     for staging, else the FP32 SIMT (FFMA) kernel.
+#   "fp32" (default)  FP32-accurate results (parity bar rtol 1e-4).  Per layer the library picks the
+#                     fastest FP32-accurate engine: for problems large enough to pay for staging, the
+#                     tcgen05 tensor-core kernels — error-compensated FP16x3 operand pairs (channel counts
+#                     multiples of 64; measured 1e-6 .. 8e-6 from the SIMT kernels) or the 3xTF32 operand
+#                     split (other supported shapes; 2e-6 .. 1.4e-5 from a float64 reference) — else the
+#                     FP32 SIMT (FFMA) kernel.
 #   "simt"            FP32 SIMT kernels only.
-#   "tf32x3"          like "fp32" but tensor cores for every supported shape, whatever its size.
+#   "tf32x3"          3xTF32 tensor-core kernels for every supported shape, whatever its size.
+#   "f16x3"           FP16x3 tensor-core kernels for every supported shape, 3xTF32 for the others.
+#   "fp32_tf32x3"     the default selection without the FP16x3 engine (round-1 behaviour).
 #   "tf32"  (opt-in)  tensor cores with plain TF32 inputs / FP32 accumulation (parity bar rtol 1e-2).
 # Selected with NANOGRAD_B200_MATH (or the reference-survey spelling NANOGRAD_TF32=1) or set_math_mode().
 F_TC_FORCE, F_X_NHWC, F_DY_NHWC, F_F16X3, F_STAGE_F16 = 8, 16, 32, 64, 128
-_MATH_MODES = {"fp32": F_TF32X3, "simt": 0, "tf32x3": F_TF32X3 | F_TC_FORCE, "tf32": F_TF32,
-               "fp32_f16": F_F16X3 | F_TF32X3, "f16x3": F_F16X3 | F_TF32X3 | F_TC_FORCE}
+_MATH_MODES = {"fp32": F_F16X3 | F_TF32X3, "simt": 0, "tf32x3": F_TF32X3 | F_TC_FORCE, "tf32": F_TF32,
+               "fp32_tf32x3": F_TF32X3, "f16x3": F_F16X3 | F_TF32X3 | F_TC_FORCE}
 _math_flags = _MATH_MODES["tf32" if os.environ.get("NANOGRAD_TF32", "0") == "1"
                           else os.environ.get("NANOGRAD_B200_MATH", "fp32").lower()]
 

@@ -405,6 +405,18 @@ def all_cases():
     cases["conv2d_wide_c32_k64"] = (case_conv2d_wide, dict(c=32, k=64, hw=16, n=4, pad=0))
     cases["conv2d_wide_c64_k32_p1"] = (case_conv2d_wide, dict(c=64, k=32, hw=8, n=3, pad=1))
     cases["conv2d_wide_c128_k128_p1"] = (case_conv2d_wide, dict(c=128, k=128, hw=12, n=2, pad=1))
+    # channel counts that are multiples of 64: the layers the FP16x3 tensor-core engine takes (the first conv,
+    # 3 -> 64, stays on the direct / SIMT kernels).  With 130-260 k BatchNorm outputs per layer some land within
+    # 1e-6 of the ReLU kink or of another element of their max-pool window, where a rounding difference flips
+    # relu'(z) / the window's argmax and moves whole gradient entries by 1e-3 on ANY float32 implementation
+    # (measured: seed 0 at a ReLU kink with the 3xTF32 engine, seed 6 at a 9e-7 pool near-tie with both
+    # tensor-core engines, while the kernels replayed on the recorded operands are within 4e-6 of float64:
+    # tools/conv_replay.py).  Seed 23 is the seed in 0..23 that keeps the tensor-core-fed BatchNorm outputs
+    # furthest from both discontinuities (>= 7.5e-6, CPU oracle).
+    cases["vgg_w64_sgd"] = (case_vgg_bn, dict(opt_name="sgd", widths=(64, 128), hw=16, batch=16, seed=23))
+    cases["vgg_w64_adam_8steps"] = (case_vgg_bn, dict(opt_name="adam", widths=(64, 128), hw=16, batch=16, steps=8, seed=23))
+    cases["conv2d_wide_c64_k128_p1"] = (case_conv2d_wide, dict(c=64, k=128, hw=12, n=3, pad=1))
+    cases["conv2d_wide_c192_k64"] = (case_conv2d_wide, dict(c=192, k=64, hw=9, n=2, pad=0))
     cases["attention_adamw"] = (case_attention, {})
     for o in ("sgd", "sgdm", "adam", "adamw1", "adamw2", "adamw3"):
         cases[f"tinynet_{o}"] = (case_tinynet_step, dict(opt_name=o))
@@ -432,4 +444,5 @@ for _p in range(1, 4):
 # implementation — the float64-drifting oracle included — amplifies 1e-7 rounding differences
 # through 8-10 optimizer steps (Adam divides by sqrt(v) ~ |g|).
 # Measured on the FP32 SIMT kernels: 7e-6 / 4e-7 / 1.0e-4 (profiles/README.md keeps the GPU numbers).
-TRAJECTORY_RTOL = {"mnist_cnn_adam_10steps": 2e-4, "mnist_cnn_sgdm_10steps": 1e-4, "vgg_wide_adam_8steps": 1e-3}
+TRAJECTORY_RTOL = {"mnist_cnn_adam_10steps": 2e-4, "mnist_cnn_sgdm_10steps": 1e-4, "vgg_wide_adam_8steps": 1e-3,
+                   "vgg_w64_adam_8steps": 1e-3}

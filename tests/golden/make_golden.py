@@ -4,6 +4,7 @@ Run in the build container (the reference lives read-only at /root/reference; it
 to the GPU box, the vectors can):
 
     python tests/golden/make_golden.py            # writes one .npz per case + MANIFEST.json
+    python tests/golden/make_golden.py NAME ...   # only these cases (the manifest keeps the others)
 
 The reference is imported unmodified through tests/helpers.load_reference() (a stub graphviz
 module is the only shim; pyopencl's absence just leaves its GPU namespace empty).
@@ -35,8 +36,14 @@ def reference_framework():
 def main():
     fw = reference_framework()
     manifest = {}
+    only = set(sys.argv[1:])
+    if only and os.path.exists(os.path.join(HERE, "MANIFEST.json")):
+        with open(os.path.join(HERE, "MANIFEST.json")) as f:
+            manifest = json.load(f)["cases"]
     warnings.simplefilter("ignore")
     for name, (fn, kwargs) in cases.all_cases().items():
+        if only and name not in only:
+            continue
         with np.errstate(all="ignore"):
             out = fn(fw, **kwargs)
         path = os.path.join(HERE, name + ".npz")

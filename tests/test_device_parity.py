@@ -26,9 +26,10 @@ EMU_SUBSET = (
 
 # cases whose convolutions the tensor-core path accepts; run in TF32 mode at the north-star's TF32 bar
 TF32_CASES = ["conv2d_wide_c32_k64", "conv2d_wide_c64_k32_p1", "conv2d_wide_c128_k128_p1", "mnist_cnn_sgd",
-              "mnist_cnn_sgdm", "vgg_wide_sgd", "vgg_wide_adam"]
+              "mnist_cnn_sgdm", "vgg_wide_sgd", "vgg_wide_adam", "vgg_w64_sgd", "conv2d_wide_c64_k128_p1",
+              "conv2d_wide_c192_k64"]
 # multi-step trajectories in both FP32-accurate engines (bar: cases.TRAJECTORY_RTOL)
-TRAJECTORY_CASES = ["mnist_cnn_adam_10steps", "mnist_cnn_sgdm_10steps", "vgg_wide_adam_8steps"]
+TRAJECTORY_CASES = ["mnist_cnn_adam_10steps", "mnist_cnn_sgdm_10steps", "vgg_wide_adam_8steps", "vgg_w64_adam_8steps"]
 
 
 def _run(name):
@@ -48,11 +49,12 @@ def test_case_matches_reference_golden_on_b200(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["simt", "tf32x3"])
+@pytest.mark.parametrize("mode", ["simt", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("name", TF32_CASES)
 def test_case_matches_reference_golden_on_b200_fp32_engines(name, mode):
-    """Both FP32-accurate engines at the FP32 bar (rtol 1e-4): the SIMT FFMA kernels alone, and the
-    tensor-core 3xTF32 kernels forced on for every shape they accept."""
+    """Every FP32-accurate engine at the FP32 bar (rtol 1e-4): the SIMT FFMA kernels alone, the tensor-core
+    3xTF32 kernels forced on for every shape they accept, and the FP16x3 kernels forced on for the layers whose
+    channel counts are multiples of 64 (3xTF32 for the rest)."""
     from nanograd_b200 import backend
     H.use_cuda_library()
     backend.set_math_mode(mode)
@@ -70,7 +72,7 @@ def test_case_matches_reference_golden_on_b200_fp32_engines(name, mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["simt", "tf32x3"])
+@pytest.mark.parametrize("mode", ["simt", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("name", TRAJECTORY_CASES)
 def test_multi_step_trajectory_matches_reference_on_b200(name, mode):
     """8-10 optimizer steps: step-0 outputs and gradients at rtol 1e-4, the loss history and the final

@@ -122,6 +122,8 @@ def test_conv_engines_elementwise_and_against_float64_at_full_size(shape):
     operands = {"fprop": (xd, wd), "dgrad": (dyd, wd), "wgrad": (dyd, xd)}
     engines = [("simt", 0, H.RTOL_FP32), ("tf32x3", B.F_TF32X3 | B.F_TC_FORCE, H.RTOL_FP32),
                ("tf32", B.F_TF32, H.RTOL_TF32)]
+    if c % 64 == 0 and k % 64 == 0:
+        engines.insert(2, ("f16x3", B.F_F16X3 | B.F_TC_FORCE, H.RTOL_FP32))
     report = []
     for which in ("fprop", "dgrad", "wgrad"):
         idx, ref = samples[which]

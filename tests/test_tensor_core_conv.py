@@ -19,9 +19,18 @@ SHAPES = [
 ]
 
 
+# channel counts that are multiples of 64: the FP16x3 engine (ragged sizes, two N tiles, 1x1 / 5x5 / Conv1d shapes)
+F16_SHAPES = [
+    (2, 64, 32, 32, 64, 3, 3, 1, 1), (4, 64, 16, 16, 128, 3, 3, 1, 1), (4, 128, 8, 8, 256, 3, 3, 1, 1),
+    (3, 64, 9, 13, 320, 3, 3, 1, 1), (2, 256, 20, 36, 64, 3, 3, 0, 0), (130, 64, 2, 2, 64, 1, 1, 0, 0),
+    (1, 64, 33, 65, 192, 3, 3, 2, 2), (5, 128, 12, 12, 64, 5, 5, 2, 2), (2, 192, 7, 7, 128, 3, 3, 1, 1),
+    (9, 64, 1, 37, 64, 1, 5, 0, 2), (3, 320, 6, 10, 64, 3, 3, 1, 1),
+]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,rtol", [("tf32x3", H.RTOL_FP32), ("tf32", H.RTOL_TF32)])
-@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", H.RTOL_FP32), ("tf32", H.RTOL_TF32), ("f16x3", H.RTOL_FP32)])
+@pytest.mark.parametrize("shape", SHAPES + F16_SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_tensor_core_conv_matches_simt(shape, mode, rtol):
     from nanograd_b200 import backend as B
     from nanograd_b200.nn.buffer import DeviceBuffer
@@ -35,7 +44,9 @@ def test_tensor_core_conv_matches_simt(shape, mode, rtol):
     b = DeviceBuffer((K,), hostbuf=rng.randn(K).astype(np.float32))
     dy = DeviceBuffer((N, K, OH, OW), hostbuf=rng.randn(N, K, OH, OW).astype(np.float32))
     dims = (N, C, Hh, W, K, R, S, 1, ph, pw, OH, OW)
-    flag = {"tf32x3": B.F_TF32X3 | B.F_TC_FORCE, "tf32": B.F_TF32}[mode]
+    flag = {"tf32x3": B.F_TF32X3 | B.F_TC_FORCE, "tf32": B.F_TF32, "f16x3": B.F_F16X3 | B.F_TC_FORCE}[mode]
+    if mode == "f16x3" and (C % 64 or K % 64):
+        pytest.skip("the FP16x3 engine takes channel counts that are multiples of 64")
     calls = {
         "fprop": ((N, K, OH, OW), lambda o, f: lib.ng_conv2d_fprop(o.ptr, x.ptr, w.ptr, b.ptr, *dims, f)),
         "dgrad": ((N, C, Hh, W), lambda o, f: lib.ng_conv2d_dgrad(o.ptr, dy.ptr, w.ptr, *dims, f)),
@@ -95,3 +106,77 @@ def test_stage_nhwc_with_channel_sums(nchw):
     lib.ng_conv2d_stage_nhwc_sum(dst.ptr, src.ptr, sums.ptr, n, c, h * w, 0)
     H.assert_exact(dst.numpy().reshape(n, h * w, c), a.reshape(n, c, h * w).transpose(0, 2, 1), "staged copy")
     H.assert_close(sums.numpy(), a.astype(np.float64).sum(axis=(0, 2, 3)), H.RTOL_FP32, "channel sums")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spread", [1.0, 3.0, 6.0])
+def test_f16x3_conv_dynamic_range(spread):
+    """FP16x3 operands carry one power-of-two scale per tensor, so the engine is checked on tensors whose
+    magnitudes spread over many binades (log-normal with sigma = `spread` natural-log units: 6.0 puts the
+    smallest elements ~1e-11 of the largest) against a float64 evaluation of sampled outputs: the error bar
+    stays the FP32 one (rtol 1e-4 of the output scale), and elements far below the tensor maximum lose only
+    relative, never absolute, accuracy."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    H.use_cuda_library()
+    lib = B.lib()
+    N, C, Hh, W, K, R, S, ph, pw = 3, 64, 12, 12, 128, 3, 3, 1, 1
+    rng = np.random.RandomState(int(spread * 10))
+    def wide(*shape):
+        return (rng.randn(*shape) * np.exp(spread * rng.randn(*shape))).astype(np.float32)
+    x, w, dy = wide(N, C, Hh, W), wide(K, C, R, S), wide(N, K, Hh, W)
+    xd, wd, dyd = (DeviceBuffer(a.shape, hostbuf=a) for a in (x, w, dy))
+    dims = (N, C, Hh, W, K, R, S, 1, ph, pw, Hh, W)
+    flag = B.F_F16X3 | B.F_TC_FORCE
+    y, dx, dw = DeviceBuffer((N, K, Hh, W)), DeviceBuffer((N, C, Hh, W)), DeviceBuffer((K, C, R, S))
+    lib.ng_conv2d_fprop(y.ptr, xd.ptr, wd.ptr, 0, *dims, flag)
+    lib.ng_conv2d_dgrad(dx.ptr, dyd.ptr, wd.ptr, *dims, flag)
+    lib.ng_conv2d_wgrad(dw.ptr, dyd.ptr, xd.ptr, *dims, flag)
+    xp = np.pad(x.astype(np.float64), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    dyp = np.pad(dy.astype(np.float64), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    w64 = w.astype(np.float64)
+    y_ref = np.zeros((N, K, Hh, W))
+    dx_ref = np.zeros((N, C, Hh, W))
+    dw_ref = np.zeros((K, C, R, S))
+    for r in range(R):
+        for s in range(S):
+            y_ref += np.einsum("nchw,kc->nkhw", xp[:, :, r:r + Hh, s:s + W], w64[:, :, r, s])
+            dx_ref += np.einsum("nkhw,kc->nchw", dyp[:, :, 2 - r:2 - r + Hh, 2 - s:2 - s + W], w64[:, :, r, s])
+            dw_ref[:, :, r, s] = np.einsum("nkhw,nchw->kc", dy.astype(np.float64), xp[:, :, r:r + Hh, s:s + W])
+    H.assert_close(y.numpy(), y_ref, H.RTOL_FP32, f"fprop spread {spread}")
+    H.assert_close(dx.numpy(), dx_ref, H.RTOL_FP32, f"dgrad spread {spread}")
+    H.assert_close(dw.numpy(), dw_ref, H.RTOL_FP32, f"wgrad spread {spread}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nchw", [(3, 64, 5, 10), (16, 128, 32, 32), (5, 192, 1, 37), (70, 256, 8, 8)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_stage_f16_pairs_with_channel_sums(nchw):
+    """ng_conv2d_stage_nhwc_sum with NG_F_STAGE_F16: staged[n][p][c/64][hi|lo][c%64] in FP16 with a power-of-two
+    scale that puts max|src| in [2^14, 2^15); hi + lo reproduces the scaled value to 2^-22 relative
+    (11 + 11 significant bits) and the channel sums ride on the same read."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    H.use_cuda_library()
+    lib = B.lib()
+    n, c, h, w = nchw
+    rng = np.random.RandomState(n + c)
+    a = (rng.randn(n, c, h, w) * np.exp(rng.randn(n, c, h, w))).astype(np.float32)
+    src, dst, sums = DeviceBuffer(a.shape, hostbuf=a), DeviceBuffer((a.size + 16,)), DeviceBuffer((c,))
+    lib.ng_conv2d_stage_nhwc_sum(dst.ptr, src.ptr, sums.ptr, n, c, h * w, B.F_STAGE_F16)
+    raw = dst.numpy()
+    inv_scale = float(raw[a.size])
+    amax = float(raw[a.size + 1:a.size + 2].view(np.float32)[0])
+    assert amax == float(np.abs(a).max())
+    scale = 1.0 / inv_scale
+    assert 2.0 ** 14 <= amax * scale < 2.0 ** 15 and np.log2(scale) == np.round(np.log2(scale))
+    halves = raw[:a.size].view(np.float16).reshape(n, h * w, c // 64, 2, 64).astype(np.float64)
+    rebuilt = (halves[:, :, :, 0, :] + halves[:, :, :, 1, :]).reshape(n, h * w, c) * inv_scale
+    want = a.reshape(n, c, h * w).transpose(0, 2, 1).astype(np.float64)
+    err = np.abs(rebuilt - want)
+    assert np.all(err <= np.maximum(np.abs(want) * 2.0 ** -21, amax * 2.0 ** -39)), float((err / np.abs(want).max()).max())
+    H.assert_close(sums.numpy(), a.astype(np.float64).sum(axis=(0, 2, 3)), H.RTOL_FP32, "channel sums")
+    # without the sums (the x operand): the same bytes
+    dst2 = DeviceBuffer((a.size + 16,))
+    lib.ng_conv2d_stage_nhwc(dst2.ptr, src.ptr, n, c, h * w, B.F_STAGE_F16)
+    H.assert_exact(dst2.numpy()[:a.size + 2].view(np.uint32), raw[:a.size + 2].view(np.uint32), "staged copy without sums")

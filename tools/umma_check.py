@@ -95,7 +95,9 @@ def main():
            (2, 64, 64, 64, 64, 3, 3, 1), (3, 64, 9, 13, 320, 3, 3, 1), (2, 256, 20, 36, 64, 3, 3, 0),
            (130, 64, 2, 2, 64, 1, 1, 0), (1, 64, 33, 65, 192, 3, 3, 2), (5, 128, 12, 12, 64, 5, 5, 2),
            (2, 192, 7, 7, 128, 3, 3, 1), (9, 64, 1, 37, 64, 1, 5, 2)]
-    for shp in {"small": small, "vgg": vgg, "sweep": sweep, "odd": odd, "f16": f16}[args.set]:
+    w64 = [(16, 64, 16, 16, 64, 3, 3, 1), (16, 64, 8, 8, 128, 3, 3, 1), (16, 128, 8, 8, 128, 3, 3, 1),
+           (16, 32, 16, 16, 32, 3, 3, 1), (16, 32, 8, 8, 64, 3, 3, 1), (16, 64, 8, 8, 64, 3, 3, 1)]
+    for shp in {"small": small, "vgg": vgg, "sweep": sweep, "odd": odd, "f16": f16, "w64": w64}[args.set]:
         run(*shp, perf=args.perf, passes=passes)
     if args.set == "odd":   # conv1d-shaped problems (H = R = 1), as Conv1d issues them
         run(5, 32, 1, 100, 48, 1, 3, 0, perf=args.perf, passes=passes, pad_h=0)
