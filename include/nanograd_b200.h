@@ -201,6 +201,23 @@ int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64
  * (Add.backward's unbroadcast of the conv bias, ops_cpu.py:12-18, module.py:476) from the one read. */
 int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t N, int64_t C, int64_t HW, int flags);
 
+/* FP16x3 staging with what the producer of the tensor already knows (no separate magnitude pass, and for
+ * BatchNorm neighbours no separate normalise pass either):
+ *   ng_conv2d_stage_f16      like NG_F_STAGE_F16 staging; sums (optional) as ng_conv2d_stage_nhwc_sum; absmax_bits
+ *                            (optional) = device word with the bits of max|src| or an upper bound of it.
+ *   ng_conv2d_stage_f16_bn   staged copy of y = act(BatchNorm2d(x)) recomputed from x and the batch statistics
+ *                            (ng_bn2d_act_fwd_stats): y itself is never written.
+ *   ng_conv2d_stage_f16_bnbwd staged copy (and channel sums) of the BatchNorm2d input gradient recomputed from
+ *                            (dy, x) and the backward sums (ng_bn2d_act_bwd_sums): dx itself is never written.
+ * These replace, for the conv -> BatchNorm2d -> ReLU -> conv chains of module.py:356-391 / 476, the second
+ * half of the ~30 primitive ops the reference composes per BatchNorm layer. */
+int ng_conv2d_stage_f16(uint64_t dst, uint64_t src, uint64_t sums, uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW);
+int ng_conv2d_stage_f16_bn(uint64_t dst, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd,
+                           uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW, int act);
+int ng_conv2d_stage_f16_bnbwd(uint64_t dst, uint64_t chan_sums, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta,
+                              uint64_t mean, uint64_t invstd, uint64_t bn_sums, uint64_t bound_bits, int64_t N,
+                              int64_t C, int64_t HW, int act);
+
 /* -------------------------------------------------------------------- pooling ------ */
 /* fused replacements for Tensor._pool2d → Slice, Reshape, Max/Sum(axis=(3,5)), Mul
  * (tensor.py:370-406) and Max.backward's tie-splitting mask (ops_cpu.py:121-127).
@@ -256,6 +273,27 @@ int ng_bn2d_act_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
 int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x,
                     uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd,
                     int64_t N, int64_t C, int64_t HW, int act);
+
+/* The two halves of the fused layer as separate calls, so that the element-wise half can be fused into the
+ * consumer (ng_conv2d_stage_f16_bn / _bnbwd) instead of writing a tensor nobody else reads:
+ *   ng_bn2d_act_fwd_stats  statistics + running-stat update; absmax_bits[0] = bits of max|y| of the output the
+ *                          apply pass WOULD write (the normalised output is monotone in x per channel, so the
+ *                          channel extremes of x, tracked by the statistics pass, give it exactly);
+ *   ng_bn2d_act_apply      the normalise (+ activation) pass alone;
+ *   ng_bn2d_act_bwd_sums   dgamma, dbeta, sums[2C + 1] = per channel {sum dy, sum dy (x - mean)} + the count,
+ *                          bound_bits[0] = bits of an upper bound of max|dx|;
+ *   ng_bn2d_act_bwd_dx     the dx pass alone.
+ * Single process only (synchronised BatchNorm keeps the one-call forms above). */
+int ng_bn2d_act_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean, uint64_t running_var,
+                          uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits,
+                          int64_t N, int64_t C, int64_t HW, float eps, float momentum, int act);
+int ng_bn2d_act_apply(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd,
+                      int64_t N, int64_t C, int64_t HW, int act);
+int ng_bn2d_act_bwd_sums(uint64_t dgamma, uint64_t dbeta, uint64_t sums, uint64_t bound_bits, uint64_t dy, uint64_t x,
+                         uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd,
+                         int64_t N, int64_t C, int64_t HW, int act);
+int ng_bn2d_act_bwd_dx(uint64_t dx, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean,
+                       uint64_t save_invstd, uint64_t sums, int64_t N, int64_t C, int64_t HW, int act);
 
 /* ------------------------------------------------------------------- optimizers ---- */
 /* one multi-tensor launch per step for the whole parameter list.

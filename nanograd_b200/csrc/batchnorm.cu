@@ -13,15 +13,30 @@
 
 namespace ng {
 
-// z = (x - mean) * (gamma * invstd) + beta, written ONE way so the forward kernel and the backward
-// kernels that recompute z for the fused-ReLU mask produce bit-identical values.
-__device__ __forceinline__ float bn_affine(float x, float mu, float a, float b) { return fmaf(x - mu, a, b); }
+// bn_affine (ng_common.h): z = (x - mean) * (gamma * invstd) + beta, written ONE way so the forward kernel, the
+// backward kernels that recompute z for the fused-ReLU mask and the fused staging kernels of the FP16x3
+// convolution engine (umma_conv_f16.cu) produce bit-identical values.
+
+// Block-wide maximum for blockDim.x a multiple of 32 (<= 1024); thread 0 holds the result.
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = (lane < nwarp) ? scratch[lane] : -3.4e38f;
+  return warp_max(t);
+}
 
 // MODE 0: a = x - shift[c], b = a*a          (forward statistics)
 // MODE 1: a = dy,           b = dy*(x-mean)  (backward reductions)
 // MODE 2: like MODE 1 with dy masked by the fused ReLU: dy * (z >= 0), z recomputed from x
 // partial layout: [S][C][2]; grid = (C, S)
-template <int MODE>
+// EXTRA: two more partials per (split, channel), folded with max by the *_extra finalize kernels, from which the
+// magnitude of the pass's OUTPUT is known before it is written (the FP16x3 convolution engine stages its operands
+// with one power-of-two scale per tensor):  MODE 0: max (x - shift), max (shift - x);  MODE 1/2: max |dy (masked)|,
+// max |x - mean|.  partial layout [S][C][4].
+template <int MODE, bool EXTRA = false>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ partial, const float* __restrict__ x,
                                                         const float* __restrict__ dy, const float* __restrict__ mean,
                                                         int64_t N, int64_t C, int64_t P, int64_t n_per_split,
@@ -37,6 +52,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
   if (n1 > N) n1 = N;
   const float ref = (MODE == 0) ? x[c * P] : mean[c];
   float sa = 0.f, sb = 0.f;
+  float ea = 0.f, eb = 0.f;   // EXTRA maxima (all four candidates are >= 0 at the reference point)
   if (vec_ok) {
     const int64_t P4 = P >> 2;
     const int64_t items = (n1 - n0) * P4;
@@ -72,6 +88,10 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
           const float a0 = xv[u].x - ref, a1 = xv[u].y - ref, a2 = xv[u].z - ref, a3 = xv[u].w - ref;
           sa += (a0 + a1) + (a2 + a3);
           sb += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          if (EXTRA) {
+            ea = fmaxf(ea, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+            eb = fmaxf(eb, -fminf(fminf(a0, a1), fminf(a2, a3)));
+          }
         } else {
           float4 g = gv[u];
           if (MODE == 2) {
@@ -82,6 +102,11 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
           }
           sa += (g.x + g.y) + (g.z + g.w);
           sb += (g.x * (xv[u].x - ref) + g.y * (xv[u].y - ref)) + (g.z * (xv[u].z - ref) + g.w * (xv[u].w - ref));
+          if (EXTRA) {
+            ea = fmaxf(ea, fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w))));
+            eb = fmaxf(eb, fmaxf(fmaxf(fabsf(xv[u].x - ref), fabsf(xv[u].y - ref)),
+                                 fmaxf(fabsf(xv[u].z - ref), fabsf(xv[u].w - ref))));
+          }
         }
       }
     }
@@ -94,19 +119,30 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
         const float a = x[off] - ref;
         sa += a;
         sb += a * a;
+        if (EXTRA) { ea = fmaxf(ea, a); eb = fmaxf(eb, -a); }
       } else {
         float g = dy[off];
         if (MODE == 2 && !(bn_affine(x[off], ref, za, zb) >= 0.f)) g = 0.f;
         sa += g;
         sb += g * (x[off] - ref);
+        if (EXTRA) { ea = fmaxf(ea, fabsf(g)); eb = fmaxf(eb, fabsf(x[off] - ref)); }
       }
     }
   }
+  constexpr int PS = EXTRA ? 4 : 2;
   const float ta = block_sum(sa, scratch);
   const float tb = block_sum(sb, scratch);
   if (threadIdx.x == 0) {
-    partial[(s * C + c) * 2 + 0] = ta;
-    partial[(s * C + c) * 2 + 1] = tb;
+    partial[(s * C + c) * PS + 0] = ta;
+    partial[(s * C + c) * PS + 1] = tb;
+  }
+  if (EXTRA) {
+    const float ma = block_max(ea, scratch);
+    const float mb = block_max(eb, scratch);
+    if (threadIdx.x == 0) {
+      partial[(s * C + c) * PS + 2] = ma;
+      partial[(s * C + c) * PS + 3] = mb;
+    }
   }
 }
 
@@ -114,13 +150,23 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
 __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ x,
                                                               float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                                               float* running_mean, float* running_var, int64_t C,
-                                                              int64_t P, int S, float count, float eps, float momentum) {
+                                                              int64_t P, int S, float count, float eps, float momentum,
+                                                              int PS = 2, const float* __restrict__ gamma = nullptr,
+                                                              const float* __restrict__ beta = nullptr, int act = 0,
+                                                              unsigned int* absmax_bits = nullptr) {
+  // PS == 4 (absmax_bits given): the partials carry max (x - shift) and max (shift - x); the normalised output is
+  // monotone in x, so max |y| of the channel is attained at one of the two extremes and *absmax_bits becomes the
+  // bits of max |y| over the tensor (y = the output of the apply pass, ReLU included, evaluated with bn_affine)
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  float sa = 0.f, sb = 0.f;
+  float sa = 0.f, sb = 0.f, hi = 0.f, lo = 0.f;
   for (int s = 0; s < S; ++s) {
-    sa += partial[(s * C + c) * 2 + 0];
-    sb += partial[(s * C + c) * 2 + 1];
+    sa += partial[(s * C + c) * PS + 0];
+    sb += partial[(s * C + c) * PS + 1];
+    if (PS == 4) {
+      hi = fmaxf(hi, partial[(s * C + c) * PS + 2]);
+      lo = fmaxf(lo, partial[(s * C + c) * PS + 3]);
+    }
   }
   const float shift = x[c * P];
   const float d = sa / count;               // mean - shift
@@ -128,12 +174,22 @@ __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __res
   float ssd = sb - sa * d;                  // sum (x-mean)^2 = sum a^2 - (sum a)^2 / n
   if (ssd < 0.f) ssd = 0.f;
   const float var_b = ssd / count;          // module.py:366
+  const float invstd = 1.f / sqrtf(var_b + eps);
   save_mean[c] = mean;
-  save_invstd[c] = 1.f / sqrtf(var_b + eps);
+  save_invstd[c] = invstd;
   if (running_mean) {
     const float var_u = ssd / (count - 1.f);  // module.py:367-368
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * var_u;
+  }
+  if (absmax_bits) {
+    const float a = gamma[c] * invstd, b = beta[c];
+    const float z0 = bn_affine(shift + hi, mean, a, b), z1 = bn_affine(shift - lo, mean, a, b);
+    // (shift + hi and shift - lo reproduce the extreme elements exactly: a - ref is exact only up to rounding, so
+    //  one ulp of slack is added below)
+    float m = act ? fmaxf(fmaxf(z0, z1), 0.f) : fmaxf(fabsf(z0), fabsf(z1));
+    m *= 1.0001f;
+    if (m > 0.f && m < 3.0e38f) atomicMax(absmax_bits, __float_as_uint(m));
   }
 }
 
@@ -228,19 +284,33 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, co
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial,
                                                               const float* __restrict__ invstd, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ sums, int64_t C,
-                                                              int S, float count) {
+                                                              int S, float count, int PS = 2,
+                                                              const float* __restrict__ gamma = nullptr,
+                                                              unsigned int* bound_bits = nullptr) {
+  // PS == 4 (bound_bits given, single process): *bound_bits becomes the bits of an upper bound of max |dx| over the
+  // tensor, |dx| <= |k0| (max |dy| + |k1| + max |x - mean| |k2|) per channel with the k's of bn_bwd_dx_kernel
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0) sums[2 * C] = count;  // summed across ranks with the two per-channel sums (synchronised BatchNorm)
   if (c >= C) return;
-  float sa = 0.f, sb = 0.f;
+  float sa = 0.f, sb = 0.f, mg = 0.f, mx = 0.f;
   for (int s = 0; s < S; ++s) {
-    sa += partial[(s * C + c) * 2 + 0];
-    sb += partial[(s * C + c) * 2 + 1];
+    sa += partial[(s * C + c) * PS + 0];
+    sb += partial[(s * C + c) * PS + 1];
+    if (PS == 4) {
+      mg = fmaxf(mg, partial[(s * C + c) * PS + 2]);
+      mx = fmaxf(mx, partial[(s * C + c) * PS + 3]);
+    }
   }
   dbeta[c] = sa;
   dgamma[c] = sb * invstd[c];
   sums[c * 2 + 0] = sa;  // sum dy
   sums[c * 2 + 1] = sb;  // sum dy * (x - mean)
+  if (bound_bits) {
+    const float inv = invstd[c], inv_count = 1.f / count;
+    const float k0 = gamma[c] * inv, k1 = sa * inv_count, k2 = inv * inv * sb * inv_count;
+    const float m = fabsf(k0) * (mg + fabsf(k1) + mx * fabsf(k2)) * 1.0001f;
+    if (m > 0.f && m < 3.0e38f) atomicMax(bound_bits, __float_as_uint(m));
+  }
 }
 
 // dx = gamma*invstd * (dy - sum_dy/n - (x-mean) * invstd^2 * sum_dy_xmu / n)
@@ -318,21 +388,28 @@ using namespace ng;
 
 extern "C" {
 
-int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
-                          uint64_t running_var, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C,
-                          int64_t HW, float eps, float momentum, int act) {
-  NG_ENSURE_INIT();
-  NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_fwd_train: empty input");
-  NG_REQUIRE(C <= 65535, "ng_bn2d_fwd_train: too many channels");
-  NG_REQUIRE(act == 0 || act == 1, "ng_bn2d_act_fwd_train: act must be 0 (none) or 1 (ReLU)");
+// Statistics half of the training forward: mean / invstd (and the running statistics) of x.  With absmax_bits
+// (single process only) the statistics pass also tracks the channel extremes and *absmax_bits receives the bits of
+// max |y| of the normalised (and activated) output before any of it is written.
+static int bn_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean, uint64_t running_var,
+                        uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW,
+                        float eps, float momentum, int act, int vec) {
   int64_t n_per = 0;
   const int S = bn_split(N, C, HW, &n_per);
+  const bool extra = absmax_bits != 0;
+  NG_REQUIRE(!(extra && dp_sync_bn()), "ng_bn2d_act_fwd_stats: not available under synchronised BatchNorm");
   float* partial = nullptr;
-  if (pool_alloc((void**)&partial, (uint64_t)S * C * 2 * sizeof(float))) return 1;
-  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
-  NG_LAUNCH((bn_reduce_kernel<0>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
-            (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr,
-            (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
+  if (pool_alloc((void**)&partial, (uint64_t)S * C * (extra ? 4 : 2) * sizeof(float))) return 1;
+  if (extra) {
+    NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(absmax_bits), 0, 4, g_stream));
+    NG_LAUNCH((bn_reduce_kernel<0, true>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
+              (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr,
+              (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
+  } else {
+    NG_LAUNCH((bn_reduce_kernel<0>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
+              (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr,
+              (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
+  }
   NG_CHECK_LAUNCH();
   if (dp_sync_bn()) {
     const int world = dp_world();
@@ -351,17 +428,58 @@ int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
   } else {
     NG_LAUNCH(bn_fwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, dptr<const float>(x),
               dptr<float>(save_mean), dptr<float>(save_invstd), running_mean ? dptr<float>(running_mean) : nullptr,
-              running_var ? dptr<float>(running_var) : nullptr, C, HW, S, (float)(N * HW), eps, momentum);
+              running_var ? dptr<float>(running_var) : nullptr, C, HW, S, (float)(N * HW), eps, momentum,
+              extra ? 4 : 2, extra ? dptr<const float>(gamma) : nullptr, extra ? dptr<const float>(beta) : nullptr, act,
+              extra ? dptr<unsigned int>(absmax_bits) : nullptr);
     NG_CHECK_LAUNCH();
   }
-  const int64_t total = N * C * HW;
-  NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
-            dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(save_mean),
-            dptr<const float>(save_invstd), total, C, HW, eps, 0, vec, act, make_fastdiv(vec ? HW / 4 : 0),
-            make_fastdiv(C));
-  NG_CHECK_LAUNCH();
   pool_free(partial);
   return 0;
+}
+
+static int bn_apply(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd, int64_t N,
+                    int64_t C, int64_t HW, int act, int vec) {
+  const int64_t total = N * C * HW;
+  NG_LAUNCH(bn_apply_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(y), dptr<const float>(x),
+            dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(mean), dptr<const float>(invstd), total, C,
+            HW, 0.f, 0, vec, act, make_fastdiv(vec ? HW / 4 : 0), make_fastdiv(C));
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
+                          uint64_t running_var, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C,
+                          int64_t HW, float eps, float momentum, int act) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_fwd_train: empty input");
+  NG_REQUIRE(C <= 65535, "ng_bn2d_fwd_train: too many channels");
+  NG_REQUIRE(act == 0 || act == 1, "ng_bn2d_act_fwd_train: act must be 0 (none) or 1 (ReLU)");
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
+  if (bn_fwd_stats(x, gamma, beta, running_mean, running_var, save_mean, save_invstd, 0, N, C, HW, eps, momentum, act, vec))
+    return 1;
+  return bn_apply(y, x, gamma, beta, save_mean, save_invstd, N, C, HW, act, vec);
+}
+
+int ng_bn2d_act_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean, uint64_t running_var,
+                          uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits, int64_t N, int64_t C,
+                          int64_t HW, float eps, float momentum, int act) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_act_fwd_stats: empty input");
+  NG_REQUIRE(C <= 65535, "ng_bn2d_act_fwd_stats: too many channels");
+  NG_REQUIRE(act == 0 || act == 1, "ng_bn2d_act_fwd_stats: act must be 0 (none) or 1 (ReLU)");
+  NG_REQUIRE(absmax_bits != 0, "ng_bn2d_act_fwd_stats: absmax_bits is required");
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0);
+  return bn_fwd_stats(x, gamma, beta, running_mean, running_var, save_mean, save_invstd, absmax_bits, N, C, HW, eps,
+                      momentum, act, vec);
+}
+
+int ng_bn2d_act_apply(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd,
+                      int64_t N, int64_t C, int64_t HW, int act) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_act_apply: empty input");
+  NG_REQUIRE(act == 0 || act == 1, "ng_bn2d_act_apply: act must be 0 (none) or 1 (ReLU)");
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((y & 15u) == 0);
+  return bn_apply(y, x, gamma, beta, save_mean, save_invstd, N, C, HW, act, vec);
 }
 
 int ng_bn2d_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean,
@@ -391,6 +509,57 @@ int ng_bn2d_fwd_eval(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint
   return ng_bn2d_act_fwd_eval(y, x, gamma, beta, running_mean, running_var, N, C, HW, eps, 0);
 }
 
+// Reduction half of the backward: dgamma, dbeta and sums[2C + 1] = {sum dy, sum dy (x - mean)} per channel and
+// the element count behind them (all-reduced under synchronised BatchNorm).  With bound_bits (single process
+// only) *bound_bits receives the bits of an upper bound of max |dx|.
+static int bn_bwd_sums(float* sums, uint64_t dgamma, uint64_t dbeta, uint64_t bound_bits, uint64_t dy, uint64_t x,
+                       uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C,
+                       int64_t HW, int act, int vec) {
+  int64_t n_per = 0;
+  const int S = bn_split(N, C, HW, &n_per);
+  const bool extra = bound_bits != 0;
+  NG_REQUIRE(!(extra && dp_sync_bn()), "ng_bn2d_act_bwd_sums: not available under synchronised BatchNorm");
+  float* partial = nullptr;
+  if (pool_alloc((void**)&partial, (uint64_t)S * C * (extra ? 4 : 2) * sizeof(float))) return 1;
+  const float* g = act ? dptr<const float>(gamma) : nullptr;
+  const float* b = act ? dptr<const float>(beta) : nullptr;
+  const float* iv = act ? dptr<const float>(save_invstd) : nullptr;
+  const dim3 grid((unsigned)C, (unsigned)S);
+  const FastDiv fd = make_fastdiv(vec ? HW / 4 : 0);
+  if (extra) NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(bound_bits), 0, 4, g_stream));
+  if (act && extra)
+    NG_LAUNCH((bn_reduce_kernel<2, true>), grid, 256, 0, partial, dptr<const float>(x), dptr<const float>(dy),
+              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd);
+  else if (act)
+    NG_LAUNCH((bn_reduce_kernel<2>), grid, 256, 0, partial, dptr<const float>(x), dptr<const float>(dy),
+              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd);
+  else if (extra)
+    NG_LAUNCH((bn_reduce_kernel<1, true>), grid, 256, 0, partial, dptr<const float>(x), dptr<const float>(dy),
+              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd);
+  else
+    NG_LAUNCH((bn_reduce_kernel<1>), grid, 256, 0, partial, dptr<const float>(x), dptr<const float>(dy),
+              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd);
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial,
+            dptr<const float>(save_invstd), dptr<float>(dgamma), dptr<float>(dbeta), sums, C, S, (float)(N * HW),
+            extra ? 4 : 2, extra ? dptr<const float>(gamma) : nullptr, extra ? dptr<unsigned int>(bound_bits) : nullptr);
+  NG_CHECK_LAUNCH();
+  pool_free(partial);
+  return 0;
+}
+
+static int bn_bwd_dx(uint64_t dx, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean,
+                     uint64_t save_invstd, const float* sums, int64_t N, int64_t C, int64_t HW, int act, int vec, int sync) {
+  const int64_t total = N * C * HW;
+  NG_LAUNCH(bn_bwd_dx_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(dx), dptr<const float>(dy),
+            dptr<const float>(x), dptr<const float>(gamma), dptr<const float>(save_mean),
+            dptr<const float>(save_invstd), sums, total, C, HW, 1.f / (float)(N * HW), vec,
+            act ? dptr<const float>(beta) : (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0), make_fastdiv(C),
+            sync);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
 int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x, uint64_t gamma,
                     uint64_t beta, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C, int64_t HW,
                     int act) {
@@ -398,38 +567,39 @@ int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, u
   NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_bwd: empty input");
   NG_REQUIRE(C <= 65535, "ng_bn2d_bwd: too many channels");
   NG_REQUIRE(act == 0 || (act == 1 && beta != 0), "ng_bn2d_act_bwd: act must be 0, or 1 (ReLU) with beta given");
-  int64_t n_per = 0;
-  const int S = bn_split(N, C, HW, &n_per);
-  float* partial = nullptr;
-  if (pool_alloc((void**)&partial, ((uint64_t)(S + 1) * C * 2 + 4) * sizeof(float))) return 1;
-  float* sums = partial + (int64_t)S * C * 2;  // [C][2] sums, then the element count behind them
+  float* sums = nullptr;  // [C][2] sums, then the element count behind them
+  if (pool_alloc((void**)&sums, ((uint64_t)C * 2 + 4) * sizeof(float))) return 1;
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0) && ((dx & 15u) == 0);
-  if (act) {
-    NG_LAUNCH((bn_reduce_kernel<2>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
-              dptr<const float>(dy), dptr<const float>(save_mean), N, C, HW, n_per, vec, dptr<const float>(gamma),
-              dptr<const float>(beta), dptr<const float>(save_invstd), make_fastdiv(vec ? HW / 4 : 0));
-  } else {
-    NG_LAUNCH((bn_reduce_kernel<1>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
-              dptr<const float>(dy), dptr<const float>(save_mean), N, C, HW, n_per, vec, (const float*)nullptr,
-              (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
-  }
-  NG_CHECK_LAUNCH();
-  NG_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial,
-            dptr<const float>(save_invstd), dptr<float>(dgamma), dptr<float>(dbeta), sums, C, S, (float)(N * HW));
-  NG_CHECK_LAUNCH();
+  if (bn_bwd_sums(sums, dgamma, dbeta, 0, dy, x, gamma, beta, save_mean, save_invstd, N, C, HW, act, vec)) return 1;
   // synchronised BatchNorm: dgamma / dbeta stay this rank's sums (the gradient bucket adds them across
   // ranks); dx needs the two sums, and the count, over the global batch
   const int sync = dp_sync_bn() ? 1 : 0;
   if (sync && dp_allreduce_inline(sums, 2 * C + 1)) return 1;
-  const int64_t total = N * C * HW;
-  NG_LAUNCH(bn_bwd_dx_kernel, bgrid(vec ? total / 4 : total), 256, 0, dptr<float>(dx), dptr<const float>(dy),
-            dptr<const float>(x), dptr<const float>(gamma), dptr<const float>(save_mean),
-            dptr<const float>(save_invstd), (const float*)sums, total, C, HW, 1.f / (float)(N * HW), vec,
-            act ? dptr<const float>(beta) : (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0), make_fastdiv(C),
-            sync);
-  NG_CHECK_LAUNCH();
-  pool_free(partial);
-  return 0;
+  const int rc = bn_bwd_dx(dx, dy, x, gamma, beta, save_mean, save_invstd, sums, N, C, HW, act, vec, sync);
+  pool_free(sums);
+  return rc;
+}
+
+int ng_bn2d_act_bwd_sums(uint64_t dgamma, uint64_t dbeta, uint64_t sums, uint64_t bound_bits, uint64_t dy, uint64_t x,
+                         uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd, int64_t N, int64_t C,
+                         int64_t HW, int act) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_act_bwd_sums: empty input");
+  NG_REQUIRE(C <= 65535, "ng_bn2d_act_bwd_sums: too many channels");
+  NG_REQUIRE(act == 0 || (act == 1 && beta != 0), "ng_bn2d_act_bwd_sums: act must be 0, or 1 (ReLU) with beta given");
+  NG_REQUIRE(sums != 0 && bound_bits != 0, "ng_bn2d_act_bwd_sums: sums and bound_bits are required");
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0);
+  return bn_bwd_sums(dptr<float>(sums), dgamma, dbeta, bound_bits, dy, x, gamma, beta, save_mean, save_invstd, N, C, HW,
+                     act, vec);
+}
+
+int ng_bn2d_act_bwd_dx(uint64_t dx, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean,
+                       uint64_t save_invstd, uint64_t sums, int64_t N, int64_t C, int64_t HW, int act) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_act_bwd_dx: empty input");
+  NG_REQUIRE(act == 0 || (act == 1 && beta != 0), "ng_bn2d_act_bwd_dx: act must be 0, or 1 (ReLU) with beta given");
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0) && ((dx & 15u) == 0);
+  return bn_bwd_dx(dx, dy, x, gamma, beta, save_mean, save_invstd, dptr<const float>(sums), N, C, HW, act, vec, 0);
 }
 
 int ng_bn2d_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x, uint64_t gamma,

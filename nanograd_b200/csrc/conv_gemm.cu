@@ -1089,7 +1089,7 @@ int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL, "ng_conv2d_stage_nhwc: bad dimensions");
   if (flags & NG_F_STAGE_F16)
-    return umma::to_nhwc_f16(dptr<void>(dst), dptr<const float>(src), nullptr, (int)N, (int)C, (int)HW);
+    return umma::to_nhwc_f16(dptr<void>(dst), dptr<const float>(src), nullptr, (int)N, (int)C, (int)HW, nullptr);
   return umma::to_nhwc(dptr<float>(dst), dptr<const float>(src), (int)N, (int)C, (int)HW, (flags & NG_F_TF32) ? 1 : 0);
 #else
   (void)dst; (void)src; (void)N; (void)C; (void)HW; (void)flags;
@@ -1102,12 +1102,60 @@ int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t 
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL && N <= 65535, "ng_conv2d_stage_nhwc_sum: bad dimensions");
   if (flags & NG_F_STAGE_F16)
-    return umma::to_nhwc_f16(dptr<void>(dst), dptr<const float>(src), dptr<float>(sums), (int)N, (int)C, (int)HW);
+    return umma::to_nhwc_f16(dptr<void>(dst), dptr<const float>(src), dptr<float>(sums), (int)N, (int)C, (int)HW, nullptr);
   return umma::to_nhwc_sum(dptr<float>(dst), dptr<const float>(src), dptr<float>(sums), (int)N, (int)C, (int)HW,
                            (flags & NG_F_TF32) ? 1 : 0);
 #else
   (void)dst; (void)src; (void)sums; (void)N; (void)C; (void)HW; (void)flags;
   return set_error("ng_conv2d_stage_nhwc_sum: the tensor-core path does not exist in the emulation build");
+#endif
+}
+
+int ng_conv2d_stage_f16(uint64_t dst, uint64_t src, uint64_t sums, uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW) {
+  NG_ENSURE_INIT();
+#ifndef NG_EMU
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL && (sums == 0 || N <= 65535),
+             "ng_conv2d_stage_f16: bad dimensions");
+  return umma::to_nhwc_f16(dptr<void>(dst), dptr<const float>(src), sums ? dptr<float>(sums) : nullptr, (int)N, (int)C,
+                           (int)HW, absmax_bits ? dptr<const unsigned int>(absmax_bits) : nullptr);
+#else
+  (void)dst; (void)src; (void)sums; (void)absmax_bits; (void)N; (void)C; (void)HW;
+  return set_error("ng_conv2d_stage_f16: the tensor-core path does not exist in the emulation build");
+#endif
+}
+
+int ng_conv2d_stage_f16_bn(uint64_t dst, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd,
+                           uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW, int act) {
+  NG_ENSURE_INIT();
+#ifndef NG_EMU
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL, "ng_conv2d_stage_f16_bn: bad dimensions");
+  NG_REQUIRE(absmax_bits != 0 && (act == 0 || act == 1), "ng_conv2d_stage_f16_bn: absmax_bits required, act 0 or 1");
+  return umma::to_nhwc_f16_bn(dptr<void>(dst), dptr<const float>(x), dptr<const float>(gamma), dptr<const float>(beta),
+                              dptr<const float>(mean), dptr<const float>(invstd), act,
+                              dptr<const unsigned int>(absmax_bits), (int)N, (int)C, (int)HW);
+#else
+  (void)dst; (void)x; (void)gamma; (void)beta; (void)mean; (void)invstd; (void)absmax_bits; (void)N; (void)C; (void)HW; (void)act;
+  return set_error("ng_conv2d_stage_f16_bn: the tensor-core path does not exist in the emulation build");
+#endif
+}
+
+int ng_conv2d_stage_f16_bnbwd(uint64_t dst, uint64_t chan_sums, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta,
+                              uint64_t mean, uint64_t invstd, uint64_t bn_sums, uint64_t bound_bits, int64_t N, int64_t C,
+                              int64_t HW, int act) {
+  NG_ENSURE_INIT();
+#ifndef NG_EMU
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL && (chan_sums == 0 || N <= 65535),
+             "ng_conv2d_stage_f16_bnbwd: bad dimensions");
+  NG_REQUIRE(bound_bits != 0 && bn_sums != 0 && (act == 0 || (act == 1 && beta != 0)),
+             "ng_conv2d_stage_f16_bnbwd: bound_bits and bn_sums required; act 0, or 1 with beta");
+  return umma::to_nhwc_f16_bnbwd(dptr<void>(dst), chan_sums ? dptr<float>(chan_sums) : nullptr, dptr<const float>(dy),
+                                 dptr<const float>(x), dptr<const float>(gamma), beta ? dptr<const float>(beta) : nullptr,
+                                 dptr<const float>(mean), dptr<const float>(invstd), dptr<const float>(bn_sums), act,
+                                 dptr<const unsigned int>(bound_bits), (int)N, (int)C, (int)HW);
+#else
+  (void)dst; (void)chan_sums; (void)dy; (void)x; (void)gamma; (void)beta; (void)mean; (void)invstd; (void)bn_sums;
+  (void)bound_bits; (void)N; (void)C; (void)HW; (void)act;
+  return set_error("ng_conv2d_stage_f16_bnbwd: the tensor-core path does not exist in the emulation build");
 #endif
 }
 

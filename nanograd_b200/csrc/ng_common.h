@@ -156,6 +156,9 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return t;
 }
 
+// BatchNorm's affine map, z = (x - mean) * (gamma * invstd) + beta, written ONE way (see batchnorm.cu)
+__device__ __forceinline__ float bn_affine(float x, float mu, float a, float b) { return fmaf(x - mu, a, b); }
+
 __device__ __forceinline__ bool aligned16(const void* p) {
   return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }

@@ -332,12 +332,19 @@ int conv_wgrad_tf32(float* dw, const float* dy, const float* x, int N, int C, in
                     int stride, int pad_t, int pad_l, int OH, int OW, int x3, int x_is_nhwc, int dy_is_nhwc);
 int to_nhwc(float* out, const float* in, int N, int C, int HW, int round);
 // sums[c] = sum_n partial[n][c] in a fixed order (second pass of the staging kernels' channel sums)
-int channel_partial_sum(float* sums, const float* partial, int N, int C);
+int channel_partial_sum(float* sums, const float* partial, long long N, int C);
 // FP16x3 (FP32-accurate) engine, umma_conv_f16.cu: operands staged once per tensor as scaled (hi, lo) FP16
 // pairs, channels-last; `staged` holds N*C*HW*4 + 64 bytes; sums (optional) receives the per-channel sums of
 // `in`.  *_is_staged: that argument already is the to_nhwc_f16 copy.  Same return convention as above.
 bool f16x3_supported(int C, int K, int RS);
-int to_nhwc_f16(void* staged, const float* in, float* sums, int N, int C, int HW);
+// known_bits (optional): device word holding the bits of max |in| (or an upper bound) when the producer knows it
+int to_nhwc_f16(void* staged, const float* in, float* sums, int N, int C, int HW, const unsigned int* known_bits);
+// the same staged copy of a BatchNorm2d (+ ReLU) output / input gradient that was never written (see StageSrc)
+int to_nhwc_f16_bn(void* staged, const float* x, const float* gamma, const float* beta, const float* mean,
+                   const float* invstd, int act, const unsigned int* absmax_bits, int N, int C, int HW);
+int to_nhwc_f16_bnbwd(void* staged, float* chan_sums, const float* dy, const float* x, const float* gamma,
+                      const float* beta, const float* mean, const float* invstd, const float* bn_sums, int act,
+                      const unsigned int* bound_bits, int N, int C, int HW);
 int conv_fprop_f16(float* y, const void* x, const float* w, const float* bias, int N, int C, int H, int W, int K, int R,
                    int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x_is_staged);
 int conv_dgrad_f16(float* dx, const void* dy, const float* w, int N, int C, int H, int W, int K, int R, int S,

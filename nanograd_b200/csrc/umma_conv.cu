@@ -148,28 +148,47 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_sum_kernel(float* __restrict
   }
 }
 
-// sums[c] = sum_n partial[n][c]; block = 32 channels x 32 image lanes
-__global__ void __launch_bounds__(1024) channel_partial_sum_kernel(float* __restrict__ sums, const float* __restrict__ partial,
-                                                                   int N, int C) {
+// out[split][c] = sum over the rows n of the split of partial[n][c]; block = 32 channels x 32 row lanes,
+// grid (C / 32, splits)
+__global__ void __launch_bounds__(1024) channel_partial_sum_kernel(float* __restrict__ out, const float* __restrict__ partial,
+                                                                   long long N, int C, long long rows_per_split) {
   __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
+  const long long n0 = (long long)blockIdx.y * rows_per_split;
+  long long n1 = n0 + rows_per_split;
+  if (n1 > N) n1 = N;
   float acc = 0.f;
   if (c < C)
-    for (int n = ty; n < N; n += 32) acc += partial[(long long)n * C + c];
+    for (long long n = n0 + ty; n < n1; n += 32) acc += partial[n * C + c];
   red[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += red[i][tx];
-    sums[c] = t;
+    out[(long long)blockIdx.y * C + c] = t;
   }
 }
 
-int channel_partial_sum(float* sums, const float* partial, int N, int C) {
-  NG_LAUNCH(channel_partial_sum_kernel, (int)ceil_div(C, 32), 1024, 0, sums, partial, N, C);
+// sums[c] = sum_n partial[n][c] in a fixed order; many rows are folded in two levels so that the first one fills
+// the machine
+int channel_partial_sum(float* sums, const float* partial, long long N, int C) {
+  const unsigned cb = (unsigned)ceil_div(C, 32);
+  if (N <= 2048) {
+    NG_LAUNCH(channel_partial_sum_kernel, dim3(cb, 1), 1024, 0, sums, partial, N, C, N);
+    NG_CHECK_LAUNCH();
+    return 0;
+  }
+  const long long per = 512;
+  const long long splits = ceil_div(N, per);
+  float* mid = nullptr;
+  if (pool_alloc((void**)&mid, (uint64_t)splits * C * sizeof(float))) return 1;
+  NG_LAUNCH(channel_partial_sum_kernel, dim3(cb, (unsigned)splits), 1024, 0, mid, partial, N, C, per);
   NG_CHECK_LAUNCH();
+  NG_LAUNCH(channel_partial_sum_kernel, dim3(cb, 1), 1024, 0, sums, (const float*)mid, splits, C, splits);
+  NG_CHECK_LAUNCH();
+  pool_free(mid);
   return 0;
 }
 
@@ -179,8 +198,7 @@ int to_nhwc_sum(float* out, const float* in, float* sums, int N, int C, int HW, 
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)N);
   NG_LAUNCH(nchw_to_nhwc_sum_kernel, grid, 256, 0, out, in, partial, C, HW, round);
   NG_CHECK_LAUNCH();
-  NG_LAUNCH(channel_partial_sum_kernel, (int)ceil_div(C, 32), 1024, 0, sums, (const float*)partial, N, C);
-  NG_CHECK_LAUNCH();
+  if (channel_partial_sum(sums, partial, N, C)) return 1;
   pool_free(partial);
   return 0;
 }

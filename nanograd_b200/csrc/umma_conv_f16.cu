@@ -80,58 +80,103 @@ __device__ __forceinline__ void f16_split(float v, float scale, __half& hi, __ha
   lo = __float2half_rn(sv - __half2float(hi));
 }
 
-// staged[n][p][g][plane][64] = split(in[n][g*64 + .][p]); tiles of 64 channels x 32 pixels.
-//   SUM = false: grid (pixel tiles, groups, images).
-//   SUM = true : grid (groups, images); the block walks every pixel tile of its (image, group), keeps running channel
-//                sums in registers and writes partial[n][c] (the bias gradient when `in` is dy).
-template <bool SUM>
-__global__ void __launch_bounds__(256) stage_f16_kernel(__half* __restrict__ out, const float* __restrict__ in,
+// Where the staged tensor comes from.  SRC 0: an FP32 NCHW tensor.  SRC 1: the output of a training-mode
+// BatchNorm2d (+ ReLU) that was never written, y = act(bn_affine(x)) recomputed from the layer input x and its
+// statistics.  SRC 2: the input gradient of such a layer that was never written,
+// dx = k0 (dy (masked) - k1 - (x - mean) k2), recomputed from dy, x and the backward sums exactly as bn_bwd_dx_kernel
+// (batchnorm.cu) evaluates it.  Fusing the normalise passes into the staging pass removes one write and one read of
+// the activation (forward) and of the gradient (backward) per layer.
+struct StageSrc {
+  const float* in;       // SRC 0: the tensor; SRC 1, 2: the BatchNorm input x
+  const float* dy;       // SRC 2
+  const float* gamma;
+  const float* beta;     // null: no fused ReLU
+  const float* mean;
+  const float* invstd;
+  const float* sums;     // SRC 2: [C][2] = sum dy, sum dy (x - mean)
+  float inv_count;       // SRC 2
+  int act;
+};
+
+// staged[n][p][g][plane][64] = split(value[n][g*64 + .][p]); one tile of 64 channels x 32 pixels per block,
+// grid (pixel tiles, groups, images): many small blocks keep enough loads in flight (5.7 TB/s; a block walking all
+// the tiles of an (image, group) to keep running sums was latency-bound at 2.3 TB/s).
+//   SUM: the block also writes the channel sums of its tile, partial[(n * tiles + tile)][c] (folded in a fixed
+//        order by channel_partial_sum: the bias gradient when the staged tensor is dy).
+template <int SRC, bool SUM>
+__global__ void __launch_bounds__(256) stage_f16_kernel(__half* __restrict__ out, const StageSrc src,
                                                         float* __restrict__ partial, int C, int HW,
                                                         const unsigned int* __restrict__ max_bits,
                                                         float* __restrict__ inv_scale_out) {
   __shared__ float tile[64][33];
-  const float scale = f16_scale(*max_bits);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
+  __shared__ float cst[5][64];   // per-channel constants of the fused sources
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int G = C >> 6;
-  const int g = SUM ? blockIdx.x : blockIdx.y;
-  const int n = SUM ? blockIdx.y : blockIdx.z;
-  const int c0 = g * 64;
-  const float* src = in + ((long long)n * C + c0) * HW;
-  __half* dst = out + ((long long)n * HW * G + g) * 128;   // + p * G * 128 + plane * 64 + c
-  float acc[8];
+  const int g = blockIdx.y, n = blockIdx.z;
+  const int c0 = g * 64, p0 = blockIdx.x * 32;
+  const long long base = ((long long)n * C + c0) * HW;
+  // 1. the tile loads go out first: everything below overlaps their latency
+  float xv[8], gv[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const int p_begin = SUM ? 0 : blockIdx.x * 32;
-  const int p_end = SUM ? HW : p_begin + 32;
-  for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = ty + 8 * i, p = p0 + tx;
-      const float v = (p < HW) ? src[(long long)c * HW + p] : 0.f;
-      tile[c][tx] = v;
-      if (SUM) acc[i] += v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pl = ty + 8 * i, p = p0 + pl;
-      if (p < HW) {
-        __half h0, l0, h1, l1;
-        f16_split(tile[2 * tx][pl], scale, h0, l0);
-        f16_split(tile[2 * tx + 1][pl], scale, h1, l1);
-        __half2* row = reinterpret_cast<__half2*>(dst + (long long)p * G * 128);
-        row[tx] = __halves2half2(h0, h1);
-        row[32 + tx] = __halves2half2(l0, l1);
+  for (int i = 0; i < 8; ++i) {
+    const int p = p0 + tx;
+    const long long off = base + (long long)(ty + 8 * i) * HW + p;
+    xv[i] = (p < HW) ? src.in[off] : 0.f;
+    gv[i] = (SRC == 2 && p < HW) ? src.dy[off] : 0.f;
+  }
+  // 2. scale, and the per-channel constants (64 threads, one channel each)
+  const float scale = f16_scale(*max_bits);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
+  if (SRC != 0) {
+    if (threadIdx.x < 64) {
+      const int c = c0 + threadIdx.x;
+      const float inv = src.invstd[c];
+      const float k0 = src.gamma[c] * inv;
+      cst[0][threadIdx.x] = src.mean[c];
+      cst[1][threadIdx.x] = k0;
+      if (SRC == 1) {
+        cst[2][threadIdx.x] = src.beta[c];
+      } else {
+        cst[2][threadIdx.x] = src.sums[c * 2] * src.inv_count;
+        cst[3][threadIdx.x] = inv * inv * src.sums[c * 2 + 1] * src.inv_count;
+        cst[4][threadIdx.x] = src.act ? src.beta[c] : 0.f;
       }
     }
     __syncthreads();
   }
-  if (SUM) {
+  // 3. values -> transpose tile (+ channel sums)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float v = warp_sum(acc[i]);
-      if (tx == 0) partial[(long long)n * C + c0 + ty + 8 * i] = v;
+  for (int i = 0; i < 8; ++i) {
+    const int c = ty + 8 * i;
+    float v = xv[i];
+    if (SRC == 1) {
+      v = bn_affine(xv[i], cst[0][c], cst[1][c], cst[2][c]);
+      if (src.act) v = fmaxf(v, 0.f);
+    } else if (SRC == 2) {
+      const float mu = cst[0][c], k0 = cst[1][c];
+      float gg = gv[i];
+      if (src.act && !(bn_affine(xv[i], mu, k0, cst[4][c]) >= 0.f)) gg = 0.f;
+      v = k0 * (gg - cst[2][c] - (xv[i] - mu) * cst[3][c]);
+    }
+    if (p0 + tx >= HW) v = 0.f;
+    tile[c][tx] = v;
+    if (SUM) {
+      const float t = warp_sum(v);
+      if (tx == 0) partial[((long long)n * gridDim.x + blockIdx.x) * C + c0 + c] = t;
+    }
+  }
+  __syncthreads();
+  __half* dst = out + ((long long)n * HW * G + g) * 128;   // + p * G * 128 + plane * 64 + c
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pl = ty + 8 * i, p = p0 + pl;
+    if (p < HW) {
+      __half h0, l0, h1, l1;
+      f16_split(tile[2 * tx][pl], scale, h0, l0);
+      f16_split(tile[2 * tx + 1][pl], scale, h1, l1);
+      __half2* row = reinterpret_cast<__half2*>(dst + (long long)p * G * 128);
+      row[tx] = __halves2half2(h0, h1);
+      row[32 + tx] = __halves2half2(l0, l1);
     }
   }
 }
@@ -171,29 +216,61 @@ static inline float* staged_meta(void* staged, long long n_elems) {
   return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(staged) + n_elems * 4);
 }
 
-// Stage an NCHW FP32 tensor (C % 64 == 0) as the pair-interleaved FP16 channels-last copy.
-// `staged` holds N*C*HW*4 + 64 bytes; sums (optional) receives the per-channel sums of `in`.
-int to_nhwc_f16(void* staged, const float* in, float* sums, int N, int C, int HW) {
+// Stage a tensor (C % 64 == 0) as the pair-interleaved FP16 channels-last copy.  `staged` holds N*C*HW*4 + 64
+// bytes; sums (optional) receives the per-channel sums of the staged values; known_bits (optional) points at the
+// bits of max |value| (or an upper bound) established by the producer, else an absmax pass over src.in runs first.
+template <int SRC>
+static int stage_f16(void* staged, const StageSrc& src, float* sums, const unsigned int* known_bits, int N, int C, int HW) {
   if (C % 64 != 0) return set_error("to_nhwc_f16: channel count %d is not a multiple of 64", C);
   const long long n = (long long)N * C * HW;
   float* meta = staged_meta(staged, n);
-  unsigned int* bits = reinterpret_cast<unsigned int*>(meta + 1);
-  if (launch_absmax(bits, in, n)) return 1;
+  const unsigned int* bits = known_bits;
+  if (!bits) {
+    if (SRC != 0) return set_error("to_nhwc_f16: a fused source needs the magnitude of its values");
+    unsigned int* own = reinterpret_cast<unsigned int*>(meta + 1);
+    if (launch_absmax(own, src.in, n)) return 1;
+    bits = own;
+  }
   __half* out = reinterpret_cast<__half*>(staged);
+  dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)(C / 64), (unsigned)N);
   if (sums) {
+    const long long rows = (long long)N * grid.x;
     float* partial = nullptr;
-    if (pool_alloc((void**)&partial, (uint64_t)N * C * sizeof(float))) return 1;
-    dim3 grid((unsigned)(C / 64), (unsigned)N);
-    NG_LAUNCH((stage_f16_kernel<true>), grid, 256, 0, out, in, partial, C, HW, (const unsigned int*)bits, meta);
+    if (pool_alloc((void**)&partial, (uint64_t)rows * C * sizeof(float))) return 1;
+    NG_LAUNCH((stage_f16_kernel<SRC, true>), grid, 256, 0, out, src, partial, C, HW, bits, meta);
     NG_CHECK_LAUNCH();
-    if (channel_partial_sum(sums, partial, N, C)) return 1;
+    if (channel_partial_sum(sums, partial, rows, C)) return 1;
     pool_free(partial);
   } else {
-    dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)(C / 64), (unsigned)N);
-    NG_LAUNCH((stage_f16_kernel<false>), grid, 256, 0, out, in, (float*)nullptr, C, HW, (const unsigned int*)bits, meta);
+    NG_LAUNCH((stage_f16_kernel<SRC, false>), grid, 256, 0, out, src, (float*)nullptr, C, HW, bits, meta);
     NG_CHECK_LAUNCH();
   }
   return 0;
+}
+
+int to_nhwc_f16(void* staged, const float* in, float* sums, int N, int C, int HW, const unsigned int* known_bits) {
+  StageSrc src;
+  memset(&src, 0, sizeof(src));
+  src.in = in;
+  return stage_f16<0>(staged, src, sums, known_bits, N, C, HW);
+}
+
+int to_nhwc_f16_bn(void* staged, const float* x, const float* gamma, const float* beta, const float* mean,
+                   const float* invstd, int act, const unsigned int* absmax_bits, int N, int C, int HW) {
+  StageSrc src;
+  memset(&src, 0, sizeof(src));
+  src.in = x; src.gamma = gamma; src.beta = beta; src.mean = mean; src.invstd = invstd; src.act = act;
+  return stage_f16<1>(staged, src, nullptr, absmax_bits, N, C, HW);
+}
+
+int to_nhwc_f16_bnbwd(void* staged, float* chan_sums, const float* dy, const float* x, const float* gamma,
+                      const float* beta, const float* mean, const float* invstd, const float* bn_sums, int act,
+                      const unsigned int* bound_bits, int N, int C, int HW) {
+  StageSrc src;
+  memset(&src, 0, sizeof(src));
+  src.in = x; src.dy = dy; src.gamma = gamma; src.beta = beta; src.mean = mean; src.invstd = invstd;
+  src.sums = bn_sums; src.inv_count = 1.f / ((float)N * (float)HW); src.act = act;
+  return stage_f16<2>(staged, src, chan_sums, bound_bits, N, C, HW);
 }
 
 // ================================================================== gather kernel (fprop / dgrad)
@@ -474,7 +551,7 @@ static int launch_gather_f16(float* out, const void* act, const float* filt, con
   if (pool_alloc(&wt, (uint64_t)filt_elems * 4 + 64)) { pool_free(act_t); return 1; }
   int rc = 0;
   const void* act_s = act_is_staged ? act : act_t;
-  if (!act_is_staged) rc = to_nhwc_f16(act_t, reinterpret_cast<const float*>(act), nullptr, n_img, KC, AH * AW);
+  if (!act_is_staged) rc = to_nhwc_f16(act_t, reinterpret_cast<const float*>(act), nullptr, n_img, KC, AH * AW, nullptr);
   float* wmeta = staged_meta(wt, filt_elems);
   if (rc == 0) {
     // max|w| over the filter tensor: the KCRS block is contiguous whichever of (j, kc) is the outer axis
@@ -829,8 +906,8 @@ int conv_wgrad_f16(float* dw, const void* dyv, const void* x, int N, int C, int 
   int rc = 0;
   const void* x_s = x_is_staged ? x : x_t;
   const void* dy_s = dy_is_staged ? dyv : dy_t;
-  if (!x_is_staged) rc = to_nhwc_f16(x_t, reinterpret_cast<const float*>(x), nullptr, N, C, H * W);
-  if (rc == 0 && !dy_is_staged) rc = to_nhwc_f16(dy_t, reinterpret_cast<const float*>(dyv), nullptr, N, K, OH * OW);
+  if (!x_is_staged) rc = to_nhwc_f16(x_t, reinterpret_cast<const float*>(x), nullptr, N, C, H * W, nullptr);
+  if (rc == 0 && !dy_is_staged) rc = to_nhwc_f16(dy_t, reinterpret_cast<const float*>(dyv), nullptr, N, K, OH * OW, nullptr);
   if (rc == 0) {
     const uint64_t pix = (uint64_t)C * 4u;
     const uint64_t dims[5] = {64u, (uint64_t)W, (uint64_t)H, (uint64_t)(2 * (C / 64)), (uint64_t)N};

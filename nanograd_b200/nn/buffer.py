@@ -95,6 +95,42 @@ class DeviceBuffer:
         return f"<DeviceBuffer with shape {self.shape}>"
 
 
+class LazyBuffer(DeviceBuffer):
+    """A result whose device memory is only allocated and written if somebody asks for its pointer.
+
+    BatchNorm2d's normalise pass (and the dx pass of its backward) produce tensors whose only reader, in a
+    conv -> BatchNorm2d -> ReLU -> conv chain, is the staging copy of the next convolution's tensor-core
+    operands.  The op returns one of these instead: ``source`` describes how to recompute the values
+    (kind + the buffers involved), the convolution stages straight from it
+    (``ng_conv2d_stage_f16_bn`` / ``_bnbwd``) and the tensor itself is never written.  Any other consumer
+    (pooling, ``numpy()``, a view, an op of the generic namespace) reads ``.ptr``, which runs
+    ``materialize(ptr)`` once — the kernel the eager path would have run — so values and semantics are those
+    of a plain ``DeviceBuffer``."""
+
+    def __init__(self, shape, materialize, kind=None, source=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.float32
+        self.size = _numel(self.shape)
+        self._base = None
+        self._ptr = 0
+        self._materialize = materialize
+        self.kind = kind
+        self.source = source
+
+    @property
+    def pending(self):
+        """True while the values exist only as a recipe."""
+        return self._ptr == 0
+
+    @property
+    def ptr(self):
+        if not self._ptr:
+            self._ptr = backend.malloc(self.size * 4)
+            fn, self._materialize = self._materialize, None
+            fn(self._ptr)
+        return self._ptr
+
+
 class ScalarBuffer(DeviceBuffer):
     """A Python scalar travelling as a 1-element tensor.
 

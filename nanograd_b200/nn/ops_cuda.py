@@ -23,7 +23,7 @@ import numpy as np
 from nanograd_b200 import backend as B
 from nanograd_b200 import dist as _dist
 from nanograd_b200.autograd import Function
-from nanograd_b200.nn.buffer import DeviceBuffer, ScalarBuffer
+from nanograd_b200.nn.buffer import DeviceBuffer, LazyBuffer, ScalarBuffer
 
 __all__ = []  # classes are discovered by register_ops via inspect
 
@@ -587,17 +587,41 @@ def _stage_nhwc(buf, engine, channel_sums=False, sums_out=None):
     """Channels-last staging copy of an NCHW buffer for the tensor-core kernels (made once, shared
     by the passes of one layer that read the same tensor).  engine 1: FP32 NHWC; engine 2 (FP16x3):
     scaled (hi, lo) FP16 pairs plus 64 bytes of metadata.  channel_sums=True also returns the
-    per-channel sums of `buf` from the same read (the bias gradient when `buf` is dy)."""
+    per-channel sums of `buf` from the same read (the bias gradient when `buf` is dy).
+
+    Engine 2 uses what the producer left on the buffer: a pending ``LazyBuffer`` of a BatchNorm2d forward /
+    backward is staged from its recipe (the tensor is never written), and a known magnitude (``absmax``: a
+    one-word device buffer with the bits of max|buf| or an upper bound) replaces the absmax pass."""
     n, c = buf.shape[0], buf.shape[1]
     hw = _numel(buf.shape[2:])
-    flags = B.math_flags() | (B.F_STAGE_F16 if engine == 2 else 0)
-    out = DeviceBuffer((n * c * hw + 16,)) if engine == 2 else DeviceBuffer(buf.shape)
+    want_sums = channel_sums and n <= 65535
+    if engine == 2:
+        out = DeviceBuffer((n * c * hw + 16,))
+        out.staged_flags = (B.math_flags(), engine)
+        sums = (sums_out if sums_out is not None else DeviceBuffer((c,))) if want_sums else None
+        sums_ptr = sums.ptr if sums is not None else 0
+        kind = buf.kind if isinstance(buf, LazyBuffer) and buf.pending else None
+        if kind == "bn_fwd" and not want_sums:
+            x, gamma, beta, mean, invstd, act, absmax = buf.source
+            _lib().ng_conv2d_stage_f16_bn(out.ptr, x.ptr, gamma.ptr, beta.ptr, mean.ptr, invstd.ptr, absmax.ptr,
+                                          n, c, hw, act)
+        elif kind == "bn_bwd":
+            dy, x, gamma, beta, mean, invstd, bn_sums, act, bound = buf.source
+            _lib().ng_conv2d_stage_f16_bnbwd(out.ptr, sums_ptr, dy.ptr, x.ptr, gamma.ptr, beta.ptr if act else 0,
+                                             mean.ptr, invstd.ptr, bn_sums.ptr, bound.ptr, n, c, hw, act)
+        else:
+            known = getattr(buf, "absmax", None)
+            _lib().ng_conv2d_stage_f16(out.ptr, buf.ptr, sums_ptr, known.ptr if known is not None else 0, n, c, hw)
+        if channel_sums:
+            return out, sums
+        return out
+    out = DeviceBuffer(buf.shape)
     out.staged_flags = (B.math_flags(), engine)
-    if channel_sums and n <= 65535:
+    if want_sums:
         sums = sums_out if sums_out is not None else DeviceBuffer((c,))
-        _lib().ng_conv2d_stage_nhwc_sum(out.ptr, buf.ptr, sums.ptr, n, c, hw, flags)
+        _lib().ng_conv2d_stage_nhwc_sum(out.ptr, buf.ptr, sums.ptr, n, c, hw, B.math_flags())
         return out, sums
-    _lib().ng_conv2d_stage_nhwc(out.ptr, buf.ptr, n, c, hw, flags)
+    _lib().ng_conv2d_stage_nhwc(out.ptr, buf.ptr, n, c, hw, B.math_flags())
     return (out, None) if channel_sums else out
 
 
@@ -650,8 +674,9 @@ def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding, want
         x_nhwc = None  # math mode changed between forward and backward: restage inside the call
     dy_nhwc = db = None
     db_out, db_tok = _param_out(ctx, 2, (weight.shape[0],)) if want_db else (None, None)
-    if need_dx and need_dw and d_tc and w_tc:
-        # one staging pass of dy serves dgrad and wgrad, and the bias gradient rides on its read
+    if (need_dx and need_dw and d_tc and w_tc) or (engine == 2 and ((need_dx and d_tc) or (need_dw and w_tc))):
+        # one staging pass of dy serves dgrad and wgrad, and the bias gradient rides on its read (FP16x3: staged
+        # here even for a single pass, so that a BatchNorm recipe upstream is fused into the staging)
         dy_nhwc, db = _stage_nhwc(grad_output, engine, channel_sums=True, sums_out=db_out) if want_db \
             else (_stage_nhwc(grad_output, engine), None)
     # wgrad first: it is what the data-parallel gradient arena is waiting for (dgrad only feeds this rank)
@@ -817,6 +842,8 @@ class MaxPool2d(Function):
         n, c, h, w, ph, pw = _pool_geometry(input.shape, pool_size)
         out = DeviceBuffer((n, c, h // ph, w // pw))
         _lib().ng_maxpool2d_fwd(out.ptr, input.ptr, n * c, h, w, ph, pw)
+        if getattr(input, "absmax", None) is not None:
+            out.absmax = input.absmax   # a window maximum never exceeds the tensor's largest magnitude
         ctx.save_for_backward(input, out, (ph, pw))
         return out
 
@@ -837,6 +864,8 @@ class AvgPool2d(Function):
         n, c, h, w, ph, pw = _pool_geometry(input.shape, pool_size)
         out = DeviceBuffer((n, c, h // ph, w // pw))
         _lib().ng_avgpool2d_fwd(out.ptr, input.ptr, n * c, h, w, ph, pw)
+        if getattr(input, "absmax", None) is not None:
+            out.absmax = input.absmax   # nor does a window mean
         ctx.save_for_backward(input.shape, (ph, pw))
         return out
 
@@ -984,6 +1013,16 @@ class Swish(Function):
         return dx, dbeta
 
 
+def _bn_split_ok(shape):
+    """Run BatchNorm2d as statistics now + element-wise pass on demand (LazyBuffer)?  Only when a consumer
+    could fuse the element-wise pass: the FP16x3 convolution engine is enabled, the channel count is one it
+    takes, the tensor is image-shaped, and BatchNorm is not synchronised across ranks (whose one-call kernels
+    carry the collectives).  (Under the host emulation of the CPU test-suite no convolution fuses, so every
+    LazyBuffer is materialised: the split kernels are exercised against the golden vectors there too.)"""
+    return (len(shape) == 4 and shape[1] % 64 == 0 and (B.math_flags() & B.F_F16X3) != 0
+            and not _dist.sync_bn())
+
+
 class BatchNorm2d(Function):
     """nn.BatchNorm2d.forward fused (module.py:356-391).  ``running_mean`` / ``running_var`` are
     raw buffers updated in place in training mode; parents are (x, gamma, beta).  ``relu=True``
@@ -995,15 +1034,28 @@ class BatchNorm2d(Function):
                 training=True, relu=False):
         n, c = input.shape[0], input.shape[1]
         hw = _numel(input.shape[2:])
-        out = DeviceBuffer(input.shape)
         act = 1 if relu else 0
         if training:
             save_mean, save_invstd = DeviceBuffer((c,)), DeviceBuffer((c,))
-            _lib().ng_bn2d_act_fwd_train(out.ptr, input.ptr, gamma.ptr, beta.ptr,
-                                         running_mean.ptr if running_mean is not None else 0,
-                                         running_var.ptr if running_var is not None else 0,
-                                         save_mean.ptr, save_invstd.ptr, n, c, hw, float(eps), float(momentum), act)
+            rm = running_mean.ptr if running_mean is not None else 0
+            rv = running_var.ptr if running_var is not None else 0
+            if _bn_split_ok(input.shape):
+                # statistics now; the normalise pass only if somebody other than an FP16x3 convolution reads y
+                absmax = DeviceBuffer((1,))
+                _lib().ng_bn2d_act_fwd_stats(input.ptr, gamma.ptr, beta.ptr, rm, rv, save_mean.ptr, save_invstd.ptr,
+                                             absmax.ptr, n, c, hw, float(eps), float(momentum), act)
+
+                def apply(ptr, x=input):
+                    _lib().ng_bn2d_act_apply(ptr, x.ptr, gamma.ptr, beta.ptr, save_mean.ptr, save_invstd.ptr, n, c, hw, act)
+
+                out = LazyBuffer(input.shape, apply, "bn_fwd", (input, gamma, beta, save_mean, save_invstd, act, absmax))
+                out.absmax = absmax
+            else:
+                out = DeviceBuffer(input.shape)
+                _lib().ng_bn2d_act_fwd_train(out.ptr, input.ptr, gamma.ptr, beta.ptr, rm, rv,
+                                             save_mean.ptr, save_invstd.ptr, n, c, hw, float(eps), float(momentum), act)
         else:
+            out = DeviceBuffer(input.shape)
             _lib().ng_bn2d_act_fwd_eval(out.ptr, input.ptr, gamma.ptr, beta.ptr, running_mean.ptr, running_var.ptr,
                                         n, c, hw, float(eps), act)
             # evaluation mode treats the running statistics as constants
@@ -1018,10 +1070,24 @@ class BatchNorm2d(Function):
         n, c = input.shape[0], input.shape[1]
         hw = _numel(input.shape[2:])
         if training:
-            dx = DeviceBuffer(input.shape)
             (dgamma, tok_g), (dbeta, tok_b) = _param_out(ctx, 1, (c,)), _param_out(ctx, 2, (c,))
-            _lib().ng_bn2d_act_bwd(dx.ptr, dgamma.ptr, dbeta.ptr, grad_output.ptr, input.ptr, gamma.ptr, beta.ptr,
-                                   save_mean.ptr, save_invstd.ptr, n, c, hw, act)
+            if _bn_split_ok(input.shape) and _needs(ctx, 0):
+                # reductions now; the dx pass only if somebody other than an FP16x3 convolution reads dx
+                bn_sums, bound = DeviceBuffer((2 * c + 1,)), DeviceBuffer((1,))
+                _lib().ng_bn2d_act_bwd_sums(dgamma.ptr, dbeta.ptr, bn_sums.ptr, bound.ptr, grad_output.ptr, input.ptr,
+                                            gamma.ptr, beta.ptr, save_mean.ptr, save_invstd.ptr, n, c, hw, act)
+
+                def dx_pass(ptr, dy=grad_output, x=input):
+                    _lib().ng_bn2d_act_bwd_dx(ptr, dy.ptr, x.ptr, gamma.ptr, beta.ptr, save_mean.ptr, save_invstd.ptr,
+                                              bn_sums.ptr, n, c, hw, act)
+
+                dx = LazyBuffer(input.shape, dx_pass, "bn_bwd",
+                                (grad_output, input, gamma, beta, save_mean, save_invstd, bn_sums, act, bound))
+                dx.absmax = bound
+            else:
+                dx = DeviceBuffer(input.shape)
+                _lib().ng_bn2d_act_bwd(dx.ptr, dgamma.ptr, dbeta.ptr, grad_output.ptr, input.ptr, gamma.ptr, beta.ptr,
+                                       save_mean.ptr, save_invstd.ptr, n, c, hw, act)
             _dist.grad_slot_filled(tok_g)
             _dist.grad_slot_filled(tok_b)
             return dx, dgamma, dbeta

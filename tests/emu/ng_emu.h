@@ -114,6 +114,13 @@ inline float __shfl_down_sync(unsigned, float v, int delta) {
 }
 inline float __shfl_sync(unsigned, float v, int src) { return ng_emu::shfl(v, src & 31); }
 inline float __ldg(const float* p) { return *p; }
+inline unsigned int __float_as_uint(float v) { unsigned int u; memcpy(&u, &v, 4); return u; }
+inline float __uint_as_float(unsigned int u) { float v; memcpy(&v, &u, 4); return v; }
+inline unsigned int atomicMax(unsigned int* p, unsigned int v) {   // CUDA threads are host threads here
+  unsigned int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
 inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __expf(float x) { return expf(x); }

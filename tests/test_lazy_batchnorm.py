@@ -1,0 +1,163 @@
+"""BatchNorm2d as "statistics now, element-wise pass on demand" (nn/buffer.py LazyBuffer).
+
+In a conv -> BatchNorm2d -> ReLU -> conv chain the normalised activation (and, in the backward, BatchNorm's input
+gradient) is read by nobody but the staging pass of the next convolution's FP16x3 tensor-core operands, so the
+op returns a recipe and the convolution stages straight from it (ng_conv2d_stage_f16_bn / _bnbwd).  Checked here:
+  * a recipe that IS materialised (pooling, numpy(), any generic op reads .ptr) is bit-identical to the one-call
+    kernels (module.py:356-391's values) — also under the host emulation of the CPU suite;
+  * the magnitudes the statistics passes report bound the tensors they describe (exactly, for the forward);
+  * the fused staging copies equal the staging copy of the materialised tensor to the 2^-21 of the FP16 pairs,
+    the channel sums (conv bias gradient, module.py:476) included.
+Whole-model parity of the fused path: the vgg_w64_* cases of tests/test_device_parity.py (fp32 and f16x3 modes).
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+def _setup(n, c, h, w, seed):
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    rng = np.random.RandomState(seed)
+    x = (rng.randn(n, c, h, w) * rng.uniform(0.2, 3.0, (1, c, 1, 1)) + rng.uniform(-2, 2, (1, c, 1, 1))).astype(np.float32)
+    gamma = rng.uniform(-1.5, 1.5, c).astype(np.float32)
+    beta = rng.uniform(-0.5, 0.5, c).astype(np.float32)
+    dy = (rng.randn(n, c, h, w) * np.exp(rng.randn(n, c, h, w))).astype(np.float32)
+    dev = {k: DeviceBuffer(v.shape, hostbuf=v) for k, v in dict(x=x, gamma=gamma, beta=beta, dy=dy).items()}
+    return dict(x=x, gamma=gamma, beta=beta, dy=dy), dev
+
+
+def _one_call_and_split(lib, dev, n, c, hw, act):
+    """(y, mean, invstd, dx, dgamma, dbeta) from the one-call kernels and from the split kernels."""
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    B = lambda *s: DeviceBuffer(s)
+    y1, m1, i1, dx1, dg1, db1 = B(n, c, hw), B(c), B(c), B(n, c, hw), B(c), B(c)
+    lib.ng_bn2d_act_fwd_train(y1.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, m1.ptr, i1.ptr, n, c, hw,
+                              1e-5, 0.1, act)
+    lib.ng_bn2d_act_bwd(dx1.ptr, dg1.ptr, db1.ptr, dev["dy"].ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr,
+                        m1.ptr, i1.ptr, n, c, hw, act)
+    y2, m2, i2, dx2, dg2, db2 = B(n, c, hw), B(c), B(c), B(n, c, hw), B(c), B(c)
+    absmax, sums, bound = B(1), B(2 * c + 1), B(1)
+    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, m2.ptr, i2.ptr, absmax.ptr, n, c, hw,
+                              1e-5, 0.1, act)
+    lib.ng_bn2d_act_apply(y2.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, m2.ptr, i2.ptr, n, c, hw, act)
+    lib.ng_bn2d_act_bwd_sums(dg2.ptr, db2.ptr, sums.ptr, bound.ptr, dev["dy"].ptr, dev["x"].ptr, dev["gamma"].ptr,
+                             dev["beta"].ptr, m2.ptr, i2.ptr, n, c, hw, act)
+    lib.ng_bn2d_act_bwd_dx(dx2.ptr, dev["dy"].ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, m2.ptr, i2.ptr,
+                           sums.ptr, n, c, hw, act)
+    one = [b.numpy() for b in (y1, m1, i1, dx1, dg1, db1)]
+    split = [b.numpy() for b in (y2, m2, i2, dx2, dg2, db2)]
+    return one, split, (absmax, sums, bound, m2, i2)
+
+
+def _check_split(act, shape):
+    from nanograd_b200 import backend as B
+    n, c, h, w = shape
+    host, dev = _setup(n, c, h, w, seed=c + act)
+    one, split, (absmax, _, bound, _, _) = _one_call_and_split(B.lib(), dev, n, c, h * w, act)
+    for name, a, b in zip(("y", "mean", "invstd", "dx", "dgamma", "dbeta"), one, split):
+        H.assert_exact(b, a, f"{name} (split kernels vs one-call kernels, act={act})")
+    y, dx = one[0], one[3]
+    amax = float(absmax.numpy().view(np.float32)[0])
+    assert float(np.abs(y).max()) <= amax <= float(np.abs(y).max()) * 1.001 + 1e-30, (amax, float(np.abs(y).max()))
+    bnd = float(bound.numpy().view(np.float32)[0])
+    assert float(np.abs(dx).max()) <= bnd <= 16 * float(np.abs(dx).max()), (bnd, float(np.abs(dx).max()))
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_split_batchnorm_kernels_match_one_call_kernels_emulated(act):
+    H.use_emulated_library()
+    _check_split(act, (3, 8, 5, 4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("shape", [(3, 8, 5, 4), (16, 64, 16, 16), (7, 192, 9, 5), (64, 128, 32, 32)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_split_batchnorm_kernels_match_one_call_kernels(shape, act):
+    H.use_cuda_library()
+    _check_split(act, shape)
+
+
+def _decode(staged, n, c, hw):
+    raw = staged.numpy()
+    total = n * c * hw
+    inv_scale = float(raw[total])
+    halves = raw[:total].view(np.float16).reshape(n, hw, c // 64, 2, 64).astype(np.float64)
+    vals = (halves[:, :, :, 0, :] + halves[:, :, :, 1, :]).reshape(n, hw, c) * inv_scale
+    return vals.transpose(0, 2, 1), inv_scale   # [n][c][hw]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("shape", [(16, 64, 16, 16), (7, 192, 9, 5), (32, 128, 32, 32)], ids=lambda s: "x".join(map(str, s)))
+def test_fused_staging_equals_staging_of_the_materialised_tensor(shape, act):
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    H.use_cuda_library()
+    lib = B.lib()
+    n, c, h, w = shape
+    hw = h * w
+    host, dev = _setup(n, c, h, w, seed=7 * c + act)
+    one, _, (absmax, sums, bound, mean, invstd) = _one_call_and_split(lib, dev, n, c, hw, act)
+    y, dx = one[0].astype(np.float64), one[3].astype(np.float64)
+    staged = DeviceBuffer((n * c * hw + 16,))
+    lib.ng_conv2d_stage_f16_bn(staged.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, mean.ptr, invstd.ptr,
+                               absmax.ptr, n, c, hw, act)
+    got, inv_scale = _decode(staged, n, c, hw)
+    ymax = np.abs(y).max()
+    assert 2.0 ** 13 <= ymax / inv_scale < 2.0 ** 15, "scale puts the largest magnitude just under 2^15"
+    err = np.abs(got - y)
+    assert np.all(err <= np.maximum(np.abs(y) * 2.0 ** -21, ymax * 2.0 ** -38)), float(err.max() / ymax)
+
+    staged2, chan = DeviceBuffer((n * c * hw + 16,)), DeviceBuffer((c,))
+    lib.ng_conv2d_stage_f16_bnbwd(staged2.ptr, chan.ptr, dev["dy"].ptr, dev["x"].ptr, dev["gamma"].ptr,
+                                  dev["beta"].ptr if act else 0, mean.ptr, invstd.ptr, sums.ptr, bound.ptr, n, c, hw, act)
+    got, inv_scale = _decode(staged2, n, c, hw)
+    dmax = np.abs(dx).max()
+    assert 2.0 ** 10 <= dmax / inv_scale < 2.0 ** 15, "the bound costs at most a few binades of FP16 range"
+    # (the fused kernel re-evaluates k0 (dy - k1 - (x - mean) k2) in float32: where the terms cancel, the two
+    #  evaluations may contract their multiply-adds differently, hence the absolute floor of 2^-20 max|dx|)
+    err = np.abs(got - dx)
+    assert np.all(err <= np.maximum(np.abs(dx) * 2.0 ** -21, dmax * 2.0 ** -20)), float(err.max() / dmax)
+    # (the channel sums of BatchNorm's dx vanish analytically: compare on the scale of sum |dx|)
+    np.testing.assert_allclose(chan.numpy(), dx.sum(axis=(0, 2)), rtol=0, atol=1e-5 * float(np.abs(dx).sum(axis=(0, 2)).max()),
+                               err_msg="channel sums of the fused dx staging")
+
+
+@pytest.mark.gpu
+def test_lazy_outputs_are_only_written_when_somebody_reads_them():
+    """conv -> BatchNorm2d -> ReLU -> conv on the FP16x3 engine: the normalised activation and BatchNorm's input
+    gradient stay recipes (never allocated); a max-pool consumer materialises its input."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.device import Device
+    from nanograd_b200.nn.buffer import LazyBuffer
+    import nanograd_b200.nn.module as nn
+    from nanograd_b200.tensor import Tensor
+    H.use_cuda_library()
+    B.set_math_mode("f16x3")
+    try:
+        np.random.seed(3)
+        c1, bn, c2, pool = nn.Conv2d(64, 64, 3, 1, 1), nn.BatchNorm2d(64), nn.Conv2d(64, 128, 3, 1, 1), nn.MaxPool2d(2)
+        for m in (c1, bn, c2):
+            m.gpu()
+        x = Tensor(np.random.randn(4, 64, 8, 8).astype(np.float32), device=Device.GPU)
+        a = c1(x)
+        z = bn.forward(a, relu=True)
+        assert isinstance(z.data, LazyBuffer) and z.data.pending
+        y = c2(z)
+        assert z.data.pending, "the second convolution staged its operand from the recipe"
+        p = pool(y)
+        loss = (p * p).sum()
+        loss.backward()
+        assert isinstance(a.grad.data, LazyBuffer) and a.grad.data.pending, "dx of BatchNorm stayed a recipe"
+        assert z.data.pending
+        # reading the values materialises them, and they are BatchNorm + ReLU of a
+        zv, av = z.numpy(), a.numpy().astype(np.float64)
+        mu, var = av.mean(axis=(0, 2, 3), keepdims=True), av.var(axis=(0, 2, 3), keepdims=True)
+        want = np.maximum((av - mu) / np.sqrt(var + 1e-5) * bn.weight.numpy().reshape(1, -1, 1, 1)
+                          + bn.bias.numpy().reshape(1, -1, 1, 1), 0)
+        H.assert_close(zv, want, H.RTOL_FP32, "materialised BatchNorm + ReLU output")
+        assert not z.data.pending
+    finally:
+        B.set_math_mode("fp32")
