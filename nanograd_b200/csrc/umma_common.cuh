@@ -101,6 +101,63 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// ---------------------------------------------------------------- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Wait on a barrier whose arrivals come from other CTAs of the cluster (multicast tcgen05.commit).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, volatile uint32_t* dbg = nullptr,
+                                                  uint32_t who = 0) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 24)) {
+      if (dbg) {
+        dbg[0] = 0xDEAD0000u | who;
+        dbg[1] = parity;
+        dbg[2] = smem_u32(bar);
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+// TMA box delivered to the same shared-memory offset (and signalling the barrier at the same offset) of every
+// CTA of the cluster whose rank bit is set in `mask`.
+__device__ __forceinline__ void tma_load_5d_multicast(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                                      int c1, int c2, int c3, int c4, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_multicast(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                                      int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "h"(mask)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM allocation
 // Executed by one full warp.  The base address (lane 0, first column) lands in *smem_dst.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -190,6 +247,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// The same arrive delivered to the barrier at this offset in every CTA of the cluster whose rank bit is in `mask`.
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
 

@@ -660,9 +660,18 @@ struct WgradF16P {
   int pad_t, pad_l;
   uint32_t idesc_all, idesc_g, stage_b_bytes, tmem_cols;
   int stages;
+  int ct, cn;   // thread-block cluster = ct tap groups x cn output-channel tiles of the same pixels
   uint32_t* dbg;
 };
 
+// CL (thread-block clusters, experiment: see conv_wgrad_f16): the kernel streams both operands with no reuse inside
+// a CTA, 32 KB per 32-pixel chunk for 384 tensor cycles, and every (tap group, k tile) CTA of the same pixels
+// re-reads the same x / dy chunks from L2 (18x redundancy at 256 -> 256 channels).  The ct x cn CTAs of a cluster
+// work on the same chunk at the same time: the x chunk of a tap group is multicast to the cn CTAs of its k tiles
+// and the dy chunk of a k tile to the ct CTAs of its tap groups (the issuing CTA rotates with the chunk), which
+// divides the L2 reads by up to ct*cn/(ct+cn).  A slot is refilled only after every CTA of the cluster released
+// it (tcgen05.commit multicast to all their empty barriers).
+template <bool CL>
 __global__ void __launch_bounds__(WF_THREADS, 1) umma_conv_wgrad_f16_kernel(const __grid_constant__ WgradF16P p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -679,7 +688,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) umma_conv_wgrad_f16_kernel(cons
     tma_prefetch_desc(&p.tm_dy);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL ? (uint32_t)(p.ct * p.cn) : 1u);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
@@ -693,15 +702,20 @@ __global__ void __launch_bounds__(WF_THREADS, 1) umma_conv_wgrad_f16_kernel(cons
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();   // every CTA's barriers exist before a neighbour signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_cols = 2u * (uint32_t)p.n_tile;
 
-  int item = blockIdx.x;
+  // work item: cluster = (split, k-tile group, c tile, tap-group cluster); rank inside = (ci, cj)
+  const int csize = CL ? p.ct * p.cn : 1;
+  const int rank = CL ? (int)cluster_ctarank() : 0;
+  const int ci = rank % p.ct, cj = rank / p.ct;
+  int item = blockIdx.x / csize;
   const int split = item % p.splits; item /= p.splits;
-  const int n_t = item % p.n_tiles; item /= p.n_tiles;
+  const int n_t = (item % (p.n_tiles / p.cn)) * p.cn + cj; item /= (p.n_tiles / p.cn);
   const int c_t = item % p.c_tiles;
-  const int tg = item / p.c_tiles;
+  const int tg = (item / p.c_tiles) * p.ct + ci;
   const int chunk_begin = split * p.chunks_per_split;
   int chunk_end = chunk_begin + p.chunks_per_split;
   if (chunk_end > p.total_chunks) chunk_end = p.total_chunks;
@@ -732,16 +746,38 @@ __global__ void __launch_bounds__(WF_THREADS, 1) umma_conv_wgrad_f16_kernel(cons
       }
       const uint32_t tx_bytes = (uint32_t)n_taps * tap_bytes + p.stage_b_bytes;
       const int xg0 = c_t * blocks_per_tap, yg0 = n_t * 2 * p.ng;
+      // cluster ranks that share this CTA's x chunk (same tap group ci) / dy chunk (same k tile cj)
+      uint16_t mask_x = 0, mask_dy = 0;
+      if (CL) {
+        for (int j = 0; j < p.cn; ++j) mask_x |= (uint16_t)(1u << (ci + p.ct * j));
+        mask_dy = (uint16_t)(((1u << p.ct) - 1u) << (p.ct * cj));
+      }
+      int xi = pid % p.cn, yi = pid % p.ct;   // whose turn it is to issue chunk i: i % cn, i % ct (stepped)
+      const int xstep = 2 % p.cn, ystep = 2 % p.ct;
       for (int i = pid; i < n_chunks; i += 2) {
         const int ow0 = cw * p.w_c, oh0 = chh * p.rows_c;
-        mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
+        if (CL) mbar_wait_cluster(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
+        else mbar_wait(&empty_bar[s], ph ^ 1u, p.dbg, 0x100u + s);
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        if (CL) {
+          if (xi == cj) {
 #pragma unroll
-        for (int tl = 0; tl < 2; ++tl)
-          if (tl < n_taps)
-            tma_load_5d(sa + (size_t)tl * tap_bytes, &p.tm_x, &full_bar[s], 0, ow0 + tdx[tl], oh0 + tdy[tl], xg0, img);
-        tma_load_5d(sa + WF_A_BYTES, &p.tm_dy, &full_bar[s], 0, ow0, oh0, yg0, img);
+            for (int tl = 0; tl < 2; ++tl)
+              if (tl < n_taps)
+                tma_load_5d_multicast(sa + (size_t)tl * tap_bytes, &p.tm_x, &full_bar[s], 0, ow0 + tdx[tl], oh0 + tdy[tl],
+                                      xg0, img, mask_x);
+          }
+          if (yi == ci) tma_load_5d_multicast(sa + WF_A_BYTES, &p.tm_dy, &full_bar[s], 0, ow0, oh0, yg0, img, mask_dy);
+          xi += xstep; if (xi >= p.cn) xi -= p.cn;
+          yi += ystep; if (yi >= p.ct) yi -= p.ct;
+        } else {
+#pragma unroll
+          for (int tl = 0; tl < 2; ++tl)
+            if (tl < n_taps)
+              tma_load_5d(sa + (size_t)tl * tap_bytes, &p.tm_x, &full_bar[s], 0, ow0 + tdx[tl], oh0 + tdy[tl], xg0, img);
+          tma_load_5d(sa + WF_A_BYTES, &p.tm_dy, &full_bar[s], 0, ow0, oh0, yg0, img);
+        }
         s += 2;
         if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
         cw += 2;
@@ -778,7 +814,8 @@ __global__ void __launch_bounds__(WF_THREADS, 1) umma_conv_wgrad_f16_kernel(cons
             if (p.ng == 2)
               mma_f16(d_tmem + 128u, desc64(a_lo + 128u * k, dhi), desc64(b_h1 + 128u * k, dhi), p.idesc_g, 1u);
           }
-          mma_commit(&empty_bar[s]);
+          if (CL) mma_commit_multicast(&empty_bar[s], (uint16_t)((1u << (p.ct * p.cn)) - 1u));
+          else mma_commit(&empty_bar[s]);
         }
         accumulate = 1u;
         __syncwarp();
@@ -833,6 +870,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) umma_conv_wgrad_f16_kernel(cons
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();   // no CTA leaves while a neighbour may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -879,6 +917,21 @@ int conv_wgrad_f16(float* dw, const void* dyv, const void* x, int N, int C, int 
   p.chunks_w = (int)ceil_div(OW, w_c);
   p.chunks_h = (int)ceil_div(OH, p.rows_c);
   p.total_chunks = N * p.chunks_h * p.chunks_w;
+  // cluster shape: ct = the largest divisor (<= 8) of the tap-group count, cn = 2 k tiles when that still fits.
+  // MEASURED (B200, config-2 layers): correct, and 1.5-1.6x SLOWER than independent CTAs (64->64@32^2: 506 vs 335 us,
+  // 256->256@8^2: 259 vs 164 us, staging included): the lock-step of 5-6 CTAs on every stage costs more than the
+  // multicast saves, and the per-SM TMA ingest rate (~45 B/clk/SM, tools/tma_bw.cu) is the same either way.
+  // Kept behind NG_WGRAD_CLUSTER=1 as the record of the experiment; off by default.
+  p.ct = 1;
+  p.cn = 1;
+  {
+    const char* e = getenv("NG_WGRAD_CLUSTER");
+    if (e && atoi(e) != 0) {
+      for (int d = 8; d >= 2; --d)
+        if (p.tap_groups % d == 0) { p.ct = d; break; }
+      if (p.n_tiles % 2 == 0 && p.ct * 2 <= 8) p.cn = 2;
+    }
+  }
   const int items = p.tap_groups * p.c_tiles * p.n_tiles;
   const int sms = g_sm_count > 0 ? g_sm_count : 148;
   int splits = sms / items;
@@ -925,8 +978,11 @@ int conv_wgrad_f16(float* dw, const void* dyv, const void* x, int N, int C, int 
   if (rc == 0) {
     static bool configured = false;
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(umma_conv_wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(umma_conv_wgrad_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(227 * 1024));
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(umma_conv_wgrad_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(227 * 1024));
       if (e != cudaSuccess) rc = set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       configured = (e == cudaSuccess);
     }
@@ -937,10 +993,30 @@ int conv_wgrad_f16(float* dw, const void* dyv, const void* x, int N, int C, int 
     bool debug;
     p.dbg = debug_words(&debug);
     if (debug)
-      fprintf(stderr, "[umma f16] wgrad: grid %d items %d splits %d chunks %d/split Cm %d taps/cta %d n_tile %d stages %d w_c %d rows_c %d\n",
-              grid, items, splits, p.chunks_per_split, p.Cm, p.taps_per_cta, p.n_tile, stages, w_c, p.rows_c);
-    NG_LAUNCH(umma_conv_wgrad_f16_kernel, grid, WF_THREADS, smem_bytes, p);
-    cudaError_t e = cudaGetLastError();
+      fprintf(stderr, "[umma f16] wgrad: grid %d items %d splits %d chunks %d/split Cm %d taps/cta %d n_tile %d stages %d w_c %d rows_c %d cluster %dx%d\n",
+              grid, items, splits, p.chunks_per_split, p.Cm, p.taps_per_cta, p.n_tile, stages, w_c, p.rows_c, p.ct, p.cn);
+    cudaError_t e;
+    if (p.ct * p.cn > 1) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(WF_THREADS);
+      cfg.dynamicSmemBytes = smem_bytes;
+      cfg.stream = g_stream;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = (unsigned)(p.ct * p.cn);
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, umma_conv_wgrad_f16_kernel<true>, p);
+      g_launches++;
+      if (e == cudaSuccess) e = cudaGetLastError();
+    } else {
+      NG_LAUNCH(umma_conv_wgrad_f16_kernel<false>, grid, WF_THREADS, smem_bytes, p);
+      e = cudaGetLastError();
+    }
     if (e != cudaSuccess) rc = set_error("umma_conv_wgrad_f16_kernel launch failed: %s", cudaGetErrorString(e));
     if (debug) {
       cudaError_t e2 = cudaStreamSynchronize(g_stream);
