@@ -78,9 +78,13 @@ int ng_event_destroy(uint64_t ev);
 int ng_flush_l2(void);
 /* FFMA-saturating microkernel: measured FP32 SIMT peak (TFLOP/s) for the roofline */
 int ng_measure_ffma_peak(int iters, float* out_tflops);
-/* per-kernel-class CUDA-event timing of the contraction kernels on the compute stream
- * (bench.py's roofline object).  total_ms / launches / algorithmic flops and bytes per class. */
-enum { NG_PROF_CONV_FPROP = 0, NG_PROF_CONV_DGRAD = 1, NG_PROF_CONV_WGRAD = 2, NG_PROF_GEMM = 3 };
+/* per-kernel-class CUDA-event timing on the compute stream (bench.py's roofline objects): total_ms /
+ * calls / algorithmic flops and bytes per class.  Contractions: classes 0-3.  Memory-bound classes:
+ * STAGE = the channels-last staging passes of the tensor-core operands (with whatever is fused into them),
+ * BN = BatchNorm statistics / normalise / backward passes, POOL = pooling forward / backward, OPTIM = the
+ * multi-tensor optimizer step. */
+enum { NG_PROF_CONV_FPROP = 0, NG_PROF_CONV_DGRAD = 1, NG_PROF_CONV_WGRAD = 2, NG_PROF_GEMM = 3,
+       NG_PROF_STAGE = 4, NG_PROF_BN = 5, NG_PROF_POOL = 6, NG_PROF_OPTIM = 7 };
 int ng_prof_enable(int on);
 int ng_prof_reset(void);
 int ng_prof_read(int kernel_class, double* total_ms, int64_t* launches, double* flops, double* bytes);

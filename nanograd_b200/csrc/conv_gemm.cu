@@ -1086,6 +1086,7 @@ int ng_conv2d_tc_plan(int N, int C, int H, int W, int K, int R, int S, int strid
 
 int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64_t HW, int flags) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_STAGE, 0.0, 8.0 * (double)N * C * HW);
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL, "ng_conv2d_stage_nhwc: bad dimensions");
   if (flags & NG_F_STAGE_F16)
@@ -1099,6 +1100,7 @@ int ng_conv2d_stage_nhwc(uint64_t dst, uint64_t src, int64_t N, int64_t C, int64
 
 int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t N, int64_t C, int64_t HW, int flags) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_STAGE, 0.0, 8.0 * (double)N * C * HW);
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL && N <= 65535, "ng_conv2d_stage_nhwc_sum: bad dimensions");
   if (flags & NG_F_STAGE_F16)
@@ -1113,6 +1115,7 @@ int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t 
 
 int ng_conv2d_stage_f16(uint64_t dst, uint64_t src, uint64_t sums, uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_STAGE, 0.0, 8.0 * (double)N * C * HW);
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL && (sums == 0 || N <= 65535),
              "ng_conv2d_stage_f16: bad dimensions");
@@ -1127,6 +1130,7 @@ int ng_conv2d_stage_f16(uint64_t dst, uint64_t src, uint64_t sums, uint64_t absm
 int ng_conv2d_stage_f16_bn(uint64_t dst, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd,
                            uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW, int act) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_STAGE, 0.0, 8.0 * (double)N * C * HW);
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL, "ng_conv2d_stage_f16_bn: bad dimensions");
   NG_REQUIRE(absmax_bits != 0 && (act == 0 || act == 1), "ng_conv2d_stage_f16_bn: absmax_bits required, act 0 or 1");
@@ -1143,6 +1147,7 @@ int ng_conv2d_stage_f16_bnbwd(uint64_t dst, uint64_t chan_sums, uint64_t dy, uin
                               uint64_t mean, uint64_t invstd, uint64_t bn_sums, uint64_t bound_bits, int64_t N, int64_t C,
                               int64_t HW, int act) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_STAGE, 0.0, 12.0 * (double)N * C * HW);
 #ifndef NG_EMU
   NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C * HW < 2147483647LL && (chan_sums == 0 || N <= 65535),
              "ng_conv2d_stage_f16_bnbwd: bad dimensions");
@@ -1344,7 +1349,13 @@ int ng_gemm(uint64_t c, uint64_t a, uint64_t b, int64_t M, int64_t N, int64_t K,
              "ng_gemm: dimension too large");
   if (M == 0 || N == 0) return 0;
 #ifndef NG_EMU
-  if (batch == 1 && K > 0 && conv_engine(flags & ~NG_F_F16X3, 2.0 * (double)M * N * K, 0, 0, 0, 1) == 1) {
+  // tensor-core GEMM: TF32 mode always; FP32-accurate modes (3xTF32) from 30 MFLOP up — below ~0.2 GFLOP both engines
+  // are latency-bound, but the SIMT kernel's 128 x 128 tiles leave a 512 x 256 output on 8 of 148 SMs (measured
+  // 512 x 256 x 256: 50 us SIMT, 14.5 us tensor core, the q / k / v projections of BASELINE configs[3])
+  const double gflops = 2.0 * (double)M * N * K;
+  const bool gemm_tc = (flags & NG_F_TF32) ||
+                       ((flags & (NG_F_TF32X3 | NG_F_F16X3)) && ((flags & NG_F_TC_FORCE) || gflops >= 3.0e7));
+  if (batch == 1 && K > 0 && gemm_tc) {
     const int tok = prof_begin(NG_PROF_GEMM, 2.0 * (double)M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N));
     const int rc = umma::gemm_tf32(dptr<float>(c), dptr<const float>(a), dptr<const float>(b),
                                    bias ? dptr<const float>(bias) : nullptr, M, N, K, trans_a, trans_b,

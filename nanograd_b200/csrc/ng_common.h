@@ -41,6 +41,15 @@ int dp_allgather_inline(const float* send, float* recv, int64_t count_per_rank);
 int prof_begin(int cls, double flops, double bytes);
 void prof_end(int token);
 
+// prof_begin / prof_end around a C-ABI call, early returns included
+struct ProfScope {
+  int tok;
+  ProfScope(int cls, double flops, double bytes) : tok(prof_begin(cls, flops, bytes)) {}
+  ~ProfScope() { prof_end(tok); }
+  ProfScope(const ProfScope&) = delete;
+  ProfScope& operator=(const ProfScope&) = delete;
+};
+
 template <typename T>
 static inline T* dptr(uint64_t p) { return reinterpret_cast<T*>(static_cast<uintptr_t>(p)); }
 

@@ -152,6 +152,9 @@ extern "C" {
 int ng_multi_sgd(int count, const uint64_t* params, const uint64_t* grads, const uint64_t* moms,
                  const int64_t* numels, float lr, float momentum, float grad_scale) {
   NG_ENSURE_INIT();
+  double prof_elems_ = 0.0;
+  for (int i = 0; i < count; ++i) prof_elems_ += (double)numels[i];
+  ProfScope prof_(NG_PROF_OPTIM, 0.0, (momentum != 0.f ? 20.0 : 12.0) * prof_elems_);
   SgdH h{lr, momentum, grad_scale};
   for (int base = 0; base < count; base += kMT) {
     const int c = (count - base < kMT) ? count - base : kMT;
@@ -175,6 +178,9 @@ int ng_multi_adam(int count, const uint64_t* params, const uint64_t* grads, cons
                   const uint64_t* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2, float eps,
                   float bc1, float bc2, float weight_decay, int adamw, float grad_scale) {
   NG_ENSURE_INIT();
+  double prof_elems_ = 0.0;
+  for (int i = 0; i < count; ++i) prof_elems_ += (double)numels[i];
+  ProfScope prof_(NG_PROF_OPTIM, 0.0, 28.0 * prof_elems_);
   AdamH h;
   h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.bc1 = bc1; h.bc2 = bc2;
   h.decay_mul = 1.f - lr * weight_decay;

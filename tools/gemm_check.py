@@ -12,7 +12,8 @@ def t(fn, iters=20):
     e1.record(); e1.synchronize()
     return e0.elapsed_ms(e1) / iters
 perf = "--perf" in sys.argv
-shapes = [(512, 256, 4096), (512, 4096, 256), (256, 4096, 512), (128, 64, 96), (37 * 4, 96, 132), (512, 10, 256),
+shapes = [(512, 256, 256), (512, 512, 256), (512, 256, 512), (256, 256, 512), (512, 256, 4096), (512, 4096, 256),
+          (256, 4096, 512), (128, 64, 96), (37 * 4, 96, 132), (512, 10, 256),
           (512, 512, 512), (4096, 4096, 4096)] if perf else \
          [(16, 32, 2048), (16, 2048, 32), (32, 2048, 16), (16, 10, 32), (16, 32, 1024), (16, 1024, 32), (32, 1024, 16), (512, 256, 4096), (512, 4096, 256), (256, 4096, 512), (128, 64, 96), (148, 96, 132), (512, 10, 256), (64, 32, 32), (300, 160, 1000)]
 rng = np.random.RandomState(0)
