@@ -487,8 +487,10 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     B.sync()
     launches0 = B.launch_count()
     e0, e1 = B.Event().record(), B.Event()
+    h0 = time.perf_counter()
     for _ in range(K):
         loss = train_step(model, opt, crit, x_res, y_res)
+    host_ms_per_step = (time.perf_counter() - h0) * 1e3 / K   # Python + ctypes + launch time (no sync inside)
     e1.record()
     e1.synchronize()
     B.sync()
@@ -548,7 +550,7 @@ def measure_training(args, B, dist, lib, math_mode, with_clocks):
     B.set_math_mode("fp32")
     return {"value": value, "ms_per_step": ms_per_step, "e2e_value": e2e_value, "e2e_ms": e2e_ms,
             "h2d": int(Xh.nbytes + Yh.nbytes), "launches": int(launches), "loss": loss_value, "prof": prof,
-            "profiled_ms_per_step": profiled_ms_per_step,
+            "profiled_ms_per_step": profiled_ms_per_step, "host_ms_per_step": host_ms_per_step,
             "ffma_peak": float(ffma_peak.value), "clocks": clocks.summary() if clocks else None,
             "n_params": n_params, "K": K, "W": W, "batch": batch, "replica_checksum": checksum}
 
@@ -781,6 +783,7 @@ def run_device_arm(args):
         "e2e": {"value": round(m["e2e_value"], 1), "unit": "images/s", "ms_per_step": round(m["e2e_ms"], 4),
                 "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4},
         "gpu_launches": m["launches"], "launches_per_step": m["launches"] / K, "loss": m["loss"],
+        "host_ms_per_step": round(m["host_ms_per_step"], 4),
         "replica_checksum": m["replica_checksum"],
         "clocks": m["clocks"], "roofline": roofline_object(m, main_mode, peaks, peak_src, m["clocks"]),
     }

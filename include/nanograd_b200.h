@@ -231,6 +231,14 @@ int ng_maxpool2d_bwd(uint64_t dx, uint64_t dy, uint64_t x, uint64_t y,
                      int64_t NC, int H, int W, int ph, int pw);
 int ng_avgpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, int pw);
 int ng_avgpool2d_bwd(uint64_t dx, uint64_t dy, int64_t NC, int H, int W, int ph, int pw);
+/* Max pooling of y = act(BatchNorm2d(x)) that was never written (statistics from ng_bn2d_act_fwd_stats): x is the
+ * BatchNorm INPUT, every value read is normalised on the fly (C channels, NC = N*C planes); maxima and tie masks
+ * are bit-identical to pooling the materialised y.  Removes the write and the re-read of y in
+ * conv -> BatchNorm2d -> ReLU -> MaxPool2d chains. */
+int ng_maxpool2d_fwd_bn(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd,
+                        int64_t NC, int C, int H, int W, int ph, int pw, int act);
+int ng_maxpool2d_bwd_bn(uint64_t dx, uint64_t dy, uint64_t x, uint64_t y, uint64_t gamma, uint64_t beta, uint64_t mean,
+                        uint64_t invstd, int64_t NC, int C, int H, int W, int ph, int pw, int act);
 
 /* ----------------------------------------------------------------- loss head ------- */
 /* fused Tensor.log_softmax (tensor.py:327-331, nine primitive nodes in the reference) */

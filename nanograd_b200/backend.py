@@ -72,6 +72,8 @@ _PROTOTYPES = {
     "ng_conv2d_tc_plan": [i32] * 11 + [POINTER(c_int)],
     "ng_conv2d_stage_nhwc": [u64, u64, i64, i64, i64, i32],
     "ng_conv2d_stage_nhwc_sum": [u64, u64, u64, i64, i64, i64, i32],
+    "ng_maxpool2d_fwd_bn": [u64] * 6 + [i64, i32, i32, i32, i32, i32, i32],
+    "ng_maxpool2d_bwd_bn": [u64] * 8 + [i64, i32, i32, i32, i32, i32, i32],
     "ng_conv2d_stage_f16": [u64, u64, u64, u64, i64, i64, i64],
     "ng_conv2d_stage_f16_bn": [u64] * 7 + [i64, i64, i64, i32],
     "ng_conv2d_stage_f16_bnbwd": [u64] * 10 + [i64, i64, i64, i32],

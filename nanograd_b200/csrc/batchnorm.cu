@@ -28,6 +28,90 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
   return warp_max(t);
 }
 
+// Per-channel fold of the split partials, shared by the stand-alone finalize kernels (synchronised BatchNorm keeps
+// a collective between the reduction and the fold) and by the LAST block of a channel inside bn_reduce_kernel
+// (single process: the fold rides on the reduction launch; 12 launches of 5-8 us each per training step were
+// nothing but this fold).  Partials are read with ld.global.cg: they were written by other blocks.
+struct BnFin {
+  unsigned int* counter;   // [C] arrival counters, zero between launches; null = no fused fold
+  int S, PS, act;
+  float count, eps, momentum;
+  const float* gamma;
+  const float* beta;
+  unsigned int* bits;      // forward: bits of max|y|; backward: bits of a bound of max|dx| (null: not wanted)
+  float* save_mean;        // forward
+  float* save_invstd;
+  float* running_mean;
+  float* running_var;
+  const float* invstd;     // backward
+  float* dgamma;
+  float* dbeta;
+  float* sums;
+};
+
+__device__ __forceinline__ void bn_fwd_fold(const float* partial, const float* x, int64_t c, int64_t C, int64_t P,
+                                            const BnFin& f) {
+  // PS == 4 (bits given): the partials carry max (x - shift) and max (shift - x); the normalised output is
+  // monotone in x, so max |y| of the channel is attained at one of the two extremes and *bits becomes the
+  // bits of max |y| over the tensor (y = the output of the apply pass, ReLU included, evaluated with bn_affine)
+  float sa = 0.f, sb = 0.f, hi = 0.f, lo = 0.f;
+  for (int s = 0; s < f.S; ++s) {
+    sa += __ldcg(partial + (s * C + c) * f.PS + 0);
+    sb += __ldcg(partial + (s * C + c) * f.PS + 1);
+    if (f.PS == 4) {
+      hi = fmaxf(hi, __ldcg(partial + (s * C + c) * f.PS + 2));
+      lo = fmaxf(lo, __ldcg(partial + (s * C + c) * f.PS + 3));
+    }
+  }
+  const float shift = x[c * P];
+  const float d = sa / f.count;             // mean - shift
+  const float mean = shift + d;
+  float ssd = sb - sa * d;                  // sum (x-mean)^2 = sum a^2 - (sum a)^2 / n
+  if (ssd < 0.f) ssd = 0.f;
+  const float var_b = ssd / f.count;        // module.py:366
+  const float invstd = 1.f / sqrtf(var_b + f.eps);
+  f.save_mean[c] = mean;
+  f.save_invstd[c] = invstd;
+  if (f.running_mean) {
+    const float var_u = ssd / (f.count - 1.f);  // module.py:367-368
+    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * var_u;
+  }
+  if (f.bits) {
+    const float a = f.gamma[c] * invstd, b = f.beta[c];
+    const float z0 = bn_affine(shift + hi, mean, a, b), z1 = bn_affine(shift - lo, mean, a, b);
+    // (shift + hi and shift - lo reproduce the extreme elements up to rounding: a hair of slack is added)
+    float m = f.act ? fmaxf(fmaxf(z0, z1), 0.f) : fmaxf(fabsf(z0), fabsf(z1));
+    m *= 1.0001f;
+    if (m > 0.f && m < 3.0e38f) atomicMax(f.bits, __float_as_uint(m));
+  }
+}
+
+__device__ __forceinline__ void bn_bwd_fold(const float* partial, int64_t c, int64_t C, const BnFin& f) {
+  // PS == 4 (bits given, single process): *bits becomes the bits of an upper bound of max |dx| over the tensor,
+  // |dx| <= |k0| (max |dy| + |k1| + max |x - mean| |k2|) per channel with the k's of bn_bwd_dx_kernel
+  if (c == 0) f.sums[2 * C] = f.count;  // summed across ranks with the two per-channel sums (synchronised BatchNorm)
+  float sa = 0.f, sb = 0.f, mg = 0.f, mx = 0.f;
+  for (int s = 0; s < f.S; ++s) {
+    sa += __ldcg(partial + (s * C + c) * f.PS + 0);
+    sb += __ldcg(partial + (s * C + c) * f.PS + 1);
+    if (f.PS == 4) {
+      mg = fmaxf(mg, __ldcg(partial + (s * C + c) * f.PS + 2));
+      mx = fmaxf(mx, __ldcg(partial + (s * C + c) * f.PS + 3));
+    }
+  }
+  f.dbeta[c] = sa;
+  f.dgamma[c] = sb * f.invstd[c];
+  f.sums[c * 2 + 0] = sa;  // sum dy
+  f.sums[c * 2 + 1] = sb;  // sum dy * (x - mean)
+  if (f.bits) {
+    const float inv = f.invstd[c], inv_count = 1.f / f.count;
+    const float k0 = f.gamma[c] * inv, k1 = sa * inv_count, k2 = inv * inv * sb * inv_count;
+    const float m = fabsf(k0) * (mg + fabsf(k1) + mx * fabsf(k2)) * 1.0001f;
+    if (m > 0.f && m < 3.0e38f) atomicMax(f.bits, __float_as_uint(m));
+  }
+}
+
 // MODE 0: a = x - shift[c], b = a*a          (forward statistics)
 // MODE 1: a = dy,           b = dy*(x-mean)  (backward reductions)
 // MODE 2: like MODE 1 with dy masked by the fused ReLU: dy * (z >= 0), z recomputed from x
@@ -42,7 +126,8 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
                                                         int64_t N, int64_t C, int64_t P, int64_t n_per_split,
                                                         int vec_ok, const float* __restrict__ gamma = nullptr,
                                                         const float* __restrict__ beta = nullptr,
-                                                        const float* __restrict__ invstd = nullptr, FastDiv fp4 = FastDiv{0, 0, 0}) {
+                                                        const float* __restrict__ invstd = nullptr, FastDiv fp4 = FastDiv{0, 0, 0},
+                                                        const BnFin fin = BnFin{}) {
   __shared__ float scratch[32];
   const int64_t c = blockIdx.x, s = blockIdx.y;
   float za = 0.f, zb = 0.f;
@@ -144,53 +229,24 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
       partial[(s * C + c) * PS + 3] = mb;
     }
   }
+  if (fin.counter && threadIdx.x == 0) {
+    // the last block of the channel to arrive folds the channel's partials (and re-arms the counter)
+    __threadfence();
+    const unsigned int prev = atomicAdd(fin.counter + c, 1u);
+    if (prev == gridDim.y - 1) {
+      __threadfence();
+      if (MODE == 0) bn_fwd_fold(partial, x, c, C, P, fin);
+      else bn_bwd_fold(partial, c, C, fin);
+      fin.counter[c] = 0u;
+    }
+  }
 }
 
 // one thread per channel: fold the split partials, produce mean / invstd, update running stats
 __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ x,
-                                                              float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                                                              float* running_mean, float* running_var, int64_t C,
-                                                              int64_t P, int S, float count, float eps, float momentum,
-                                                              int PS = 2, const float* __restrict__ gamma = nullptr,
-                                                              const float* __restrict__ beta = nullptr, int act = 0,
-                                                              unsigned int* absmax_bits = nullptr) {
-  // PS == 4 (absmax_bits given): the partials carry max (x - shift) and max (shift - x); the normalised output is
-  // monotone in x, so max |y| of the channel is attained at one of the two extremes and *absmax_bits becomes the
-  // bits of max |y| over the tensor (y = the output of the apply pass, ReLU included, evaluated with bn_affine)
+                                                              int64_t C, int64_t P, const BnFin fin) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float sa = 0.f, sb = 0.f, hi = 0.f, lo = 0.f;
-  for (int s = 0; s < S; ++s) {
-    sa += partial[(s * C + c) * PS + 0];
-    sb += partial[(s * C + c) * PS + 1];
-    if (PS == 4) {
-      hi = fmaxf(hi, partial[(s * C + c) * PS + 2]);
-      lo = fmaxf(lo, partial[(s * C + c) * PS + 3]);
-    }
-  }
-  const float shift = x[c * P];
-  const float d = sa / count;               // mean - shift
-  const float mean = shift + d;
-  float ssd = sb - sa * d;                  // sum (x-mean)^2 = sum a^2 - (sum a)^2 / n
-  if (ssd < 0.f) ssd = 0.f;
-  const float var_b = ssd / count;          // module.py:366
-  const float invstd = 1.f / sqrtf(var_b + eps);
-  save_mean[c] = mean;
-  save_invstd[c] = invstd;
-  if (running_mean) {
-    const float var_u = ssd / (count - 1.f);  // module.py:367-368
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var_u;
-  }
-  if (absmax_bits) {
-    const float a = gamma[c] * invstd, b = beta[c];
-    const float z0 = bn_affine(shift + hi, mean, a, b), z1 = bn_affine(shift - lo, mean, a, b);
-    // (shift + hi and shift - lo reproduce the extreme elements exactly: a - ref is exact only up to rounding, so
-    //  one ulp of slack is added below)
-    float m = act ? fmaxf(fmaxf(z0, z1), 0.f) : fmaxf(fabsf(z0), fabsf(z1));
-    m *= 1.0001f;
-    if (m > 0.f && m < 3.0e38f) atomicMax(absmax_bits, __float_as_uint(m));
-  }
+  if (c < C) bn_fwd_fold(partial, x, c, C, P, fin);
 }
 
 // ---- synchronised BatchNorm (data parallel, ng_nccl_sync_bn) ----------------------------------------
@@ -281,36 +337,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, co
   }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial,
-                                                              const float* __restrict__ invstd, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta, float* __restrict__ sums, int64_t C,
-                                                              int S, float count, int PS = 2,
-                                                              const float* __restrict__ gamma = nullptr,
-                                                              unsigned int* bound_bits = nullptr) {
-  // PS == 4 (bound_bits given, single process): *bound_bits becomes the bits of an upper bound of max |dx| over the
-  // tensor, |dx| <= |k0| (max |dy| + |k1| + max |x - mean| |k2|) per channel with the k's of bn_bwd_dx_kernel
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int64_t C,
+                                                              const BnFin fin) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0) sums[2 * C] = count;  // summed across ranks with the two per-channel sums (synchronised BatchNorm)
-  if (c >= C) return;
-  float sa = 0.f, sb = 0.f, mg = 0.f, mx = 0.f;
-  for (int s = 0; s < S; ++s) {
-    sa += partial[(s * C + c) * PS + 0];
-    sb += partial[(s * C + c) * PS + 1];
-    if (PS == 4) {
-      mg = fmaxf(mg, partial[(s * C + c) * PS + 2]);
-      mx = fmaxf(mx, partial[(s * C + c) * PS + 3]);
-    }
-  }
-  dbeta[c] = sa;
-  dgamma[c] = sb * invstd[c];
-  sums[c * 2 + 0] = sa;  // sum dy
-  sums[c * 2 + 1] = sb;  // sum dy * (x - mean)
-  if (bound_bits) {
-    const float inv = invstd[c], inv_count = 1.f / count;
-    const float k0 = gamma[c] * inv, k1 = sa * inv_count, k2 = inv * inv * sb * inv_count;
-    const float m = fabsf(k0) * (mg + fabsf(k1) + mx * fabsf(k2)) * 1.0001f;
-    if (m > 0.f && m < 3.0e38f) atomicMax(bound_bits, __float_as_uint(m));
-  }
+  if (c < C) bn_bwd_fold(partial, c, C, fin);
 }
 
 // dx = gamma*invstd * (dy - sum_dy/n - (x-mean) * invstd^2 * sum_dy_xmu / n)
@@ -394,27 +424,51 @@ extern "C" {
 // Statistics half of the training forward: mean / invstd (and the running statistics) of x.  With absmax_bits
 // (single process only) the statistics pass also tracks the channel extremes and *absmax_bits receives the bits of
 // max |y| of the normalised (and activated) output before any of it is written.
+// [C] arrival counters of the fused fold: zero-initialised once, re-armed by the folding block, used by one
+// launch at a time (single in-order compute stream)
+static unsigned int* fold_counters() {
+  static unsigned int* buf = nullptr;
+  if (!buf) {
+    if (cudaMalloc((void**)&buf, 65536 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    cudaMemsetAsync(buf, 0, 65536 * sizeof(unsigned int), g_stream);
+  }
+  return buf;
+}
+
 static int bn_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean, uint64_t running_var,
                         uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW,
                         float eps, float momentum, int act, int vec) {
   int64_t n_per = 0;
   const int S = bn_split(N, C, HW, &n_per);
   const bool extra = absmax_bits != 0;
-  NG_REQUIRE(!(extra && dp_sync_bn()), "ng_bn2d_act_fwd_stats: not available under synchronised BatchNorm");
+  const bool sync = dp_sync_bn();
+  NG_REQUIRE(!(extra && sync), "ng_bn2d_act_fwd_stats: not available under synchronised BatchNorm");
   float* partial = nullptr;
   if (pool_alloc((void**)&partial, (uint64_t)S * C * (extra ? 4 : 2) * sizeof(float))) return 1;
+  BnFin fin{};
+  fin.S = S; fin.PS = extra ? 4 : 2; fin.act = act;
+  fin.count = (float)(N * HW); fin.eps = eps; fin.momentum = momentum;
+  fin.gamma = dptr<const float>(gamma); fin.beta = dptr<const float>(beta);
+  fin.bits = extra ? dptr<unsigned int>(absmax_bits) : nullptr;
+  fin.save_mean = dptr<float>(save_mean); fin.save_invstd = dptr<float>(save_invstd);
+  fin.running_mean = running_mean ? dptr<float>(running_mean) : nullptr;
+  fin.running_var = running_var ? dptr<float>(running_var) : nullptr;
+  fin.counter = sync ? nullptr : fold_counters();   // single process: the last block of a channel folds it
+  if (!sync && !fin.counter) return set_error("bn_fwd_stats: cudaMalloc of the fold counters failed");
+  const dim3 grid((unsigned)C, (unsigned)S);
+  const FastDiv fd = make_fastdiv(vec ? HW / 4 : 0);
   if (extra) {
     NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(absmax_bits), 0, 4, g_stream));
-    NG_LAUNCH((bn_reduce_kernel<0, true>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
-              (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr,
-              (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
+    NG_LAUNCH((bn_reduce_kernel<0, true>), grid, 256, 0, partial, dptr<const float>(x), (const float*)nullptr,
+              (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr, (const float*)nullptr,
+              (const float*)nullptr, fd, fin);
   } else {
-    NG_LAUNCH((bn_reduce_kernel<0>), dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
-              (const float*)nullptr, (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr,
-              (const float*)nullptr, (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
+    NG_LAUNCH((bn_reduce_kernel<0>), grid, 256, 0, partial, dptr<const float>(x), (const float*)nullptr,
+              (const float*)nullptr, N, C, HW, n_per, vec, (const float*)nullptr, (const float*)nullptr,
+              (const float*)nullptr, fd, fin);
   }
   NG_CHECK_LAUNCH();
-  if (dp_sync_bn()) {
+  if (sync) {
     const int world = dp_world();
     const int64_t stride = 2 * C + 4;
     float* xchg = nullptr;  // [stride] to send, then [world][stride] gathered
@@ -428,13 +482,6 @@ static int bn_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t runn
               running_var ? dptr<float>(running_var) : nullptr, C, eps, momentum);
     NG_CHECK_LAUNCH();
     pool_free(xchg);
-  } else {
-    NG_LAUNCH(bn_fwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, dptr<const float>(x),
-              dptr<float>(save_mean), dptr<float>(save_invstd), running_mean ? dptr<float>(running_mean) : nullptr,
-              running_var ? dptr<float>(running_var) : nullptr, C, HW, S, (float)(N * HW), eps, momentum,
-              extra ? 4 : 2, extra ? dptr<const float>(gamma) : nullptr, extra ? dptr<const float>(beta) : nullptr, act,
-              extra ? dptr<unsigned int>(absmax_bits) : nullptr);
-    NG_CHECK_LAUNCH();
   }
   pool_free(partial);
   return 0;
@@ -525,32 +572,44 @@ static int bn_bwd_sums(float* sums, uint64_t dgamma, uint64_t dbeta, uint64_t bo
   int64_t n_per = 0;
   const int S = bn_split(N, C, HW, &n_per);
   const bool extra = bound_bits != 0;
-  NG_REQUIRE(!(extra && dp_sync_bn()), "ng_bn2d_act_bwd_sums: not available under synchronised BatchNorm");
+  const bool sync = dp_sync_bn();
+  NG_REQUIRE(!(extra && sync), "ng_bn2d_act_bwd_sums: not available under synchronised BatchNorm");
   float* partial = nullptr;
   if (pool_alloc((void**)&partial, (uint64_t)S * C * (extra ? 4 : 2) * sizeof(float))) return 1;
   const float* g = act ? dptr<const float>(gamma) : nullptr;
   const float* b = act ? dptr<const float>(beta) : nullptr;
   const float* iv = act ? dptr<const float>(save_invstd) : nullptr;
+  BnFin fin{};
+  fin.S = S; fin.PS = extra ? 4 : 2; fin.act = act;
+  fin.count = (float)(N * HW);
+  fin.gamma = dptr<const float>(gamma);
+  fin.bits = extra ? dptr<unsigned int>(bound_bits) : nullptr;
+  fin.invstd = dptr<const float>(save_invstd);
+  fin.dgamma = dptr<float>(dgamma); fin.dbeta = dptr<float>(dbeta); fin.sums = sums;
+  // the fold rides on the reduction launch (last block of a channel); synchronised BatchNorm folds separately so
+  // that the sums exist as one block before the all-reduce
+  fin.counter = sync ? nullptr : fold_counters();
+  if (!sync && !fin.counter) return set_error("bn_bwd_sums: cudaMalloc of the fold counters failed");
   const dim3 grid((unsigned)C, (unsigned)S);
   const FastDiv fd = make_fastdiv(vec ? HW / 4 : 0);
   if (extra) NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(bound_bits), 0, 4, g_stream));
   if (act && extra)
     NG_LAUNCH((bn_reduce_kernel<2, true>), grid, 256, 0, partial, dptr<const float>(x), dptr<const float>(dy),
-              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd);
+              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd, fin);
   else if (act)
     NG_LAUNCH((bn_reduce_kernel<2>), grid, 256, 0, partial, dptr<const float>(x), dptr<const float>(dy),
-              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd);
+              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd, fin);
   else if (extra)
     NG_LAUNCH((bn_reduce_kernel<1, true>), grid, 256, 0, partial, dptr<const float>(x), dptr<const float>(dy),
-              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd);
+              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd, fin);
   else
     NG_LAUNCH((bn_reduce_kernel<1>), grid, 256, 0, partial, dptr<const float>(x), dptr<const float>(dy),
-              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd);
+              dptr<const float>(save_mean), N, C, HW, n_per, vec, g, b, iv, fd, fin);
   NG_CHECK_LAUNCH();
-  NG_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial,
-            dptr<const float>(save_invstd), dptr<float>(dgamma), dptr<float>(dbeta), sums, C, S, (float)(N * HW),
-            extra ? 4 : 2, extra ? dptr<const float>(gamma) : nullptr, extra ? dptr<unsigned int>(bound_bits) : nullptr);
-  NG_CHECK_LAUNCH();
+  if (sync) {
+    NG_LAUNCH(bn_bwd_finalize_kernel, (int)ceil_div(C, 256), 256, 0, (const float*)partial, C, fin);
+    NG_CHECK_LAUNCH();
+  }
   pool_free(partial);
   return 0;
 }

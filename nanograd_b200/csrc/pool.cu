@@ -19,8 +19,25 @@ struct PoolP {
   FastDiv f_ow, f_oh;  // set when the output has fewer than 2^31 elements: index math without 64-bit divisions
 };
 
-template <bool IS_MAX>
-__global__ void __launch_bounds__(256) pool_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, PoolP p) {
+// BN: the pooled tensor is the output of a training-mode BatchNorm2d (+ ReLU) that was never written
+// (nn/buffer.py LazyBuffer): x is that layer's INPUT and every value read is normalised on the fly with the
+// expression of the normalise pass (bn_affine), so the window maxima and the equality mask of the backward
+// are bit-identical to pooling the materialised tensor.
+struct PoolBN {
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* invstd;
+  int C, act;
+};
+__device__ __forceinline__ float pool_bn(float v, float mu, float a, float b, int act) {
+  const float z = bn_affine(v, mu, a, b);
+  return act ? fmaxf(z, 0.f) : z;
+}
+
+template <bool IS_MAX, bool BN = false>
+__global__ void __launch_bounds__(256) pool_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, PoolP p,
+                                                       PoolBN bn = PoolBN{nullptr, nullptr, nullptr, nullptr, 1, 0}) {
   const int64_t total = p.NC * p.OH * p.OW;
   const float scale = 1.f / (float)(p.ph * p.pw);
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
@@ -39,16 +56,26 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(float* __restrict__ y, co
       nc = t / p.OH;
     }
     const float* src = x + (nc * p.H + (int64_t)oh * p.ph) * p.W + (int64_t)ow * p.pw;
+    float mu = 0.f, ka = 1.f, kb = 0.f;
+    if (BN) {
+      const int c = (int)(nc % bn.C);
+      mu = bn.mean[c]; ka = bn.gamma[c] * bn.invstd[c]; kb = bn.beta[c];
+    }
     float acc;
     if (p.fast2) {
-      const float2 r0 = *reinterpret_cast<const float2*>(src);
-      const float2 r1 = *reinterpret_cast<const float2*>(src + p.W);
+      float2 r0 = *reinterpret_cast<const float2*>(src);
+      float2 r1 = *reinterpret_cast<const float2*>(src + p.W);
+      if (BN) {
+        r0.x = pool_bn(r0.x, mu, ka, kb, bn.act); r0.y = pool_bn(r0.y, mu, ka, kb, bn.act);
+        r1.x = pool_bn(r1.x, mu, ka, kb, bn.act); r1.y = pool_bn(r1.y, mu, ka, kb, bn.act);
+      }
       acc = IS_MAX ? fmaxf(fmaxf(r0.x, r0.y), fmaxf(r1.x, r1.y)) : ((r0.x + r0.y) + (r1.x + r1.y));
     } else {
       acc = IS_MAX ? -INFINITY : 0.f;
       for (int i = 0; i < p.ph; ++i)
         for (int j = 0; j < p.pw; ++j) {
-          const float v = src[i * p.W + j];
+          float v = src[i * p.W + j];
+          if (BN) v = pool_bn(v, mu, ka, kb, bn.act);
           acc = IS_MAX ? fmaxf(acc, v) : acc + v;
         }
     }
@@ -58,10 +85,10 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(float* __restrict__ y, co
 
 // One thread per output window writes the whole input window of dx.  Rows/columns cropped by
 // the forward pass receive zero from a preceding memset (only when H % ph or W % pw != 0).
-template <bool IS_MAX>
+template <bool IS_MAX, bool BN = false>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy,
                                                        const float* __restrict__ x, const float* __restrict__ y,
-                                                       PoolP p) {
+                                                       PoolP p, PoolBN bn = PoolBN{nullptr, nullptr, nullptr, nullptr, 1, 0}) {
   const int64_t total = p.NC * p.OH * p.OW;
   const float scale = 1.f / (float)(p.ph * p.pw);
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
@@ -81,11 +108,20 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(float* __restrict__ dx, c
     }
     const int64_t base = (nc * p.H + (int64_t)oh * p.ph) * p.W + (int64_t)ow * p.pw;
     const float g = dy[o];
+    float mu = 0.f, ka = 1.f, kb = 0.f;
+    if (BN) {
+      const int c = (int)(nc % bn.C);
+      mu = bn.mean[c]; ka = bn.gamma[c] * bn.invstd[c]; kb = bn.beta[c];
+    }
     if (IS_MAX) {
       const float m = y[o];
       if (p.fast2) {
-        const float2 r0 = *reinterpret_cast<const float2*>(x + base);
-        const float2 r1 = *reinterpret_cast<const float2*>(x + base + p.W);
+        float2 r0 = *reinterpret_cast<const float2*>(x + base);
+        float2 r1 = *reinterpret_cast<const float2*>(x + base + p.W);
+        if (BN) {
+          r0.x = pool_bn(r0.x, mu, ka, kb, bn.act); r0.y = pool_bn(r0.y, mu, ka, kb, bn.act);
+          r1.x = pool_bn(r1.x, mu, ka, kb, bn.act); r1.y = pool_bn(r1.y, mu, ka, kb, bn.act);
+        }
         const int e00 = r0.x == m, e01 = r0.y == m, e10 = r1.x == m, e11 = r1.y == m;
         const float share = g / (float)(e00 + e01 + e10 + e11);
         float2 o0, o1;
@@ -96,12 +132,18 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(float* __restrict__ dx, c
       } else {
         int cnt = 0;
         for (int i = 0; i < p.ph; ++i)
-          for (int j = 0; j < p.pw; ++j) cnt += (x[base + i * p.W + j] == m);
+          for (int j = 0; j < p.pw; ++j) {
+            float v = x[base + i * p.W + j];
+            if (BN) v = pool_bn(v, mu, ka, kb, bn.act);
+            cnt += (v == m);
+          }
         const float share = g / (float)cnt;
         for (int i = 0; i < p.ph; ++i)
           for (int j = 0; j < p.pw; ++j) {
             const int64_t a = base + i * p.W + j;
-            dx[a] = (x[a] == m) ? share : 0.f;
+            float v = x[a];
+            if (BN) v = pool_bn(v, mu, ka, kb, bn.act);
+            dx[a] = (v == m) ? share : 0.f;
           }
       }
     } else {
@@ -195,5 +237,40 @@ int ng_avgpool2d_bwd(uint64_t dx, uint64_t dy, int64_t NC, int H, int W, int ph,
   NG_CHECK_LAUNCH();
   return 0;
 }
+
+int ng_maxpool2d_fwd_bn(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd, int64_t NC,
+                        int C, int H, int W, int ph, int pw, int act) {
+  NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_POOL, 0.0, (ph > 0 && pw > 0) ? 4.0 * ((double)NC * H * W + (double)NC * (H / ph) * (W / pw)) : 0.0);
+  PoolP p;
+  if (make_pool(p, "ng_maxpool2d_fwd_bn", NC, H, W, ph, pw, x, x)) return 1;
+  NG_REQUIRE(C > 0 && NC % C == 0 && (act == 0 || act == 1), "ng_maxpool2d_fwd_bn: bad channel count or act");
+  const int64_t n = NC * p.OH * p.OW;
+  if (n <= 0) return 0;
+  const PoolBN bn{dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(mean), dptr<const float>(invstd), C, act};
+  NG_LAUNCH((pool_fwd_kernel<true, true>), pgrid(n), 256, 0, dptr<float>(y), dptr<const float>(x), p, bn);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
+int ng_maxpool2d_bwd_bn(uint64_t dx, uint64_t dy, uint64_t x, uint64_t y, uint64_t gamma, uint64_t beta, uint64_t mean,
+                        uint64_t invstd, int64_t NC, int C, int H, int W, int ph, int pw, int act) {
+  NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_POOL, 0.0,
+                  (ph > 0 && pw > 0) ? 4.0 * (2.0 * (double)NC * H * W + 2.0 * (double)NC * (H / ph) * (W / pw)) : 0.0);
+  PoolP p;
+  if (make_pool(p, "ng_maxpool2d_bwd_bn", NC, H, W, ph, pw, x, dx)) return 1;
+  NG_REQUIRE(C > 0 && NC % C == 0 && (act == 0 || act == 1), "ng_maxpool2d_bwd_bn: bad channel count or act");
+  if (NC * H * W <= 0) return 0;
+  if (H % ph || W % pw) NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(dx), 0, (size_t)(NC * H * W) * sizeof(float), g_stream));
+  const int64_t n = NC * p.OH * p.OW;
+  if (n <= 0) return 0;
+  const PoolBN bn{dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(mean), dptr<const float>(invstd), C, act};
+  NG_LAUNCH((pool_bwd_kernel<true, true>), pgrid(n), 256, 0, dptr<float>(dx), dptr<const float>(dy), dptr<const float>(x),
+            dptr<const float>(y), p, bn);
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
 
 }  // extern "C"

@@ -225,14 +225,36 @@ __global__ void __launch_bounds__(256) stage_f16_kernel(__half* __restrict__ out
   }
 }
 
-// dst[plane][rs][j][kc] = split(w[j*sj + kc*sc + rs])
-__global__ void __launch_bounds__(256) filter_relayout_f16_kernel(__half* __restrict__ dst, const float* __restrict__ w,
-                                                                  int J, int KC, int RS, long long sj, long long sc,
-                                                                  const unsigned int* __restrict__ max_bits,
-                                                                  float* __restrict__ inv_scale_out) {
-  const float scale = f16_scale(*max_bits);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
+// dst[plane][rs][j][kc] = split(w[j*sj + kc*sc + rs]) for a filter tensor of n = J*KC*RS elements, magnitude pass
+// and re-layout in ONE launch: every block folds its share of max|w| into *bits, the blocks meet at a grid barrier
+// (an arrival counter; the grid is at most one block per SM, so all blocks are resident), then re-lay with the common
+// scale.  Two launches per filter cost 8-9 us of which ~1 us was work (20 per training step).
+__global__ void __launch_bounds__(256) filter_stage_f16_kernel(__half* __restrict__ dst, const float* __restrict__ w,
+                                                               int J, int KC, int RS, long long sj, long long sc,
+                                                               unsigned int* bits, unsigned int* arrived,
+                                                               float* __restrict__ inv_scale_out) {
   const long long n = (long long)J * KC * RS;
+  float m = 0.f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[e]));   // the KCRS block is contiguous whichever of (j, kc) is the outer axis
+  m = warp_max(m);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    if (m > 0.f && m < 3.0e38f) atomicMax(bits, __float_as_uint(m));
+    __threadfence();
+    atomicAdd(arrived, 1u);
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(arrived) < gridDim.x) {
+      if (++spins > (1u << 26)) __trap();   // a scheduling assumption broke: fail instead of hanging
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const float scale = f16_scale(*reinterpret_cast<volatile unsigned int*>(bits));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const int kc = (int)(e % KC);
     const long long t = e / KC;
@@ -600,16 +622,14 @@ static int launch_gather_f16(float* out, const void* act, const float* filt, con
   int rc = 0;
   const void* act_s = act_is_staged ? act : act_t;
   if (!act_is_staged) rc = to_nhwc_f16(act_t, reinterpret_cast<const float*>(act), nullptr, n_img, KC, AH * AW, nullptr);
-  float* wmeta = staged_meta(wt, filt_elems);
+  float* wmeta = staged_meta(wt, filt_elems);   // [0] 1/scale, [1] bits of max|w|, [2] arrival counter
+  if (rc == 0 && cudaMemsetAsync(wmeta + 1, 0, 8, g_stream) != cudaSuccess) rc = set_error("cudaMemsetAsync failed");
   if (rc == 0) {
-    // max|w| over the filter tensor: the KCRS block is contiguous whichever of (j, kc) is the outer axis
-    rc = launch_absmax(reinterpret_cast<unsigned int*>(wmeta + 1), filt, filt_elems);
-  }
-  if (rc == 0) {
-    int g = (int)ceil_div(filt_elems, 256);
-    if (g > 148 * 8) g = 148 * 8;
-    NG_LAUNCH(filter_relayout_f16_kernel, g, 256, 0, reinterpret_cast<__half*>(wt), filt, J, KC, RS, sj, sc,
-              (const unsigned int*)(wmeta + 1), wmeta);
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    int g = (int)ceil_div(filt_elems, 256 * 8);
+    if (g > sms) g = sms;
+    NG_LAUNCH(filter_stage_f16_kernel, g, 256, 0, reinterpret_cast<__half*>(wt), filt, J, KC, RS, sj, sc,
+              reinterpret_cast<unsigned int*>(wmeta + 1), reinterpret_cast<unsigned int*>(wmeta + 2), wmeta);
     const int G = KC / 64;
     const uint64_t pix = (uint64_t)KC * 4u;   // bytes per staged pixel
     const uint64_t dims[5] = {64u, (uint64_t)AW, (uint64_t)AH, (uint64_t)n_img, (uint64_t)(2 * G)};

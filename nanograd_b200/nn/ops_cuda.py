@@ -841,7 +841,12 @@ class MaxPool2d(Function):
     def forward(ctx, input, pool_size=(2, 2)):
         n, c, h, w, ph, pw = _pool_geometry(input.shape, pool_size)
         out = DeviceBuffer((n, c, h // ph, w // pw))
-        _lib().ng_maxpool2d_fwd(out.ptr, input.ptr, n * c, h, w, ph, pw)
+        if isinstance(input, LazyBuffer) and input.pending and input.kind == "bn_fwd":
+            # pool the BatchNorm (+ ReLU) output straight from its recipe: the activation is never written
+            x, gamma, beta, mean, invstd, act, _ = input.source
+            _lib().ng_maxpool2d_fwd_bn(out.ptr, x.ptr, gamma.ptr, beta.ptr, mean.ptr, invstd.ptr, n * c, c, h, w, ph, pw, act)
+        else:
+            _lib().ng_maxpool2d_fwd(out.ptr, input.ptr, n * c, h, w, ph, pw)
         if getattr(input, "absmax", None) is not None:
             out.absmax = input.absmax   # a window maximum never exceeds the tensor's largest magnitude
         ctx.save_for_backward(input, out, (ph, pw))
@@ -852,7 +857,12 @@ class MaxPool2d(Function):
         input, out, (ph, pw) = ctx.saved_tensors
         n, c, h, w = input.shape
         dx = DeviceBuffer(input.shape)
-        _lib().ng_maxpool2d_bwd(dx.ptr, grad_output.ptr, input.ptr, out.ptr, n * c, h, w, ph, pw)
+        if isinstance(input, LazyBuffer) and input.pending and input.kind == "bn_fwd":
+            x, gamma, beta, mean, invstd, act, _ = input.source
+            _lib().ng_maxpool2d_bwd_bn(dx.ptr, grad_output.ptr, x.ptr, out.ptr, gamma.ptr, beta.ptr, mean.ptr, invstd.ptr,
+                                       n * c, c, h, w, ph, pw, act)
+        else:
+            _lib().ng_maxpool2d_bwd(dx.ptr, grad_output.ptr, input.ptr, out.ptr, n * c, h, w, ph, pw)
         return dx
 
 

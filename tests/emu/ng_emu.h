@@ -114,6 +114,9 @@ inline float __shfl_down_sync(unsigned, float v, int delta) {
 }
 inline float __shfl_sync(unsigned, float v, int src) { return ng_emu::shfl(v, src & 31); }
 inline float __ldg(const float* p) { return *p; }
+inline float __ldcg(const float* p) { return *(const volatile float*)p; }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned int __float_as_uint(float v) { unsigned int u; memcpy(&u, &v, 4); return u; }
 inline float __uint_as_float(unsigned int u) { float v; memcpy(&v, &u, 4); return v; }
 inline unsigned int atomicMax(unsigned int* p, unsigned int v) {   // CUDA threads are host threads here

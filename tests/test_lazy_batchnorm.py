@@ -161,3 +161,48 @@ def test_lazy_outputs_are_only_written_when_somebody_reads_them():
         assert not z.data.pending
     finally:
         B.set_math_mode("fp32")
+
+
+def _check_fused_maxpool(shape, act):
+    """Max pooling straight from the BatchNorm recipe: outputs and tie-splitting gradients bit-identical to pooling
+    the materialised tensor (the window maximum and the equality mask see the same float32 values)."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    lib = B.lib()
+    n, c, h, w = shape
+    hw = h * w
+    host, dev = _setup(n, c, h, w, seed=11 * c + act)
+    # tie-rich input: quantised values make equal window maxima common (and ReLU zeros tie by themselves)
+    xq = np.round(host["x"] * 2) / 2
+    dev["x"] = DeviceBuffer(xq.shape, hostbuf=xq.astype(np.float32))
+    y, mean, invstd, absmax = DeviceBuffer((n, c, h, w)), DeviceBuffer((c,)), DeviceBuffer((c,)), DeviceBuffer((1,))
+    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, mean.ptr, invstd.ptr, absmax.ptr,
+                              n, c, hw, 1e-5, 0.1, act)
+    lib.ng_bn2d_act_apply(y.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, mean.ptr, invstd.ptr, n, c, hw, act)
+    oh, ow = h // 2, w // 2
+    g = np.random.RandomState(5).randn(n, c, oh, ow).astype(np.float32)
+    gd = DeviceBuffer(g.shape, hostbuf=g)
+    p1, d1 = DeviceBuffer((n, c, oh, ow)), DeviceBuffer((n, c, h, w))
+    lib.ng_maxpool2d_fwd(p1.ptr, y.ptr, n * c, h, w, 2, 2)
+    lib.ng_maxpool2d_bwd(d1.ptr, gd.ptr, y.ptr, p1.ptr, n * c, h, w, 2, 2)
+    p2, d2 = DeviceBuffer((n, c, oh, ow)), DeviceBuffer((n, c, h, w))
+    lib.ng_maxpool2d_fwd_bn(p2.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, mean.ptr, invstd.ptr, n * c, c, h, w, 2, 2, act)
+    lib.ng_maxpool2d_bwd_bn(d2.ptr, gd.ptr, dev["x"].ptr, p2.ptr, dev["gamma"].ptr, dev["beta"].ptr, mean.ptr, invstd.ptr,
+                            n * c, c, h, w, 2, 2, act)
+    H.assert_exact(p2.numpy(), p1.numpy(), "fused max-pool output")
+    H.assert_exact(d2.numpy(), d1.numpy(), "fused max-pool input gradient")
+    assert (d1.numpy() != 0).sum() > n * c * oh * ow, "the data has ties (gradient split among several window elements)"
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_fused_maxpool_matches_pooling_the_materialised_tensor_emulated(act):
+    H.use_emulated_library()
+    _check_fused_maxpool((2, 6, 6, 8), act)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 6, 6, 8), (16, 64, 32, 32), (5, 128, 7, 9)], ids=lambda s: "x".join(map(str, s)))
+def test_fused_maxpool_matches_pooling_the_materialised_tensor(shape, act):
+    H.use_cuda_library()
+    _check_fused_maxpool(shape, act)
