@@ -221,6 +221,12 @@ int ng_conv2d_stage_f16_bn(uint64_t dst, uint64_t x, uint64_t gamma, uint64_t be
 int ng_conv2d_stage_f16_bnbwd(uint64_t dst, uint64_t chan_sums, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta,
                               uint64_t mean, uint64_t invstd, uint64_t bn_sums, uint64_t bound_bits, int64_t N,
                               int64_t C, int64_t HW, int act);
+/* the same when the layer's output went through a 2x2 max pooling (conv -> BatchNorm2d -> ReLU -> MaxPool2d(2)):
+ * the pooling backward (Max.backward's tie-splitting mask, ops_cpu.py:121-127) is fused in as well, dy is recomputed
+ * per window from the pooled maxima and their gradient (sums from ng_bn2d_act_bwd_sums_pool) */
+int ng_conv2d_stage_f16_bnbwd_pool(uint64_t dst, uint64_t chan_sums, uint64_t dpooled, uint64_t pooled, uint64_t x,
+                                   uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd, uint64_t bn_sums,
+                                   uint64_t bound_bits, int64_t N, int64_t C, int H, int W, int act);
 
 /* -------------------------------------------------------------------- pooling ------ */
 /* fused replacements for Tensor._pool2d → Slice, Reshape, Max/Sum(axis=(3,5)), Mul
@@ -306,6 +312,11 @@ int ng_bn2d_act_bwd_sums(uint64_t dgamma, uint64_t dbeta, uint64_t sums, uint64_
                          int64_t N, int64_t C, int64_t HW, int act);
 int ng_bn2d_act_bwd_dx(uint64_t dx, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean,
                        uint64_t save_invstd, uint64_t sums, int64_t N, int64_t C, int64_t HW, int act);
+/* ng_bn2d_act_bwd_sums for a layer whose output went through a 2x2 max pooling, with the pooling backward fused
+ * in: the gradient of the pooled tensor (dpooled) and the pooled maxima replace dy, which is never written */
+int ng_bn2d_act_bwd_sums_pool(uint64_t dgamma, uint64_t dbeta, uint64_t sums, uint64_t bound_bits, uint64_t dpooled,
+                              uint64_t pooled, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean,
+                              uint64_t save_invstd, int64_t N, int64_t C, int H, int W, int act);
 
 /* ------------------------------------------------------------------- optimizers ---- */
 /* one multi-tensor launch per step for the whole parameter list.

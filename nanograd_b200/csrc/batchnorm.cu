@@ -242,6 +242,104 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(float* __restrict__ part
   }
 }
 
+// Backward reduction of a BatchNorm2d (+ ReLU) layer whose output went through a 2x2 max pooling, with the pooling
+// backward fused in: the incoming gradient is never written.  Per window the thread recomputes the four activations
+// y = act(bn_affine(x)) from the layer input, splits the pooled gradient among the elements equal to the pooled
+// maximum (Max.backward's tie rule, ops_cpu.py:121-127 — the same float32 values as ng_maxpool2d_bwd_bn sees),
+// applies the ReLU mask (z >= 0) and accumulates sum dy, sum dy (x - mean), max |dy|, max |x - mean|.
+// Replaces pool_bwd (2.5 passes over the tensor) + the dy read of bn_reduce_kernel<2> by two quarter-size reads.
+__global__ void __launch_bounds__(256) bn_reduce_pool_kernel(float* __restrict__ partial, const float* __restrict__ x,
+                                                             const float* __restrict__ dpooled,
+                                                             const float* __restrict__ pooled,
+                                                             const float* __restrict__ mean, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ invstd,
+                                                             int64_t N, int64_t C, int H, int W, int64_t n_per_split, int act,
+                                                             FastDiv f_win, FastDiv f_ow, const BnFin fin) {
+  __shared__ float scratch[32];
+  const int64_t c = blockIdx.x, s = blockIdx.y;
+  const float mu = mean[c], za = gamma[c] * invstd[c], zb = beta[c];
+  const int64_t n0 = s * n_per_split;
+  int64_t n1 = n0 + n_per_split;
+  if (n1 > N) n1 = N;
+  const int OW = W >> 1, OH = H >> 1;
+  const int64_t wins = (int64_t)OH * OW;
+  // one item = two horizontally adjacent windows: two 128-bit loads of x, one 64-bit load each of the pooled maxima
+  // and their gradient (W % 4 == 0); two items' loads are in flight before the first is consumed
+  const int64_t pairs = wins >> 1;
+  const int64_t items = (n1 - n0) * pairs;
+  float sa = 0.f, sb = 0.f, ea = 0.f, eb = 0.f;
+  constexpr int U = 2;
+  for (int64_t i0 = threadIdx.x; i0 < items; i0 += U * (int64_t)blockDim.x) {
+    float4 r0[U], r1[U];
+    float2 pm[U], pg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * (int64_t)blockDim.x;
+      r0[u] = r1[u] = make_float4(mu, mu, mu, mu);
+      pm[u] = make_float2(3.0e38f, 3.0e38f);   // out-of-range slot: no element equals the "maximum", nothing is accumulated
+      pg[u] = make_float2(0.f, 0.f);
+      if (i < items) {
+        const uint32_t q = fastdiv((uint32_t)i, f_win);          // image within the split
+        const uint32_t wi = (uint32_t)i - q * f_win.d;           // window pair within the image
+        const uint32_t oh = fastdiv(wi, f_ow), op = wi - oh * f_ow.d;
+        const int64_t plane = (n0 + q) * C + c;
+        const float* src = x + (plane * H + 2 * (int64_t)oh) * W + 4 * op;
+        r0[u] = *reinterpret_cast<const float4*>(src);
+        r1[u] = *reinterpret_cast<const float4*>(src + W);
+        pm[u] = *reinterpret_cast<const float2*>(pooled + plane * wins + 2 * (int64_t)wi);
+        pg[u] = *reinterpret_cast<const float2*>(dpooled + plane * wins + 2 * (int64_t)wi);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float xs[4] = {half ? r0[u].z : r0[u].x, half ? r0[u].w : r0[u].y, half ? r1[u].z : r1[u].x,
+                             half ? r1[u].w : r1[u].y};
+        const float pmax = half ? pm[u].y : pm[u].x, pgrad = half ? pg[u].y : pg[u].x;
+        float z[4], y[4];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          z[k] = bn_affine(xs[k], mu, za, zb);
+          y[k] = act ? fmaxf(z[k], 0.f) : z[k];
+          cnt += (y[k] == pmax);
+        }
+        const float share = cnt ? pgrad / (float)cnt : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float g = (y[k] == pmax) ? share : 0.f;
+          if (act && !(z[k] >= 0.f)) g = 0.f;
+          const float d = xs[k] - mu;
+          sa += g;
+          sb += g * d;
+          ea = fmaxf(ea, fabsf(g));
+          eb = fmaxf(eb, fabsf(d));
+        }
+      }
+    }
+  }
+  const float ta = block_sum(sa, scratch);
+  const float tb = block_sum(sb, scratch);
+  if (threadIdx.x == 0) {
+    partial[(s * C + c) * 4 + 0] = ta;
+    partial[(s * C + c) * 4 + 1] = tb;
+  }
+  const float ma = block_max(ea, scratch);
+  const float mb = block_max(eb, scratch);
+  if (threadIdx.x == 0) {
+    partial[(s * C + c) * 4 + 2] = ma;
+    partial[(s * C + c) * 4 + 3] = mb;
+    __threadfence();
+    const unsigned int prev = atomicAdd(fin.counter + c, 1u);
+    if (prev == gridDim.y - 1) {
+      __threadfence();
+      bn_bwd_fold(partial, c, C, fin);
+      fin.counter[c] = 0u;
+    }
+  }
+}
+
 // one thread per channel: fold the split partials, produce mean / invstd, update running stats
 __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ x,
                                                               int64_t C, int64_t P, const BnFin fin) {
@@ -659,6 +757,42 @@ int ng_bn2d_act_bwd_sums(uint64_t dgamma, uint64_t dbeta, uint64_t sums, uint64_
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0);
   return bn_bwd_sums(dptr<float>(sums), dgamma, dbeta, bound_bits, dy, x, gamma, beta, save_mean, save_invstd, N, C, HW,
                      act, vec);
+}
+
+int ng_bn2d_act_bwd_sums_pool(uint64_t dgamma, uint64_t dbeta, uint64_t sums, uint64_t bound_bits, uint64_t dpooled,
+                              uint64_t pooled, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean,
+                              uint64_t save_invstd, int64_t N, int64_t C, int H, int W, int act) {
+  NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_BN, 0.0, 6.0 * (double)N * C * H * W);   // x once, pooled and its gradient (a quarter each)
+  NG_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 4 == 0 && (x & 15u) == 0 && (pooled & 7u) == 0 &&
+                 (dpooled & 7u) == 0,
+             "ng_bn2d_act_bwd_sums_pool: needs even H, W %% 4 == 0, a 16-byte aligned input and 8-byte aligned pooled tensors");
+  NG_REQUIRE(C <= 65535 && (act == 0 || act == 1), "ng_bn2d_act_bwd_sums_pool: bad channel count or act");
+  NG_REQUIRE(sums != 0 && bound_bits != 0, "ng_bn2d_act_bwd_sums_pool: sums and bound_bits are required");
+  NG_REQUIRE(!dp_sync_bn(), "ng_bn2d_act_bwd_sums_pool: not available under synchronised BatchNorm");
+  const int64_t HW = (int64_t)H * W;
+  NG_REQUIRE(N * (HW / 4) < (1LL << 31), "ng_bn2d_act_bwd_sums_pool: tensor too large");
+  int64_t n_per = 0;
+  const int S = bn_split(N, C, HW, &n_per);
+  float* partial = nullptr;
+  if (pool_alloc((void**)&partial, (uint64_t)S * C * 4 * sizeof(float))) return 1;
+  BnFin fin{};
+  fin.S = S; fin.PS = 4; fin.act = act;
+  fin.count = (float)(N * HW);
+  fin.gamma = dptr<const float>(gamma);
+  fin.bits = dptr<unsigned int>(bound_bits);
+  fin.invstd = dptr<const float>(save_invstd);
+  fin.dgamma = dptr<float>(dgamma); fin.dbeta = dptr<float>(dbeta); fin.sums = dptr<float>(sums);
+  fin.counter = fold_counters();
+  if (!fin.counter) return set_error("ng_bn2d_act_bwd_sums_pool: cudaMalloc of the fold counters failed");
+  NG_CHECK_CUDA(cudaMemsetAsync(dptr<void>(bound_bits), 0, 4, g_stream));
+  NG_LAUNCH(bn_reduce_pool_kernel, dim3((unsigned)C, (unsigned)S), 256, 0, partial, dptr<const float>(x),
+            dptr<const float>(dpooled), dptr<const float>(pooled), dptr<const float>(save_mean), dptr<const float>(gamma),
+            dptr<const float>(beta), dptr<const float>(save_invstd), N, C, H, W, n_per, act, make_fastdiv(HW / 8),
+            make_fastdiv(W / 4), fin);
+  NG_CHECK_LAUNCH();
+  pool_free(partial);
+  return 0;
 }
 
 int ng_bn2d_act_bwd_dx(uint64_t dx, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean,

@@ -1164,6 +1164,28 @@ int ng_conv2d_stage_f16_bnbwd(uint64_t dst, uint64_t chan_sums, uint64_t dy, uin
 #endif
 }
 
+int ng_conv2d_stage_f16_bnbwd_pool(uint64_t dst, uint64_t chan_sums, uint64_t dpooled, uint64_t pooled, uint64_t x,
+                                   uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd, uint64_t bn_sums,
+                                   uint64_t bound_bits, int64_t N, int64_t C, int H, int W, int act) {
+  NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_STAGE, 0.0, 10.0 * (double)N * C * H * W);   // x in, pooled + gradient (a quarter each), staged out
+#ifndef NG_EMU
+  NG_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && N * C * (int64_t)H * W < 2147483647LL && (chan_sums == 0 || N <= 65535),
+             "ng_conv2d_stage_f16_bnbwd_pool: bad dimensions");
+  NG_REQUIRE(bound_bits != 0 && bn_sums != 0 && beta != 0 && (act == 0 || act == 1),
+             "ng_conv2d_stage_f16_bnbwd_pool: bound_bits, bn_sums and beta required; act 0 or 1");
+  return umma::to_nhwc_f16_bnbwd_pool(dptr<void>(dst), chan_sums ? dptr<float>(chan_sums) : nullptr,
+                                      dptr<const float>(dpooled), dptr<const float>(pooled), dptr<const float>(x),
+                                      dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(mean),
+                                      dptr<const float>(invstd), dptr<const float>(bn_sums), act,
+                                      dptr<const unsigned int>(bound_bits), (int)N, (int)C, H, W);
+#else
+  (void)dst; (void)chan_sums; (void)dpooled; (void)pooled; (void)x; (void)gamma; (void)beta; (void)mean; (void)invstd;
+  (void)bn_sums; (void)bound_bits; (void)N; (void)C; (void)H; (void)W; (void)act;
+  return set_error("ng_conv2d_stage_f16_bnbwd_pool: the tensor-core path does not exist in the emulation build");
+#endif
+}
+
 int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, int W, int K, int R, int S,
                     int stride, int pad_t, int pad_l, int OH, int OW, int flags) {
   NG_ENSURE_INIT();

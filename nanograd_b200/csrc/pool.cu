@@ -56,15 +56,19 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(float* __restrict__ y, co
       nc = t / p.OH;
     }
     const float* src = x + (nc * p.H + (int64_t)oh * p.ph) * p.W + (int64_t)ow * p.pw;
+    // (window loads first, BatchNorm constants after: all in flight together)
+    float2 r0 = make_float2(0.f, 0.f), r1 = make_float2(0.f, 0.f);
+    if (p.fast2) {
+      r0 = *reinterpret_cast<const float2*>(src);
+      r1 = *reinterpret_cast<const float2*>(src + p.W);
+    }
     float mu = 0.f, ka = 1.f, kb = 0.f;
     if (BN) {
       const int c = (int)(nc % bn.C);
-      mu = bn.mean[c]; ka = bn.gamma[c] * bn.invstd[c]; kb = bn.beta[c];
+      mu = __ldg(bn.mean + c); ka = __ldg(bn.gamma + c) * __ldg(bn.invstd + c); kb = __ldg(bn.beta + c);
     }
     float acc;
     if (p.fast2) {
-      float2 r0 = *reinterpret_cast<const float2*>(src);
-      float2 r1 = *reinterpret_cast<const float2*>(src + p.W);
       if (BN) {
         r0.x = pool_bn(r0.x, mu, ka, kb, bn.act); r0.y = pool_bn(r0.y, mu, ka, kb, bn.act);
         r1.x = pool_bn(r1.x, mu, ka, kb, bn.act); r1.y = pool_bn(r1.y, mu, ka, kb, bn.act);
@@ -108,16 +112,23 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(float* __restrict__ dx, c
     }
     const int64_t base = (nc * p.H + (int64_t)oh * p.ph) * p.W + (int64_t)ow * p.pw;
     const float g = dy[o];
+    // (window loads first, BatchNorm constants after: all in flight together)
+    float2 r0 = make_float2(0.f, 0.f), r1 = make_float2(0.f, 0.f);
+    float m = 0.f;
+    if (IS_MAX) {
+      m = y[o];
+      if (p.fast2) {
+        r0 = *reinterpret_cast<const float2*>(x + base);
+        r1 = *reinterpret_cast<const float2*>(x + base + p.W);
+      }
+    }
     float mu = 0.f, ka = 1.f, kb = 0.f;
     if (BN) {
       const int c = (int)(nc % bn.C);
-      mu = bn.mean[c]; ka = bn.gamma[c] * bn.invstd[c]; kb = bn.beta[c];
+      mu = __ldg(bn.mean + c); ka = __ldg(bn.gamma + c) * __ldg(bn.invstd + c); kb = __ldg(bn.beta + c);
     }
     if (IS_MAX) {
-      const float m = y[o];
       if (p.fast2) {
-        float2 r0 = *reinterpret_cast<const float2*>(x + base);
-        float2 r1 = *reinterpret_cast<const float2*>(x + base + p.W);
         if (BN) {
           r0.x = pool_bn(r0.x, mu, ka, kb, bn.act); r0.y = pool_bn(r0.y, mu, ka, kb, bn.act);
           r1.x = pool_bn(r1.x, mu, ka, kb, bn.act); r1.y = pool_bn(r1.y, mu, ka, kb, bn.act);

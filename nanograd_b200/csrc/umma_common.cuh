@@ -406,6 +406,9 @@ int to_nhwc_f16(void* staged, const float* in, float* sums, int N, int C, int HW
 // the same staged copy of a BatchNorm2d (+ ReLU) output / input gradient that was never written (see StageSrc)
 int to_nhwc_f16_bn(void* staged, const float* x, const float* gamma, const float* beta, const float* mean,
                    const float* invstd, int act, const unsigned int* absmax_bits, int N, int C, int HW);
+int to_nhwc_f16_bnbwd_pool(void* staged, float* chan_sums, const float* dpooled, const float* pooled, const float* x,
+                           const float* gamma, const float* beta, const float* mean, const float* invstd,
+                           const float* bn_sums, int act, const unsigned int* bound_bits, int N, int C, int H, int W);
 int to_nhwc_f16_bnbwd(void* staged, float* chan_sums, const float* dy, const float* x, const float* gamma,
                       const float* beta, const float* mean, const float* invstd, const float* bn_sums, int act,
                       const unsigned int* bound_bits, int N, int C, int HW);

@@ -84,8 +84,9 @@ __device__ __forceinline__ void f16_split(float v, float scale, __half& hi, __ha
 // BatchNorm2d (+ ReLU) that was never written, y = act(bn_affine(x)) recomputed from the layer input x and its
 // statistics.  SRC 2: the input gradient of such a layer that was never written,
 // dx = k0 (dy (masked) - k1 - (x - mean) k2), recomputed from dy, x and the backward sums exactly as bn_bwd_dx_kernel
-// (batchnorm.cu) evaluates it.  Fusing the normalise passes into the staging pass removes one write and one read of
-// the activation (forward) and of the gradient (backward) per layer.
+// (batchnorm.cu) evaluates it.  SRC 3: the same with dy itself recomputed from a fused 2x2 max-pool backward.
+// Fusing the normalise passes into the staging pass removes one write and one read of the activation (forward) and
+// of the gradient (backward) per layer.
 struct StageSrc {
   const float* in;       // SRC 0: the tensor; SRC 1, 2: the BatchNorm input x
   const float* dy;       // SRC 2
@@ -93,9 +94,15 @@ struct StageSrc {
   const float* beta;     // null: no fused ReLU
   const float* mean;
   const float* invstd;
-  const float* sums;     // SRC 2: [C][2] = sum dy, sum dy (x - mean)
-  float inv_count;       // SRC 2
+  const float* sums;     // SRC 2, 3: [C][2] = sum dy, sum dy (x - mean)
+  float inv_count;       // SRC 2, 3
   int act;
+  // SRC 3: like SRC 2, but the layer's output went through a 2x2 max pooling whose backward is fused in as well:
+  // dy is never written, it is recomputed per window from the pooled maxima and their gradient (see
+  // bn_reduce_pool_kernel in batchnorm.cu).  Tiles are th rows x tw columns (whole windows), tw * th == 32.
+  const float* pooled;
+  const float* dpooled;
+  int H, W, tw;
 };
 
 // staged[n][p][g][plane][64] = split(value[n][g*64 + .][p]); one tile of 64 channels x 32 pixels per block,
@@ -123,27 +130,47 @@ __global__ void __launch_bounds__(256) stage_f16_kernel(__half* __restrict__ out
                                                         float* __restrict__ partial, int C, int HW,
                                                         const unsigned int* __restrict__ max_bits,
                                                         float* __restrict__ inv_scale_out) {
+  static_assert(SRC != 3 || VEC, "the pooled source exists in the vector form only");
   __shared__ float tile[64][33];
   __shared__ float cst[5][64];   // per-channel constants of the fused sources
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int G = C >> 6;
   const int g = blockIdx.y, n = blockIdx.z;
-  const int c0 = g * 64, p0 = blockIdx.x * 32;
+  const int c0 = g * 64;
+  // pixel of local index l (0..31) of this block's tile: 32 consecutive pixels, or (SRC 3) th rows x tw columns
+  int p0 = blockIdx.x * 32, h0 = 0, w0 = 0, tw = 32, tw_shift = 5;
+  if (SRC == 3) {
+    tw = src.tw;
+    tw_shift = tw == 16 ? 4 : 3;
+    const int tiles_w = src.W / tw;
+    const int tyi = (int)blockIdx.x / tiles_w, txi = (int)blockIdx.x - tyi * tiles_w;
+    h0 = tyi * (32 >> tw_shift);
+    w0 = txi * tw;
+    p0 = 0;
+  }
+  auto pix = [&](int l) -> int { return SRC == 3 ? (h0 + (l >> tw_shift)) * src.W + w0 + (l & (tw - 1)) : p0 + l; };
   const long long base = ((long long)n * C + c0) * HW;
   // 1. the tile loads go out first: everything below overlaps their latency
-  constexpr int NV = VEC ? 2 : 8;
   float4 xq[VEC ? 2 : 1], gq[VEC ? 2 : 1];
+  float2 pm[VEC ? 2 : 1], pg[VEC ? 2 : 1];   // SRC 3: pooled maxima and their gradient of the thread's two windows
   float xv[VEC ? 1 : 8], gv[VEC ? 1 : 8];
   const int vc = threadIdx.x >> 3, vj = threadIdx.x & 7;   // VEC: channel row (and + 32), float4 column
   if (VEC) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int p = p0 + 4 * vj;
+      const int p = pix(4 * vj);
       const long long off = base + (long long)(vc + 32 * i) * HW + p;
       xq[i] = gq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pm[i] = pg[i] = make_float2(0.f, 0.f);
       if (p < HW) {
         xq[i] = *reinterpret_cast<const float4*>(src.in + off);
         if (SRC == 2) gq[i] = *reinterpret_cast<const float4*>(src.dy + off);
+        if (SRC == 3) {
+          const int hh = h0 + ((4 * vj) >> tw_shift), ww = w0 + ((4 * vj) & (tw - 1));
+          const long long po = (((long long)n * C + c0 + vc + 32 * i) * (src.H >> 1) + (hh >> 1)) * (src.W >> 1) + (ww >> 1);
+          pm[i] = *reinterpret_cast<const float2*>(src.pooled + po);
+          pg[i] = *reinterpret_cast<const float2*>(src.dpooled + po);
+        }
       }
     }
   } else {
@@ -170,7 +197,7 @@ __global__ void __launch_bounds__(256) stage_f16_kernel(__half* __restrict__ out
       } else {
         cst[2][threadIdx.x] = src.sums[c * 2] * src.inv_count;
         cst[3][threadIdx.x] = inv * inv * src.sums[c * 2 + 1] * src.inv_count;
-        cst[4][threadIdx.x] = src.act ? src.beta[c] : 0.f;
+        cst[4][threadIdx.x] = (src.act || SRC == 3) ? src.beta[c] : 0.f;
       }
     }
     __syncthreads();
@@ -181,9 +208,36 @@ __global__ void __launch_bounds__(256) stage_f16_kernel(__half* __restrict__ out
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int c = vc + 32 * i;
-      const bool ok = p0 + 4 * vj < HW;
-      float v0 = stage_value<SRC>(xq[i].x, gq[i].x, src.act, cst, c), v1 = stage_value<SRC>(xq[i].y, gq[i].y, src.act, cst, c);
-      float v2 = stage_value<SRC>(xq[i].z, gq[i].z, src.act, cst, c), v3 = stage_value<SRC>(xq[i].w, gq[i].w, src.act, cst, c);
+      const bool ok = pix(4 * vj) < HW;
+      float v0, v1, v2, v3;
+      if (SRC == 3) {
+        // own four activations and those of the vertical neighbour row (the other half of the two windows)
+        const float mu = cst[0][c], k0 = cst[1][c], zb = cst[4][c];
+        const float z0 = bn_affine(xq[i].x, mu, k0, zb), z1 = bn_affine(xq[i].y, mu, k0, zb);
+        const float z2 = bn_affine(xq[i].z, mu, k0, zb), z3 = bn_affine(xq[i].w, mu, k0, zb);
+        const float y0 = src.act ? fmaxf(z0, 0.f) : z0, y1 = src.act ? fmaxf(z1, 0.f) : z1;
+        const float y2 = src.act ? fmaxf(z2, 0.f) : z2, y3 = src.act ? fmaxf(z3, 0.f) : z3;
+        const int partner = tw >> 2;   // lane distance of the thread holding the other row of the same windows
+        const float n0 = __shfl_xor_sync(0xffffffffu, y0, partner), n1 = __shfl_xor_sync(0xffffffffu, y1, partner);
+        const float n2 = __shfl_xor_sync(0xffffffffu, y2, partner), n3 = __shfl_xor_sync(0xffffffffu, y3, partner);
+        const int ca = (y0 == pm[i].x) + (y1 == pm[i].x) + (n0 == pm[i].x) + (n1 == pm[i].x);
+        const int cb = (y2 == pm[i].y) + (y3 == pm[i].y) + (n2 == pm[i].y) + (n3 == pm[i].y);
+        const float sa = ca ? pg[i].x / (float)ca : 0.f, sb = cb ? pg[i].y / (float)cb : 0.f;
+        float g0 = (y0 == pm[i].x) ? sa : 0.f, g1 = (y1 == pm[i].x) ? sa : 0.f;
+        float g2 = (y2 == pm[i].y) ? sb : 0.f, g3 = (y3 == pm[i].y) ? sb : 0.f;
+        if (src.act) {
+          if (!(z0 >= 0.f)) g0 = 0.f;
+          if (!(z1 >= 0.f)) g1 = 0.f;
+          if (!(z2 >= 0.f)) g2 = 0.f;
+          if (!(z3 >= 0.f)) g3 = 0.f;
+        }
+        const float k1 = cst[2][c], k2 = cst[3][c];
+        v0 = k0 * (g0 - k1 - (xq[i].x - mu) * k2); v1 = k0 * (g1 - k1 - (xq[i].y - mu) * k2);
+        v2 = k0 * (g2 - k1 - (xq[i].z - mu) * k2); v3 = k0 * (g3 - k1 - (xq[i].w - mu) * k2);
+      } else {
+        v0 = stage_value<SRC>(xq[i].x, gq[i].x, src.act, cst, c); v1 = stage_value<SRC>(xq[i].y, gq[i].y, src.act, cst, c);
+        v2 = stage_value<SRC>(xq[i].z, gq[i].z, src.act, cst, c); v3 = stage_value<SRC>(xq[i].w, gq[i].w, src.act, cst, c);
+      }
       if (!ok) v0 = v1 = v2 = v3 = 0.f;
       tile[c][4 * vj + 0] = v0; tile[c][4 * vj + 1] = v1; tile[c][4 * vj + 2] = v2; tile[c][4 * vj + 3] = v3;
       if (SUM) {
@@ -199,7 +253,7 @@ __global__ void __launch_bounds__(256) stage_f16_kernel(__half* __restrict__ out
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = ty + 8 * i;
-      float v = stage_value<SRC>(xv[i], gv[i], src.act, cst, c);
+      float v = stage_value<(SRC == 3 ? 2 : SRC)>(xv[i], gv[i], src.act, cst, c);
       if (p0 + tx >= HW) v = 0.f;
       tile[c][tx] = v;
       if (SUM) {
@@ -208,53 +262,32 @@ __global__ void __launch_bounds__(256) stage_f16_kernel(__half* __restrict__ out
       }
     }
   }
-  (void)NV;
   __syncthreads();
   __half* dst = out + ((long long)n * HW * G + g) * 128;   // + p * G * 128 + plane * 64 + c
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int pl = ty + 8 * i, p = p0 + pl;
+    const int pl = ty + 8 * i, p = pix(pl);
     if (p < HW) {
-      __half h0, l0, h1, l1;
-      f16_split(tile[2 * tx][pl], scale, h0, l0);
+      __half h0_, l0, h1, l1;
+      f16_split(tile[2 * tx][pl], scale, h0_, l0);
       f16_split(tile[2 * tx + 1][pl], scale, h1, l1);
       __half2* row = reinterpret_cast<__half2*>(dst + (long long)p * G * 128);
-      row[tx] = __halves2half2(h0, h1);
+      row[tx] = __halves2half2(h0_, h1);
       row[32 + tx] = __halves2half2(l0, l1);
     }
   }
 }
 
-// dst[plane][rs][j][kc] = split(w[j*sj + kc*sc + rs]) for a filter tensor of n = J*KC*RS elements, magnitude pass
-// and re-layout in ONE launch: every block folds its share of max|w| into *bits, the blocks meet at a grid barrier
-// (an arrival counter; the grid is at most one block per SM, so all blocks are resident), then re-lay with the common
-// scale.  Two launches per filter cost 8-9 us of which ~1 us was work (20 per training step).
-__global__ void __launch_bounds__(256) filter_stage_f16_kernel(__half* __restrict__ dst, const float* __restrict__ w,
-                                                               int J, int KC, int RS, long long sj, long long sc,
-                                                               unsigned int* bits, unsigned int* arrived,
-                                                               float* __restrict__ inv_scale_out) {
-  const long long n = (long long)J * KC * RS;
-  float m = 0.f;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(w[e]));   // the KCRS block is contiguous whichever of (j, kc) is the outer axis
-  m = warp_max(m);
-  __shared__ float red[8];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-    if (m > 0.f && m < 3.0e38f) atomicMax(bits, __float_as_uint(m));
-    __threadfence();
-    atomicAdd(arrived, 1u);
-    unsigned int spins = 0;
-    while (*reinterpret_cast<volatile unsigned int*>(arrived) < gridDim.x) {
-      if (++spins > (1u << 26)) __trap();   // a scheduling assumption broke: fail instead of hanging
-    }
-    __threadfence();
-  }
-  __syncthreads();
-  const float scale = f16_scale(*reinterpret_cast<volatile unsigned int*>(bits));
+// dst[plane][rs][j][kc] = split(w[j*sj + kc*sc + rs])
+// (A single launch doing the magnitude pass, a grid barrier and the re-layout was built and measured: 11 us per filter
+//  against 4 + 5 us for the two launches below — the barrier's global round trips cost more than a launch.)
+__global__ void __launch_bounds__(256) filter_relayout_f16_kernel(__half* __restrict__ dst, const float* __restrict__ w,
+                                                                  int J, int KC, int RS, long long sj, long long sc,
+                                                                  const unsigned int* __restrict__ max_bits,
+                                                                  float* __restrict__ inv_scale_out) {
+  const float scale = f16_scale(*max_bits);
   if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
+  const long long n = (long long)J * KC * RS;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const int kc = (int)(e % KC);
     const long long t = e / KC;
@@ -301,18 +334,19 @@ static int stage_f16(void* staged, const StageSrc& src, float* sums, const unsig
   dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)(C / 64), (unsigned)N);
   const bool vec = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(src.in) & 15u) == 0 &&
                    (SRC != 2 || (reinterpret_cast<uintptr_t>(src.dy) & 15u) == 0);
+  if (SRC == 3 && (!vec || HW % 32 != 0)) return set_error("to_nhwc_f16: the pooled source needs whole 32-pixel tiles");
   if (sums) {
     const long long rows = (long long)N * grid.x;
     float* partial = nullptr;
     if (pool_alloc((void**)&partial, (uint64_t)rows * C * sizeof(float))) return 1;
     if (vec) NG_LAUNCH((stage_f16_kernel<SRC, true, true>), grid, 256, 0, out, src, partial, C, HW, bits, meta);
-    else NG_LAUNCH((stage_f16_kernel<SRC, true, false>), grid, 256, 0, out, src, partial, C, HW, bits, meta);
+    else NG_LAUNCH((stage_f16_kernel<(SRC == 3 ? 2 : SRC), true, false>), grid, 256, 0, out, src, partial, C, HW, bits, meta);
     NG_CHECK_LAUNCH();
     if (channel_partial_sum(sums, partial, rows, C)) return 1;
     pool_free(partial);
   } else {
     if (vec) NG_LAUNCH((stage_f16_kernel<SRC, false, true>), grid, 256, 0, out, src, (float*)nullptr, C, HW, bits, meta);
-    else NG_LAUNCH((stage_f16_kernel<SRC, false, false>), grid, 256, 0, out, src, (float*)nullptr, C, HW, bits, meta);
+    else NG_LAUNCH((stage_f16_kernel<(SRC == 3 ? 2 : SRC), false, false>), grid, 256, 0, out, src, (float*)nullptr, C, HW, bits, meta);
     NG_CHECK_LAUNCH();
   }
   return 0;
@@ -341,6 +375,23 @@ int to_nhwc_f16_bnbwd(void* staged, float* chan_sums, const float* dy, const flo
   src.in = x; src.dy = dy; src.gamma = gamma; src.beta = beta; src.mean = mean; src.invstd = invstd;
   src.sums = bn_sums; src.inv_count = 1.f / ((float)N * (float)HW); src.act = act;
   return stage_f16<2>(staged, src, chan_sums, bound_bits, N, C, HW);
+}
+
+int to_nhwc_f16_bnbwd_pool(void* staged, float* chan_sums, const float* dpooled, const float* pooled, const float* x,
+                           const float* gamma, const float* beta, const float* mean, const float* invstd,
+                           const float* bn_sums, int act, const unsigned int* bound_bits, int N, int C, int H, int W) {
+  if (H % 2 || W % 8 || ((H * W) % 32) != 0) return set_error("to_nhwc_f16_bnbwd_pool: needs even H, W %% 8 == 0, H*W %% 32 == 0");
+  const int tw = (W % 16 == 0) ? 16 : 8;
+  const int th = 32 / tw;
+  if (H % th) return set_error("to_nhwc_f16_bnbwd_pool: H must be a multiple of %d", th);
+  if ((reinterpret_cast<uintptr_t>(pooled) & 7u) || (reinterpret_cast<uintptr_t>(dpooled) & 7u))
+    return set_error("to_nhwc_f16_bnbwd_pool: pooled tensors must be 8-byte aligned");
+  StageSrc src;
+  memset(&src, 0, sizeof(src));
+  src.in = x; src.gamma = gamma; src.beta = beta; src.mean = mean; src.invstd = invstd;
+  src.sums = bn_sums; src.inv_count = 1.f / ((float)N * (float)H * (float)W); src.act = act;
+  src.pooled = pooled; src.dpooled = dpooled; src.H = H; src.W = W; src.tw = tw;
+  return stage_f16<3>(staged, src, chan_sums, bound_bits, N, C, H * W);
 }
 
 // ================================================================== gather kernel (fprop / dgrad)
@@ -622,14 +673,16 @@ static int launch_gather_f16(float* out, const void* act, const float* filt, con
   int rc = 0;
   const void* act_s = act_is_staged ? act : act_t;
   if (!act_is_staged) rc = to_nhwc_f16(act_t, reinterpret_cast<const float*>(act), nullptr, n_img, KC, AH * AW, nullptr);
-  float* wmeta = staged_meta(wt, filt_elems);   // [0] 1/scale, [1] bits of max|w|, [2] arrival counter
-  if (rc == 0 && cudaMemsetAsync(wmeta + 1, 0, 8, g_stream) != cudaSuccess) rc = set_error("cudaMemsetAsync failed");
+  float* wmeta = staged_meta(wt, filt_elems);   // [0] 1/scale, [1] bits of max|w|
   if (rc == 0) {
-    const int sms = g_sm_count > 0 ? g_sm_count : 148;
-    int g = (int)ceil_div(filt_elems, 256 * 8);
-    if (g > sms) g = sms;
-    NG_LAUNCH(filter_stage_f16_kernel, g, 256, 0, reinterpret_cast<__half*>(wt), filt, J, KC, RS, sj, sc,
-              reinterpret_cast<unsigned int*>(wmeta + 1), reinterpret_cast<unsigned int*>(wmeta + 2), wmeta);
+    // max|w| over the filter tensor: the KCRS block is contiguous whichever of (j, kc) is the outer axis
+    rc = launch_absmax(reinterpret_cast<unsigned int*>(wmeta + 1), filt, filt_elems);
+  }
+  if (rc == 0) {
+    int g = (int)ceil_div(filt_elems, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    NG_LAUNCH(filter_relayout_f16_kernel, g, 256, 0, reinterpret_cast<__half*>(wt), filt, J, KC, RS, sj, sc,
+              (const unsigned int*)(wmeta + 1), wmeta);
     const int G = KC / 64;
     const uint64_t pix = (uint64_t)KC * 4u;   // bytes per staged pixel
     const uint64_t dims[5] = {64u, (uint64_t)AW, (uint64_t)AH, (uint64_t)n_img, (uint64_t)(2 * G)};

@@ -606,9 +606,14 @@ def _stage_nhwc(buf, engine, channel_sums=False, sums_out=None):
             _lib().ng_conv2d_stage_f16_bn(out.ptr, x.ptr, gamma.ptr, beta.ptr, mean.ptr, invstd.ptr, absmax.ptr,
                                           n, c, hw, act)
         elif kind == "bn_bwd":
-            dy, x, gamma, beta, mean, invstd, bn_sums, act, bound = buf.source
-            _lib().ng_conv2d_stage_f16_bnbwd(out.ptr, sums_ptr, dy.ptr, x.ptr, gamma.ptr, beta.ptr if act else 0,
-                                             mean.ptr, invstd.ptr, bn_sums.ptr, bound.ptr, n, c, hw, act)
+            dy, x, gamma, beta, mean, invstd, bn_sums, act, bound, pooled = buf.source
+            if pooled is not None and isinstance(dy, LazyBuffer) and dy.pending:
+                dpool, pool_out, h, w = pooled
+                _lib().ng_conv2d_stage_f16_bnbwd_pool(out.ptr, sums_ptr, dpool.ptr, pool_out.ptr, x.ptr, gamma.ptr, beta.ptr,
+                                                      mean.ptr, invstd.ptr, bn_sums.ptr, bound.ptr, n, c, h, w, act)
+            else:
+                _lib().ng_conv2d_stage_f16_bnbwd(out.ptr, sums_ptr, dy.ptr, x.ptr, gamma.ptr, beta.ptr if act else 0,
+                                                 mean.ptr, invstd.ptr, bn_sums.ptr, bound.ptr, n, c, hw, act)
         else:
             known = getattr(buf, "absmax", None)
             _lib().ng_conv2d_stage_f16(out.ptr, buf.ptr, sums_ptr, known.ptr if known is not None else 0, n, c, hw)
@@ -856,13 +861,22 @@ class MaxPool2d(Function):
     def backward(ctx, grad_output):
         input, out, (ph, pw) = ctx.saved_tensors
         n, c, h, w = input.shape
-        dx = DeviceBuffer(input.shape)
         if isinstance(input, LazyBuffer) and input.pending and input.kind == "bn_fwd":
             x, gamma, beta, mean, invstd, act, _ = input.source
-            _lib().ng_maxpool2d_bwd_bn(dx.ptr, grad_output.ptr, x.ptr, out.ptr, gamma.ptr, beta.ptr, mean.ptr, invstd.ptr,
-                                       n * c, c, h, w, ph, pw, act)
-        else:
-            _lib().ng_maxpool2d_bwd(dx.ptr, grad_output.ptr, input.ptr, out.ptr, n * c, h, w, ph, pw)
+
+            def pool_bwd(ptr, dy=grad_output):
+                _lib().ng_maxpool2d_bwd_bn(ptr, dy.ptr, x.ptr, out.ptr, gamma.ptr, beta.ptr, mean.ptr, invstd.ptr,
+                                           n * c, c, h, w, ph, pw, act)
+
+            if (ph, pw) == (2, 2) and h % 2 == 0 and w % 8 == 0 and (h * w) % 32 == 0 and h % (32 // (16 if w % 16 == 0 else 8)) == 0:
+                # the gradient of the (never written) BatchNorm output stays a recipe too: BatchNorm's backward
+                # reduction and the staging pass of the convolution below recompute it per window
+                return LazyBuffer(input.shape, pool_bwd, "pool_bwd", (grad_output, out, input))
+            dx = DeviceBuffer(input.shape)
+            pool_bwd(dx.ptr)
+            return dx
+        dx = DeviceBuffer(input.shape)
+        _lib().ng_maxpool2d_bwd(dx.ptr, grad_output.ptr, input.ptr, out.ptr, n * c, h, w, ph, pw)
         return dx
 
 
@@ -1084,15 +1098,25 @@ class BatchNorm2d(Function):
             if _bn_split_ok(input.shape) and _needs(ctx, 0):
                 # reductions now; the dx pass only if somebody other than an FP16x3 convolution reads dx
                 bn_sums, bound = DeviceBuffer((2 * c + 1,)), DeviceBuffer((1,))
-                _lib().ng_bn2d_act_bwd_sums(dgamma.ptr, dbeta.ptr, bn_sums.ptr, bound.ptr, grad_output.ptr, input.ptr,
-                                            gamma.ptr, beta.ptr, save_mean.ptr, save_invstd.ptr, n, c, hw, act)
+                pooled = None
+                if (isinstance(grad_output, LazyBuffer) and grad_output.pending and grad_output.kind == "pool_bwd"
+                        and grad_output.source[2] is out):
+                    # the incoming gradient is the recipe of a 2x2 max-pool backward over THIS layer's output: fused
+                    dpool, pool_out, _ = grad_output.source
+                    pooled = (dpool, pool_out, input.shape[2], input.shape[3])
+                    _lib().ng_bn2d_act_bwd_sums_pool(dgamma.ptr, dbeta.ptr, bn_sums.ptr, bound.ptr, dpool.ptr, pool_out.ptr,
+                                                     input.ptr, gamma.ptr, beta.ptr, save_mean.ptr, save_invstd.ptr,
+                                                     n, c, input.shape[2], input.shape[3], act)
+                else:
+                    _lib().ng_bn2d_act_bwd_sums(dgamma.ptr, dbeta.ptr, bn_sums.ptr, bound.ptr, grad_output.ptr, input.ptr,
+                                                gamma.ptr, beta.ptr, save_mean.ptr, save_invstd.ptr, n, c, hw, act)
 
                 def dx_pass(ptr, dy=grad_output, x=input):
                     _lib().ng_bn2d_act_bwd_dx(ptr, dy.ptr, x.ptr, gamma.ptr, beta.ptr, save_mean.ptr, save_invstd.ptr,
                                               bn_sums.ptr, n, c, hw, act)
 
                 dx = LazyBuffer(input.shape, dx_pass, "bn_bwd",
-                                (grad_output, input, gamma, beta, save_mean, save_invstd, bn_sums, act, bound))
+                                (grad_output, input, gamma, beta, save_mean, save_invstd, bn_sums, act, bound, pooled))
                 dx.absmax = bound
             else:
                 dx = DeviceBuffer(input.shape)

@@ -38,6 +38,7 @@
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
   unsigned x, y, z;

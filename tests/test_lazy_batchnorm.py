@@ -206,3 +206,86 @@ def test_fused_maxpool_matches_pooling_the_materialised_tensor_emulated(act):
 def test_fused_maxpool_matches_pooling_the_materialised_tensor(shape, act):
     H.use_cuda_library()
     _check_fused_maxpool(shape, act)
+
+
+def _pooled_setup(shape, act, seed):
+    """A conv -> BatchNorm(+ReLU) -> MaxPool2d(2) backward: x (layer input), the pooled maxima, their gradient,
+    and the materialised chain (pool backward -> BatchNorm sums -> dx) to compare the fused kernels with."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    lib = B.lib()
+    n, c, h, w = shape
+    hw = h * w
+    host, dev = _setup(n, c, h, w, seed=seed)
+    xq = np.round(host["x"] * 2) / 2   # tie-rich
+    dev["x"] = DeviceBuffer(xq.shape, hostbuf=xq.astype(np.float32))
+    mean, invstd, absmax = DeviceBuffer((c,)), DeviceBuffer((c,)), DeviceBuffer((1,))
+    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, mean.ptr, invstd.ptr, absmax.ptr,
+                              n, c, hw, 1e-5, 0.1, act)
+    oh, ow = h // 2, w // 2
+    pooled = DeviceBuffer((n, c, oh, ow))
+    lib.ng_maxpool2d_fwd_bn(pooled.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, mean.ptr, invstd.ptr, n * c, c, h, w, 2, 2, act)
+    g = (np.random.RandomState(seed + 1).randn(n, c, oh, ow) * 0.1).astype(np.float32)
+    dpool = DeviceBuffer(g.shape, hostbuf=g)
+    # materialised chain
+    dy = DeviceBuffer((n, c, h, w))
+    lib.ng_maxpool2d_bwd_bn(dy.ptr, dpool.ptr, dev["x"].ptr, pooled.ptr, dev["gamma"].ptr, dev["beta"].ptr, mean.ptr, invstd.ptr,
+                            n * c, c, h, w, 2, 2, act)
+    dg1, db1, sums1, bound1, dx1 = DeviceBuffer((c,)), DeviceBuffer((c,)), DeviceBuffer((2 * c + 1,)), DeviceBuffer((1,)), DeviceBuffer((n, c, h, w))
+    lib.ng_bn2d_act_bwd_sums(dg1.ptr, db1.ptr, sums1.ptr, bound1.ptr, dy.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr,
+                             mean.ptr, invstd.ptr, n, c, hw, act)
+    lib.ng_bn2d_act_bwd_dx(dx1.ptr, dy.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, mean.ptr, invstd.ptr, sums1.ptr,
+                           n, c, hw, act)
+    return lib, dev, (mean, invstd), (pooled, dpool), (dg1, db1, sums1, bound1, dx1)
+
+
+def _check_pooled_sums(shape, act):
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    n, c, h, w = shape
+    lib, dev, (mean, invstd), (pooled, dpool), (dg1, db1, sums1, bound1, dx1) = _pooled_setup(shape, act, seed=3 * c + act)
+    dg2, db2, sums2, bound2 = DeviceBuffer((c,)), DeviceBuffer((c,)), DeviceBuffer((2 * c + 1,)), DeviceBuffer((1,))
+    lib.ng_bn2d_act_bwd_sums_pool(dg2.ptr, db2.ptr, sums2.ptr, bound2.ptr, dpool.ptr, pooled.ptr, dev["x"].ptr, dev["gamma"].ptr,
+                                  dev["beta"].ptr, mean.ptr, invstd.ptr, n, c, h, w, act)
+    # same terms, another summation order (windows instead of rows): compare on the scale of sum |term|
+    for name, a, b in (("dgamma", dg2, dg1), ("dbeta", db2, db1), ("sums", sums2, sums1)):
+        av, bv = a.numpy().astype(np.float64), b.numpy().astype(np.float64)
+        np.testing.assert_allclose(av, bv, rtol=1e-4, atol=1e-5 * max(float(np.abs(bv).max()), 1e-30), err_msg=name)
+    bnd = float(bound2.numpy().view(np.float32)[0])
+    dxmax = float(np.abs(dx1.numpy()).max())
+    assert dxmax <= bnd * 1.001 <= 32 * dxmax, (bnd, dxmax)
+    return lib, dev, mean, invstd, pooled, dpool, sums2, bound2, dx1
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_bn_backward_sums_with_fused_maxpool_backward_emulated(act):
+    H.use_emulated_library()
+    _check_pooled_sums((2, 6, 4, 8), act)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 6, 4, 8), (16, 64, 32, 32), (8, 128, 16, 16), (5, 192, 8, 8), (3, 64, 4, 24)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_bn_backward_with_fused_maxpool_backward(shape, act):
+    """conv -> BatchNorm2d (+ReLU) -> MaxPool2d(2) backward without ever writing the gradient of the BatchNorm output:
+    reduction (ng_bn2d_act_bwd_sums_pool) and, for 64-multiple channel counts, the staged FP16-pair copy of dx
+    (ng_conv2d_stage_f16_bnbwd_pool) against the materialised chain pool backward -> sums -> dx."""
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    H.use_cuda_library()
+    n, c, h, w = shape
+    lib, dev, mean, invstd, pooled, dpool, sums2, bound2, dx1 = _check_pooled_sums(shape, act)
+    if c % 64:
+        return
+    hw = h * w
+    staged, chan = DeviceBuffer((n * c * hw + 16,)), DeviceBuffer((c,))
+    lib.ng_conv2d_stage_f16_bnbwd_pool(staged.ptr, chan.ptr, dpool.ptr, pooled.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr,
+                                       mean.ptr, invstd.ptr, sums2.ptr, bound2.ptr, n, c, h, w, act)
+    got, inv_scale = _decode(staged, n, c, hw)
+    dx = dx1.numpy().astype(np.float64).reshape(n, c, hw)
+    dmax = np.abs(dx).max()
+    assert 2.0 ** 9 <= dmax / inv_scale < 2.0 ** 15
+    err = np.abs(got - dx)
+    # (sums2 and the materialised chain's sums differ by a summation order: 1e-5 of the scale on top of the FP16 pairs)
+    assert np.all(err <= np.maximum(np.abs(dx) * 2.0 ** -20, dmax * 2e-5)), float(err.max() / dmax)
+    np.testing.assert_allclose(chan.numpy(), dx.sum(axis=(0, 2)), rtol=0, atol=1e-4 * float(np.abs(dx).sum(axis=(0, 2)).max()),
+                               err_msg="channel sums of the fused dx staging")

@@ -7,6 +7,9 @@ for m in fp32 tf32 simt; do
 done
 ncu --set full --clock-control none --import-source on -k regex:umma_conv_gather_f16 -c 10 -o gpurun_out/prof_f16_gather_r2 -f python bench.py --no-tf32 --no-extras --steps 2 --warmup 3 > gpurun_out/r2_ncu_f1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:umma_conv_wgrad_f16 -c 5 -o gpurun_out/prof_f16_wgrad_r2 -f python bench.py --no-tf32 --no-extras --steps 2 --warmup 3 > gpurun_out/r2_ncu_f2.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:stage_f16|bn_reduce|bn_apply|bn_bwd_dx|pool_fwd|pool_bwd|multi_update|absmax" -c 60 -o gpurun_out/prof_membound_r2 -f python bench.py --no-tf32 --no-extras --steps 2 --warmup 3 > gpurun_out/r2_ncu_f3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:smallc -c 2 -o gpurun_out/prof_smallc_r2 -f python bench.py --no-tf32 --no-extras --steps 2 --warmup 3 > gpurun_out/r2_ncu_f4.log 2>&1
-ls -la gpurun_out/*_r2.ncu-rep
+ncu --set full --clock-control none -k "regex:stage_f16|bn_reduce|bn_apply|bn_bwd_dx|pool_fwd|pool_bwd|multi_update|filter_stage" -c 36 -o gpurun_out/prof_membound_r2 -f python bench.py --no-tf32 --no-extras --steps 2 --warmup 3 > gpurun_out/r2_ncu_f3.log 2>&1
+ncu --set full --clock-control none -k regex:smallc -c 2 -o gpurun_out/prof_smallc_r2 -f python bench.py --no-tf32 --no-extras --steps 2 --warmup 3 > gpurun_out/r2_ncu_f4.log 2>&1
+# gpurun copies back at most 64 MiB: summarise on the box, keep only the two tensor-core captures
+for k in f16_gather f16_wgrad membound smallc; do python tools/ncu_summary.py gpurun_out/prof_${k}_r2.ncu-rep > gpurun_out/r2_ncu_$k.txt 2>&1; done
+rm -f gpurun_out/prof_membound_r2.ncu-rep gpurun_out/prof_smallc_r2.ncu-rep
+ls -la gpurun_out/ | head -40; du -sh gpurun_out
