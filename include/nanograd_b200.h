@@ -167,8 +167,10 @@ int ng_onehot(uint64_t out, uint64_t labels, int64_t rows, int64_t classes);
  *                at twice the TF32 rate; taken for stride-1 layers whose channel counts are both multiples
  *                of 64, other layers follow NG_F_TF32X3 when that is set as well.
  *   NG_F_STAGE_F16  (ng_conv2d_stage_nhwc*) make the FP16x3 staged copy: dst holds N*C*HW*4 + 64 bytes. */
+/*   NG_F_W_STAGED (FP16x3 engine only) the w argument of ng_conv2d_fprop / ng_conv2d_dgrad is the staged filter copy
+ *                made by ng_conv2d_stage_filters_f16 for that pass. */
 enum { NG_F_RELU = 1, NG_F_TF32 = 2, NG_F_TF32X3 = 4, NG_F_TC_FORCE = 8, NG_F_X_NHWC = 16, NG_F_DY_NHWC = 32,
-       NG_F_F16X3 = 64, NG_F_STAGE_F16 = 128 };
+       NG_F_F16X3 = 64, NG_F_STAGE_F16 = 128, NG_F_W_STAGED = 256 };
 /* C[M,N] = op(A) @ op(B) (+ bias[N]) ; row-major; op = transpose when the flag is set.
  * replaces matmul_op, ops_gpu.py:214-232, and the perm+matmul chain in MatMul.backward,
  * ops_gpu.py:452-459.  batch > 1: equally strided batches of A, B and C.
@@ -216,6 +218,9 @@ int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t 
  * These replace, for the conv -> BatchNorm2d -> ReLU -> conv chains of module.py:356-391 / 476, the second
  * half of the ~30 primitive ops the reference composes per BatchNorm layer. */
 int ng_conv2d_stage_f16(uint64_t dst, uint64_t src, uint64_t sums, uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW);
+/* Both FP16x3 filter layouts of a KCRS tensor w[K][C][RS] from one pass (the weights of a step serve its forward and
+ * its backward): dst_fprop = [hi|lo][rs][k][c], dst_dgrad (optional) = [hi|lo][rs][c][k], each K*C*RS*4 + 64 bytes. */
+int ng_conv2d_stage_filters_f16(uint64_t dst_fprop, uint64_t dst_dgrad, uint64_t w, int K, int C, int RS);
 int ng_conv2d_stage_f16_bn(uint64_t dst, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t mean, uint64_t invstd,
                            uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW, int act);
 int ng_conv2d_stage_f16_bnbwd(uint64_t dst, uint64_t chan_sums, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta,

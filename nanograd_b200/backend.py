@@ -75,6 +75,7 @@ _PROTOTYPES = {
     "ng_maxpool2d_fwd_bn": [u64] * 6 + [i64, i32, i32, i32, i32, i32, i32],
     "ng_maxpool2d_bwd_bn": [u64] * 8 + [i64, i32, i32, i32, i32, i32, i32],
     "ng_conv2d_stage_f16": [u64, u64, u64, u64, i64, i64, i64],
+    "ng_conv2d_stage_filters_f16": [u64, u64, u64, i32, i32, i32],
     "ng_conv2d_stage_f16_bn": [u64] * 7 + [i64, i64, i64, i32],
     "ng_conv2d_stage_f16_bnbwd": [u64] * 10 + [i64, i64, i64, i32],
     "ng_bn2d_act_fwd_stats": [u64] * 8 + [i64, i64, i64, f32, f32, i32],
@@ -145,7 +146,7 @@ F_RELU, F_TF32, F_TF32X3 = 1, 2, 4
 #   "fp32_tf32x3"     the default selection without the FP16x3 engine (round-1 behaviour).
 #   "tf32"  (opt-in)  tensor cores with plain TF32 inputs / FP32 accumulation (parity bar rtol 1e-2).
 # Selected with NANOGRAD_B200_MATH (or the reference-survey spelling NANOGRAD_TF32=1) or set_math_mode().
-F_TC_FORCE, F_X_NHWC, F_DY_NHWC, F_F16X3, F_STAGE_F16 = 8, 16, 32, 64, 128
+F_TC_FORCE, F_X_NHWC, F_DY_NHWC, F_F16X3, F_STAGE_F16, F_W_STAGED = 8, 16, 32, 64, 128, 256
 _MATH_MODES = {"fp32": F_F16X3 | F_TF32X3, "simt": 0, "tf32x3": F_TF32X3 | F_TC_FORCE, "tf32": F_TF32,
                "fp32_tf32x3": F_TF32X3, "f16x3": F_F16X3 | F_TF32X3 | F_TC_FORCE}
 _math_flags = _MATH_MODES["tf32" if os.environ.get("NANOGRAD_TF32", "0") == "1"

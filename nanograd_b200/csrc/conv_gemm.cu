@@ -995,13 +995,13 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
   const int engine = conv_engine(flags, flops, C, K, R * S, stride);
   if (engine == 2)
     rc = umma::conv_fprop_f16(p.out, p.a, p.b, p.bias, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW, p.relu,
-                              (flags & NG_F_X_NHWC) ? 1 : 0);
+                              (flags & NG_F_X_NHWC) ? 1 : 0, (flags & NG_F_W_STAGED) ? 1 : 0);
   else if (engine == 1)
     rc = umma::conv_fprop_tf32(p.out, p.a, p.b, p.bias, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW, p.relu,
                                (flags & NG_F_TF32) ? 0 : 1, (flags & NG_F_X_NHWC) ? 1 : 0);
 #endif
-  if (rc < 0 && (flags & NG_F_X_NHWC))
-    rc = set_error("ng_conv2d_fprop: NG_F_X_NHWC given but this shape does not take the tensor-core kernel");
+  if (rc < 0 && (flags & (NG_F_X_NHWC | NG_F_W_STAGED)))
+    rc = set_error("ng_conv2d_fprop: staged operands given but this shape does not take the tensor-core kernel");
   if (rc < 0 && C <= 4 && R == 3 && S == 3 && stride == 1 && OW % 4 == 0 && (y & 15u) == 0 &&
       (long long)N * OH * OW >= 4096)
     rc = launch_fprop_smallc(p, N, C, H, W, K, OH, OW, pad_t, pad_l);
@@ -1048,13 +1048,13 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
   const int engine = conv_engine(flags, flops, C, K, R * S, stride);
   if (engine == 2)
     rc = umma::conv_dgrad_f16(p.out, p.a, p.b, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW,
-                              (flags & NG_F_DY_NHWC) ? 1 : 0);
+                              (flags & NG_F_DY_NHWC) ? 1 : 0, (flags & NG_F_W_STAGED) ? 1 : 0);
   else if (engine == 1)
     rc = umma::conv_dgrad_tf32(p.out, p.a, p.b, N, C, H, W, K, R, S, stride, pad_t, pad_l, OH, OW,
                                (flags & NG_F_TF32) ? 0 : 1, (flags & NG_F_DY_NHWC) ? 1 : 0);
 #endif
-  if (rc < 0 && (flags & NG_F_DY_NHWC))
-    rc = set_error("ng_conv2d_dgrad: NG_F_DY_NHWC given but this shape does not take the tensor-core kernel");
+  if (rc < 0 && (flags & (NG_F_DY_NHWC | NG_F_W_STAGED)))
+    rc = set_error("ng_conv2d_dgrad: staged operands given but this shape does not take the tensor-core kernel");
   if (rc < 0) rc = launch_conv_gather(p, stride > 1);
   prof_end(tok);
   return rc;
@@ -1110,6 +1110,17 @@ int ng_conv2d_stage_nhwc_sum(uint64_t dst, uint64_t src, uint64_t sums, int64_t 
 #else
   (void)dst; (void)src; (void)sums; (void)N; (void)C; (void)HW; (void)flags;
   return set_error("ng_conv2d_stage_nhwc_sum: the tensor-core path does not exist in the emulation build");
+#endif
+}
+
+int ng_conv2d_stage_filters_f16(uint64_t dst_fprop, uint64_t dst_dgrad, uint64_t w, int K, int C, int RS) {
+  NG_ENSURE_INIT();
+#ifndef NG_EMU
+  NG_REQUIRE(K > 0 && C > 0 && RS > 0 && dst_fprop != 0, "ng_conv2d_stage_filters_f16: bad arguments");
+  return umma::stage_filters_f16(dptr<void>(dst_fprop), dst_dgrad ? dptr<void>(dst_dgrad) : nullptr, dptr<const float>(w), K, C, RS);
+#else
+  (void)dst_fprop; (void)dst_dgrad; (void)w; (void)K; (void)C; (void)RS;
+  return set_error("ng_conv2d_stage_filters_f16: the tensor-core path does not exist in the emulation build");
 #endif
 }
 

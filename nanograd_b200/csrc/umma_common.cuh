@@ -412,10 +412,12 @@ int to_nhwc_f16_bnbwd_pool(void* staged, float* chan_sums, const float* dpooled,
 int to_nhwc_f16_bnbwd(void* staged, float* chan_sums, const float* dy, const float* x, const float* gamma,
                       const float* beta, const float* mean, const float* invstd, const float* bn_sums, int act,
                       const unsigned int* bound_bits, int N, int C, int HW);
+// w_is_staged: `w` is the stage_filters_f16 copy for that pass (fprop: staged_f, dgrad: staged_d)
 int conv_fprop_f16(float* y, const void* x, const float* w, const float* bias, int N, int C, int H, int W, int K, int R,
-                   int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x_is_staged);
+                   int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x_is_staged, int w_is_staged);
 int conv_dgrad_f16(float* dx, const void* dy, const float* w, int N, int C, int H, int W, int K, int R, int S,
-                   int stride, int pad_t, int pad_l, int OH, int OW, int dy_is_staged);
+                   int stride, int pad_t, int pad_l, int OH, int OW, int dy_is_staged, int w_is_staged);
+int stage_filters_f16(void* staged_f, void* staged_d, const float* w, int K, int C, int RS);
 int conv_wgrad_f16(float* dw, const void* dy, const void* x, int N, int C, int H, int W, int K, int R, int S,
                    int stride, int pad_t, int pad_l, int OH, int OW, int x_is_staged, int dy_is_staged);
 // to_nhwc plus sums[c] = sum over (n, p) of in[n][c][p] (the bias gradient when `in` is dy)

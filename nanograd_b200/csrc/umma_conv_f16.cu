@@ -311,6 +311,37 @@ static int launch_absmax(unsigned int* bits, const float* in, long long n) {
   return 0;
 }
 
+// Both staged layouts of one KCRS filter tensor in one pass over it (the weights are the same for the forward and
+// the backward of a step, so the layer stages them once, at the forward): fprop reads [plane][rs][k][c],
+// dgrad [plane][rs][c][k].  One thread per (k, c, rs) source element, read in storage order.
+__global__ void __launch_bounds__(256) filter_relayout2_f16_kernel(__half* __restrict__ dst_f, __half* __restrict__ dst_d,
+                                                                   const float* __restrict__ w, int K, int C, int RS,
+                                                                   const unsigned int* __restrict__ max_bits,
+                                                                   float* __restrict__ inv_f, float* __restrict__ inv_d) {
+  const float scale = f16_scale(*max_bits);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *inv_f = 1.f / scale;
+    if (dst_d) *inv_d = 1.f / scale;
+  }
+  const long long n = (long long)K * C * RS;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int rs = (int)(e % RS);
+    const long long t = e / RS;
+    const int c = (int)(t % C);
+    const int k = (int)(t / C);
+    __half h, l;
+    f16_split(w[e], scale, h, l);
+    const long long ef = ((long long)rs * K + k) * C + c;
+    dst_f[ef] = h;
+    dst_f[n + ef] = l;
+    if (dst_d) {
+      const long long ed = ((long long)rs * C + c) * K + k;
+      dst_d[ed] = h;
+      dst_d[n + ed] = l;
+    }
+  }
+}
+
 static inline float* staged_meta(void* staged, long long n_elems) {
   return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(staged) + n_elems * 4);
 }
@@ -392,6 +423,20 @@ int to_nhwc_f16_bnbwd_pool(void* staged, float* chan_sums, const float* dpooled,
   src.sums = bn_sums; src.inv_count = 1.f / ((float)N * (float)H * (float)W); src.act = act;
   src.pooled = pooled; src.dpooled = dpooled; src.H = H; src.W = W; src.tw = tw;
   return stage_f16<3>(staged, src, chan_sums, bound_bits, N, C, H * W);
+}
+
+// Stage the filters of a layer for fprop (and, with staged_d, for dgrad): each buffer holds K*C*RS*4 + 64 bytes.
+int stage_filters_f16(void* staged_f, void* staged_d, const float* w, int K, int C, int RS) {
+  const long long n = (long long)K * C * RS;
+  float* mf = staged_meta(staged_f, n);
+  float* md = staged_d ? staged_meta(staged_d, n) : nullptr;
+  if (launch_absmax(reinterpret_cast<unsigned int*>(mf + 1), w, n)) return 1;
+  int g = (int)ceil_div(n, 256);
+  if (g > 148 * 8) g = 148 * 8;
+  NG_LAUNCH(filter_relayout2_f16_kernel, g, 256, 0, reinterpret_cast<__half*>(staged_f),
+            reinterpret_cast<__half*>(staged_d), w, K, C, RS, (const unsigned int*)(mf + 1), mf, md);
+  NG_CHECK_LAUNCH();
+  return 0;
 }
 
 // ================================================================== gather kernel (fprop / dgrad)
@@ -628,7 +673,8 @@ static uint32_t* debug_words(bool* debug) {
 // `filt` are the KCRS filters addressed as filt[j*sj + kc*sc + rs]; the output is [n_img, J, OH, OW] NCHW FP32.
 static int launch_gather_f16(float* out, const void* act, const float* filt, const float* bias, int n_img, int KC,
                              int AH, int AW, int J, int R, int S, long long sj, long long sc, int OH, int OW,
-                             const int* tap_dy, const int* tap_dx, int relu, int act_is_staged) {
+                             const int* tap_dy, const int* tap_dx, int relu, int act_is_staged,
+                             const void* filt_staged) {
   const int RS = R * S;
   GatherF16P p;
   memset(&p, 0, sizeof(p));
@@ -667,22 +713,25 @@ static int launch_gather_f16(float* out, const void* act, const float* filt, con
   const long long act_elems = (long long)n_img * KC * AH * AW;
   const long long filt_elems = (long long)RS * J * KC;
   void* act_t = nullptr;
-  void* wt = nullptr;
+  void* wt_own = nullptr;
   if (!act_is_staged && pool_alloc(&act_t, (uint64_t)act_elems * 4 + 64)) return 1;
-  if (pool_alloc(&wt, (uint64_t)filt_elems * 4 + 64)) { pool_free(act_t); return 1; }
+  if (!filt_staged && pool_alloc(&wt_own, (uint64_t)filt_elems * 4 + 64)) { pool_free(act_t); return 1; }
+  void* wt = filt_staged ? const_cast<void*>(filt_staged) : wt_own;
   int rc = 0;
   const void* act_s = act_is_staged ? act : act_t;
   if (!act_is_staged) rc = to_nhwc_f16(act_t, reinterpret_cast<const float*>(act), nullptr, n_img, KC, AH * AW, nullptr);
   float* wmeta = staged_meta(wt, filt_elems);   // [0] 1/scale, [1] bits of max|w|
-  if (rc == 0) {
+  if (rc == 0 && !filt_staged) {
     // max|w| over the filter tensor: the KCRS block is contiguous whichever of (j, kc) is the outer axis
     rc = launch_absmax(reinterpret_cast<unsigned int*>(wmeta + 1), filt, filt_elems);
+    if (rc == 0) {
+      int g = (int)ceil_div(filt_elems, 256);
+      if (g > 148 * 8) g = 148 * 8;
+      NG_LAUNCH(filter_relayout_f16_kernel, g, 256, 0, reinterpret_cast<__half*>(wt), filt, J, KC, RS, sj, sc,
+                (const unsigned int*)(wmeta + 1), wmeta);
+    }
   }
   if (rc == 0) {
-    int g = (int)ceil_div(filt_elems, 256);
-    if (g > 148 * 8) g = 148 * 8;
-    NG_LAUNCH(filter_relayout_f16_kernel, g, 256, 0, reinterpret_cast<__half*>(wt), filt, J, KC, RS, sj, sc,
-              (const unsigned int*)(wmeta + 1), wmeta);
     const int G = KC / 64;
     const uint64_t pix = (uint64_t)KC * 4u;   // bytes per staged pixel
     const uint64_t dims[5] = {64u, (uint64_t)AW, (uint64_t)AH, (uint64_t)n_img, (uint64_t)(2 * G)};
@@ -725,30 +774,30 @@ static int launch_gather_f16(float* out, const void* act, const float* filt, con
       fprintf(stderr, "[umma f16] sync: %s ; dbg: %08x %08x %08x\n", cudaGetErrorString(e2), p.dbg[0], p.dbg[1], p.dbg[2]);
     }
   }
-  pool_free(wt);
+  pool_free(wt_own);
   pool_free(act_t);
   return rc;
 }
 
 int conv_fprop_f16(float* y, const void* x, const float* w, const float* bias, int N, int C, int H, int W, int K, int R,
-                   int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x_is_staged) {
+                   int S, int stride, int pad_t, int pad_l, int OH, int OW, int relu, int x_is_staged, int w_is_staged) {
   if (stride != 1 || !f16x3_supported(C, K, R * S)) return -1;
   int dy[64], dx[64];
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) { dy[r * S + s] = r - pad_t; dx[r * S + s] = s - pad_l; }
   return launch_gather_f16(y, x, w, bias, N, C, H, W, K, R, S, (long long)C * R * S, (long long)R * S, OH, OW, dy, dx,
-                           relu, x_is_staged);
+                           relu, x_is_staged, w_is_staged ? w : nullptr);
 }
 
 int conv_dgrad_f16(float* dx_out, const void* dyv, const float* w, int N, int C, int H, int W, int K, int R, int S,
-                   int stride, int pad_t, int pad_l, int OH, int OW, int dy_is_staged) {
+                   int stride, int pad_t, int pad_l, int OH, int OW, int dy_is_staged, int w_is_staged) {
   if (stride != 1 || !f16x3_supported(C, K, R * S)) return -1;
   int dy[64], dx[64];
   // dx[n,c,y,x] = sum_{k,r,s} dy[n,k,y+pt-r,x+pl-s] * w[k,c,r,s]
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) { dy[r * S + s] = pad_t - r; dx[r * S + s] = pad_l - s; }
   return launch_gather_f16(dx_out, dyv, w, nullptr, N, K, OH, OW, C, R, S, (long long)R * S, (long long)C * R * S, H, W,
-                           dy, dx, 0, dy_is_staged);
+                           dy, dx, 0, dy_is_staged, w_is_staged ? w : nullptr);
 }
 
 // ================================================================== wgrad kernel

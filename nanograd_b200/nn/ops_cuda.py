@@ -630,22 +630,35 @@ def _stage_nhwc(buf, engine, channel_sums=False, sums_out=None):
     return (out, None) if channel_sums else out
 
 
-def _conv2d_forward(x, w, bias, stride, padding, flags=0, x_nhwc=None):
+def _conv2d_forward(x, w, bias, stride, padding, flags=0, x_nhwc=None, w_staged=None):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x.shape, w.shape, stride, padding)
     y = DeviceBuffer((n, k, oh, ow))
     src, extra = (x_nhwc, B.F_X_NHWC) if x_nhwc is not None else (x, 0)
-    _lib().ng_conv2d_fprop(y.ptr, src.ptr, w.ptr, bias.ptr if bias is not None else 0,
-                           n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, flags | B.math_flags() | extra)
+    wsrc, wextra = (w_staged, B.F_W_STAGED) if w_staged is not None else (w, 0)
+    _lib().ng_conv2d_fprop(y.ptr, src.ptr, wsrc.ptr, bias.ptr if bias is not None else 0,
+                           n, c, h, wd, k, r, s, stride, pt, pl, oh, ow, flags | B.math_flags() | extra | wextra)
     return y
 
 
-def _conv2d_dgrad(dy, w, x_shape, stride, padding, dy_nhwc=None):
+def _conv2d_dgrad(dy, w, x_shape, stride, padding, dy_nhwc=None, w_staged=None):
     n, c, h, wd, k, r, s, oh, ow, pt, pl = _conv_geometry(x_shape, w.shape, stride, padding)
     dx = DeviceBuffer(x_shape)
     src, extra = (dy_nhwc, B.F_DY_NHWC) if dy_nhwc is not None else (dy, 0)
-    _lib().ng_conv2d_dgrad(dx.ptr, src.ptr, w.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow,
-                           B.math_flags() | extra)
+    wsrc, wextra = (w_staged, B.F_W_STAGED) if w_staged is not None else (w, 0)
+    _lib().ng_conv2d_dgrad(dx.ptr, src.ptr, wsrc.ptr, n, c, h, wd, k, r, s, stride, pt, pl, oh, ow,
+                           B.math_flags() | extra | wextra)
     return dx
+
+
+def _stage_filters(w, want_dgrad):
+    """FP16x3 engine: both staged layouts of the filters from one pass at the forward (the weights of a step serve
+    its forward and its backward); returns (fprop copy, dgrad copy or None)."""
+    k, c = w.shape[0], w.shape[1]
+    rs = _numel(w.shape[2:])
+    wf = DeviceBuffer((w.size + 16,))
+    wd = DeviceBuffer((w.size + 16,)) if want_dgrad else None
+    _lib().ng_conv2d_stage_filters_f16(wf.ptr, wd.ptr if wd is not None else 0, w.ptr, k, c, rs)
+    return wf, wd
 
 
 def _conv2d_wgrad(dy, x, w_shape, stride, padding, x_nhwc=None, dy_nhwc=None, out=None):
@@ -667,7 +680,14 @@ def _conv_forward_shared(ctx, input, weight, bias, stride, padding):
     if f_tc and w_tc and _needs(ctx, 1):
         x_nhwc = _stage_nhwc(input, engine)
     ctx.conv_nhwc = x_nhwc
-    return _conv2d_forward(input, weight, bias, stride, padding, x_nhwc=x_nhwc)
+    w_f = None
+    ctx.conv_w_dgrad = None
+    if engine == 2 and f_tc:
+        w_f, w_d = _stage_filters(weight, want_dgrad=d_tc and _needs(ctx, 0))
+        if w_d is not None:
+            w_d.staged_flags = (B.math_flags(), engine)
+            ctx.conv_w_dgrad = w_d
+    return _conv2d_forward(input, weight, bias, stride, padding, x_nhwc=x_nhwc, w_staged=w_f)
 
 
 def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding, want_db=False):
@@ -695,7 +715,10 @@ def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding, want
         _dist.grad_slot_filled(db_tok)
     if need_dw:
         _dist.grad_slot_filled(dw_tok)
-    dx = _conv2d_dgrad(grad_output, weight, input.shape, stride, padding, dy_nhwc=dy_nhwc) if need_dx else None
+    w_d = getattr(ctx, "conv_w_dgrad", None)
+    if w_d is not None and (not d_tc or w_d.staged_flags != (B.math_flags(), engine)):
+        w_d = None  # math mode changed between forward and backward: restage inside the call
+    dx = _conv2d_dgrad(grad_output, weight, input.shape, stride, padding, dy_nhwc=dy_nhwc, w_staged=w_d) if need_dx else None
     if want_db:
         return dx, dw, db
     return dx, dw

@@ -27,7 +27,13 @@ def main():
                    "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
                    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
                    "lts__t_sectors_srcunit_tex.sum", "lts__t_bytes.sum.per_second", "dram__bytes.sum.per_second",
-                   "sm__cycles_elapsed.avg", "sm__cycles_active.avg"]
+                   "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
+                   # operand feed of the tcgen05 kernels: bytes TMA brought into the SMs, and the tensor core's
+                   # shared-memory read wavefronts
+                   "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+                   "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.per_second",
+                   "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.pct_of_peak_sustained_elapsed",
+                   "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
     print(f"# {rep}: {len(data)} launches")
     for name in WANT + [c for c in tensor_cols if c not in WANT]:
         if name not in hdr:
