@@ -351,6 +351,35 @@ def conv2d_sweep(B, lib, ffma_peak):
                 row[f"{mode}{name}_tflops"] = round(flops / (ms * 1e-3) / 1e12, 2)
             row[f"{mode}fwd_bwd_tflops"] = round(3 * flops / (total * 1e-3) / 1e12, 2)
         row["frac_of_ffma_peak"] = round(row["fwd_bwd_tflops"] / ffma_peak, 3) if ffma_peak else None
+        if ch % 64 == 0:
+            # the layer-level cost of the FP16x3 engine, as a training step pays it: x, dy and the filters are staged
+            # ONCE (timed as `staging`) and shared by the three passes (x: fprop + wgrad, dy: dgrad + wgrad)
+            flag = B.F_F16X3 | B.F_TC_FORCE
+            xs, dys = DeviceBuffer((x.size + 16,)), DeviceBuffer((dy.size + 16,))
+            wf, wd = DeviceBuffer((w.size + 16,)), DeviceBuffer((w.size + 16,))
+            staged = {"staging": lambda: (lib.ng_conv2d_stage_f16(xs.ptr, x.ptr, 0, 0, N, C, H * W),
+                                          lib.ng_conv2d_stage_f16(dys.ptr, dy.ptr, 0, 0, N, K, OH * OW),
+                                          lib.ng_conv2d_stage_filters_f16(wf.ptr, wd.ptr, w.ptr, K, C, R * S)),
+                      "fprop": lambda: lib.ng_conv2d_fprop(y.ptr, xs.ptr, wf.ptr, 0, *dims, flag | B.F_X_NHWC | B.F_W_STAGED),
+                      "dgrad": lambda: lib.ng_conv2d_dgrad(dx.ptr, dys.ptr, wd.ptr, *dims, flag | B.F_DY_NHWC | B.F_W_STAGED),
+                      "wgrad": lambda: lib.ng_conv2d_wgrad(dw.ptr, dys.ptr, xs.ptr, *dims, flag | B.F_X_NHWC | B.F_DY_NHWC)}
+            total = 0.0
+            for name, fn in staged.items():
+                for _ in range(3):
+                    fn()
+                e0, e1 = B.Event().record(), B.Event()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_ms(e1) / iters
+                total += ms
+                if name == "staging":
+                    row["f16x3_layer_staging_ms"] = round(ms, 4)
+                else:
+                    row[f"f16x3_layer_{name}_tflops"] = round(flops / (ms * 1e-3) / 1e12, 2)
+            row["f16x3_layer_fwd_bwd_tflops"] = round(3 * flops / (total * 1e-3) / 1e12, 2)
+            del xs, dys, wf, wd
         rows.append(row)
         del x, w, dy, y, dx, dw
     return rows
@@ -797,6 +826,10 @@ def run_device_arm(args):
     if world == 1 and not args.no_extras:
         ffma = m["ffma_peak"]
         line["conv2d_sweep"] = {"workload": "Conv2d 3x3 s1 p0, x(256,C,32,32), BASELINE configs[1]",
+                                "columns": "<engine>_<pass>_tflops: one C-ABI call per pass on NCHW operands, every call "
+                                           "staging its own tensor-core operands; f16x3_layer_*: operands staged once per "
+                                           "layer and shared by the passes, as a training step does (staging time included "
+                                           "in f16x3_layer_fwd_bwd_tflops)",
                                 "ffma_peak_tflops": round(ffma, 2),
                                 "rows": conv2d_sweep(B, lib, ffma)}
         line["mnist_cnn"] = mnist_cnn_images_per_sec(B)
