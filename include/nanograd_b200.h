@@ -69,6 +69,10 @@ int ng_host_gather_rows(void* dst, const void* src, const int64_t* idx, int64_t 
 int ng_pinned_alloc(void** out, uint64_t bytes);
 int ng_pinned_free(void* p);
 /* CUDA-event timers on the compute stream */
+/* D2H of a result whose producing kernel was enqueued before `ready_event` was recorded: runs on a read-back stream
+ * that waits for that event only (reading a step's loss does not drain the work queued behind it).  Replaces the
+ * blocking cl.enqueue_copy of Tensor.cpu(), tensor.py:167-180, for the loss read of a training loop. */
+int ng_d2h_after(void* dst, uint64_t src, uint64_t bytes, uint64_t ready_event);
 int ng_event_create(uint64_t* out_ev);
 int ng_event_record(uint64_t ev);
 int ng_event_sync(uint64_t ev);

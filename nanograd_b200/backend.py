@@ -33,6 +33,7 @@ _PROTOTYPES = {
     "ng_memset_zero": [u64, u64],
     "ng_h2d": [u64, c_void_p, u64],
     "ng_d2h": [c_void_p, u64, u64],
+    "ng_d2h_after": [c_void_p, u64, u64, u64],
     "ng_d2d": [u64, u64, u64],
     "ng_h2d_prefetch": [i32, u64, c_void_p, u64],
     "ng_prefetch_wait": [i32],

@@ -358,6 +358,21 @@ int ng_d2h(void* dst, uint64_t src, uint64_t bytes) {
   return 0;
 }
 
+// Device-to-host read of a result whose producer was enqueued before `ready_event` (an ng_event_* handle recorded
+// right after it): the copy runs on a separate read-back stream that waits for that event only, so reading a
+// step's loss does not drain the backward pass and the optimizer step already queued behind it.
+static cudaStream_t g_read_stream = nullptr;
+
+int ng_d2h_after(void* dst, uint64_t src, uint64_t bytes, uint64_t ready_event) {
+  NG_ENSURE_INIT();
+  NG_REQUIRE(ready_event != 0, "ng_d2h_after: null event");
+  if (!g_read_stream) NG_CHECK_CUDA(cudaStreamCreateWithFlags(&g_read_stream, cudaStreamNonBlocking));
+  NG_CHECK_CUDA(cudaStreamWaitEvent(g_read_stream, reinterpret_cast<cudaEvent_t>(static_cast<uintptr_t>(ready_event)), 0));
+  if (bytes) NG_CHECK_CUDA(cudaMemcpyAsync(dst, dptr<void>(src), bytes, cudaMemcpyDeviceToHost, g_read_stream));
+  NG_CHECK_CUDA(cudaStreamSynchronize(g_read_stream));
+  return 0;
+}
+
 int ng_d2d(uint64_t dst, uint64_t src, uint64_t bytes) {
   NG_ENSURE_INIT();
   if (bytes == 0) return 0;

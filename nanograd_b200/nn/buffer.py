@@ -71,10 +71,24 @@ class DeviceBuffer:
         return out
 
     def numpy(self):
-        """Blocking device-to-host copy (the only synchronising operation besides sync())."""
+        """Blocking device-to-host copy (the only synchronising operation besides sync()).  A buffer that carries
+        a ``ready`` event (recorded right after the kernel that produced it: the loss ops do) is read on a separate
+        stream that waits for that event only, so ``float(loss.numpy())`` in a training loop does not drain the
+        backward pass and the optimizer step already queued behind the loss."""
         out = np.empty(self.shape, dtype=np.float32)
-        backend.lib().ng_d2h(out.ctypes.data_as(ctypes.c_void_p), self.ptr, self.size * 4)
+        ready = getattr(self, "ready", None)
+        if ready is not None:
+            backend.lib().ng_d2h_after(out.ctypes.data_as(ctypes.c_void_p), self.ptr, self.size * 4, ready.handle)
+        else:
+            backend.lib().ng_d2h(out.ctypes.data_as(ctypes.c_void_p), self.ptr, self.size * 4)
         return out
+
+    def mark_ready(self):
+        """Record that everything this buffer will ever hold has been enqueued (see ``numpy``).  Not inside a
+        stream capture: an event recorded there cannot be waited on from outside the graph."""
+        if not backend.graph_capturing():
+            self.ready = backend.Event().record()
+        return self
 
     def copy_from_host(self, host):
         host = np.ascontiguousarray(host, dtype=np.float32)

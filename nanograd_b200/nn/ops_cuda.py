@@ -959,7 +959,7 @@ class NLLLoss(Function):
         out = DeviceBuffer((1,))
         _lib().ng_nll_fwd(out.ptr, log_probs.ptr, target.ptr, rows, cols)
         ctx.save_for_backward(target, (rows, cols))
-        return out
+        return out.mark_ready()   # reading the loss waits for the forward pass only
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -982,7 +982,7 @@ class MSELoss(Function):
         out = DeviceBuffer((1,))
         _lib().ng_mse_fwd(out.ptr, predicted.ptr, target.ptr, predicted.size)
         ctx.save_for_backward(predicted, target)
-        return out
+        return out.mark_ready()   # reading the loss waits for the forward pass only
 
     @staticmethod
     def backward(ctx, grad_output):
