@@ -296,6 +296,143 @@ __global__ void __launch_bounds__(256) conv_fprop_smallc_kernel(const __grid_con
   }
 }
 
+// =====================================================================================
+// Direct fprop / dgrad for narrow layers (both channel counts <= 32, stride 1): BASELINE configs[1] at C = K = 16 / 32.
+// The implicit GEMM has J <= 32 output columns there (8 x 1..4 register micro-tiles: one FFMA per shared-memory
+// read) and the tensor-core kernels spend their time filling and draining a pipeline that is 9 short stages deep.
+// Here a thread owns a strip of 4 output pixels x JT output channels (JT x 4 accumulators), walks the reduction
+// channels and filter rows, keeps the S + 3 input values of a row segment in registers and reads the filter taps as
+// warp-uniform LDS.128 from a [kc][tap][JT] copy in shared memory: S * JT * 4 FFMA per (channel, row) for S + 3
+// loads and S * JT / 4 LDS.128.  dgrad is the same correlation with the filter flipped (FLIP) and transposed by the
+// (b_sj, b_sc) strides.
+// =====================================================================================
+template <int JT, int S, bool FLIP>
+__global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant__ ConvGatherP p, int n_img, int OH, int OW,
+                                                          int strips_per_row, long long total_strips) {
+  // square S x S filters; blockIdx.y = tile of JT output channels (a grid dimension rather than a loop: the strips
+  // alone leave a 256 x 30 x 30 output at 13 warps per SM)
+  NG_DYN_SMEM(float, wsm);   // [KC][S*S][JT]
+  constexpr int RS = S * S;
+  const int opix = OH * OW;
+  const int j0 = blockIdx.y * JT;
+  for (int e = threadIdx.x; e < p.KC * RS * JT; e += blockDim.x) {
+    const int j = e % JT, t = e / JT;
+    const int rs = t % RS, kc = t / RS;
+    wsm[e] = (j0 + j < p.J) ? p.b[(long long)(j0 + j) * p.b_sj + (long long)kc * p.b_sc + rs] : 0.f;
+  }
+  __syncthreads();
+  for (long long strip = (long long)blockIdx.x * blockDim.x + threadIdx.x; strip < total_strips;
+       strip += (long long)gridDim.x * blockDim.x) {
+    const int sx = (int)(strip % strips_per_row);
+    const long long t = strip / strips_per_row;
+    const int oy = (int)(t % OH), n = (int)(t / OH);
+    const int ox0 = sx * 4;
+    float acc[JT][4];
+#pragma unroll
+    for (int j = 0; j < JT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    const float* img = p.a + (long long)n * p.a_img_stride;
+    // input columns of a row's taps: ox + x_add + dx, dx = s (fprop) or -s (dgrad, FLIP): S + 3 values per row
+    const int ix0 = ox0 + p.x_add + (FLIP ? -(S - 1) : 0);
+    const int iy0 = oy + p.y_add + (FLIP ? -(S - 1) : 0);   // smallest input row; filter row r reads iy0 + (FLIP ? S-1-r : r)
+    bool colok[S + 3];
+#pragma unroll
+    for (int i = 0; i < S + 3; ++i) colok[i] = (ix0 + i >= 0) && (ix0 + i < p.a_w);
+    for (int kc = 0; kc < p.KC; ++kc) {
+      const float* plane = img + (long long)kc * p.a_chan_stride;
+      // the S rows of this channel's window: all loads issued before the first use
+      float in[S][S + 3];
+#pragma unroll
+      for (int rr = 0; rr < S; ++rr) {
+        const int iy = iy0 + rr;
+        const bool rowok = iy >= 0 && iy < p.a_h;
+        const float* rowp = plane + (long long)iy * p.a_w + ix0;
+#pragma unroll
+        for (int i = 0; i < S + 3; ++i) in[rr][i] = (rowok && colok[i]) ? rowp[i] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        const int rr = FLIP ? (S - 1 - r) : r;
+        const float4* wrow = reinterpret_cast<const float4*>(wsm + (kc * RS + r * S) * JT);
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2) {
+          const int off = FLIP ? (S - 1 - s2) : s2;
+#pragma unroll
+          for (int j4 = 0; j4 < JT / 4; ++j4) {
+            const float4 w = wrow[s2 * (JT / 4) + j4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[4 * j4 + 0][q] = fmaf(in[rr][off + q], w.x, acc[4 * j4 + 0][q]);
+              acc[4 * j4 + 1][q] = fmaf(in[rr][off + q], w.y, acc[4 * j4 + 1][q]);
+              acc[4 * j4 + 2][q] = fmaf(in[rr][off + q], w.z, acc[4 * j4 + 2][q]);
+              acc[4 * j4 + 3][q] = fmaf(in[rr][off + q], w.w, acc[4 * j4 + 3][q]);
+            }
+          }
+        }
+      }
+    }
+    float* o = p.out + ((long long)n * p.J + j0) * opix + (long long)oy * OW + ox0;
+#pragma unroll
+    for (int j = 0; j < JT; ++j) {
+      if (j0 + j >= p.J) break;
+      const float bv = p.bias ? p.bias[j0 + j] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (ox0 + q < OW) {
+          float v = acc[j][q] + bv;
+          if (p.relu) v = fmaxf(v, 0.f);
+          o[(long long)j * opix + q] = v;
+        }
+      }
+    }
+  }
+}
+
+// Returns 0 when launched, -1 when the shape is not one the direct kernel takes.
+static int launch_conv_direct(const ConvGatherP& p, int R, int S, bool flip, int n_img, int OH, int OW) {
+  if (p.y_mul != 1 || p.x_mul != 1 || p.dstride != 1 || R != S) return -1;
+  if (p.J > 32 || p.KC > 32 || p.KC < 8 || (S != 3 && S != 5 && S != 1)) return -1;
+#ifdef NG_EMU
+  const long long min_pixels = 1024;    // the CPU suite's fixture sizes exercise the kernel under the host emulation
+#else
+  const long long min_pixels = 65536;   // tiny problems keep their own kernels (README CNN)
+#endif
+  if ((long long)n_img * OH * OW < min_pixels) return -1;
+  // the taps must be in storage order (fprop: (dy, dx) = (r, s) + const, dgrad: (-r, -s) + const)
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s)
+      if (p.tap_dy[r * S + s] != (flip ? -r : r) || p.tap_dx[r * S + s] != (flip ? -s : s)) return -1;
+  const int strips_per_row = (int)ceil_div(OW, 4);
+  const long long total = (long long)n_img * OH * strips_per_row;
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  // output-channel tile: the widest that still gives ~24 warps per SM (5 x 5 filters keep the window small)
+  int JT = p.J <= 8 ? 8 : (p.J <= 16 ? 16 : 32);
+  if (S == 5 && JT > 16) JT = 16;
+  while (JT > 8 && total * ceil_div(p.J, JT) < (long long)sms * 24 * 32) JT >>= 1;
+  const size_t smem = sizeof(float) * (size_t)p.KC * R * S * JT;
+  if (smem > 48 * 1024) return -1;
+  long long g = ceil_div(total, 128);
+  if (g > (long long)sms * 16) g = (long long)sms * 16;
+  const dim3 grid((unsigned)g, (unsigned)ceil_div(p.J, JT));
+#define NG_DIRECT(JT_, S_)                                                                                        \
+  do {                                                                                                            \
+    if (flip) NG_LAUNCH((conv_direct_kernel<JT_, S_, true>), grid, 128, smem, p, n_img, OH, OW, strips_per_row, total); \
+    else NG_LAUNCH((conv_direct_kernel<JT_, S_, false>), grid, 128, smem, p, n_img, OH, OW, strips_per_row, total);     \
+  } while (0)
+#define NG_DIRECT_S(JT_)                                                                                          \
+  do {                                                                                                            \
+    if (S == 1) NG_DIRECT(JT_, 1);                                                                                \
+    else if (S == 3) NG_DIRECT(JT_, 3);                                                                           \
+    else NG_DIRECT(JT_, 5);                                                                                       \
+  } while (0)
+  if (JT == 8) NG_DIRECT_S(8);
+  else if (JT == 16) NG_DIRECT_S(16);
+  else NG_DIRECT_S(32);
+#undef NG_DIRECT_S
+#undef NG_DIRECT
+  NG_CHECK_LAUNCH();
+  return 0;
+}
+
 static int launch_fprop_smallc(const ConvGatherP& g, int N, int C, int H, int W, int K, int OH, int OW, int pad_t,
                                int pad_l) {
   FpropSmallP p;
@@ -952,6 +1089,189 @@ static int check_conv_dims(const char* who, int N, int C, int H, int W, int K, i
   return 0;
 }
 
+// =====================================================================================
+// Direct wgrad for narrow layers (C, K <= 32, S == 3, stride 1): conv_wgrad_smallc_kernel generalised to any output
+// width (rows are zero-padded to a multiple of 4 in shared memory) and to a KT x RPG register tile: thread (kg, g)
+// keeps dW[kg*KT + 0..KT-1][row][0..2] for its RPG filter rows (row = c*R + r); per 4-pixel strip KT LDS.128 of dy
+// and 2*RPG LDS.128 of x feed KT*RPG*12 FFMA.  One partial per CTA, fixed-order reduce (splitk_reduce_wide_kernel).
+// =====================================================================================
+struct WgradDirectP {
+  const float* x;
+  const float* dy;
+  float* ws;  // [gridDim.x][K][C*R*3]
+  int N, C, H, W, K, R, OH, OW, OWP, pad_t, pad_l;
+  int TR, row_blocks, tiles, NR, KG, G, PSN, xrows, xpitch, dpitch;
+};
+
+template <int KT, int RPG>
+__global__ void __launch_bounds__(512) conv_wgrad_direct_kernel(const __grid_constant__ WgradDirectP p) {
+  NG_DYN_SMEM(float, sm);
+  float* dys = sm;                       // [K][dpitch]: TR rows of OWP pixels
+  float* xs = sm + p.K * p.dpitch;       // [C][xrows][xpitch]: column j holds input column j - pad_l
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  // thread = (kg, g, ps): KT output channels x RPG filter rows, and one of PSN interleaved subsets of the tile's
+  // 4-pixel strips (with K/KT x NR/RPG = 128 threads alone a CTA keeps 4 warps busy: the strips are what is left to
+  // split); the PSN partial tiles are added in a fixed order through shared memory at the end
+  const int base = p.KG * p.G;
+  const int ps = tid / base, tb = tid - ps * base;
+  const int kg = tb % p.KG, g = tb / p.KG;
+  int xoff[RPG];
+  bool live[RPG];
+  float acc[KT][RPG][3];
+#pragma unroll
+  for (int q = 0; q < RPG; ++q) {
+    const int row = g * RPG + q;
+    live[q] = row < p.NR;
+    const int c = live[q] ? row / p.R : 0, r = live[q] ? row % p.R : 0;
+    xoff[q] = (c * p.xrows + r) * p.xpitch;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) acc[kk][q][0] = acc[kk][q][1] = acc[kk][q][2] = 0.f;
+  }
+  const int dtile = p.K * p.TR * p.OWP, xtile = p.C * p.xrows * p.xpitch;
+  const int spr = p.OWP >> 2, nstrips = p.TR * spr;   // strips per row / per tile
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    const int n = tile / p.row_blocks, oh0 = (tile - n * p.row_blocks) * p.TR;
+    __syncthreads();  // the previous tile has been consumed
+    for (int e = tid; e < dtile; e += nthr) {
+      const int ow = e % p.OWP, t = e / p.OWP;
+      const int tr = t % p.TR, kk = t / p.TR;
+      float v = 0.f;
+      if (ow < p.OW && oh0 + tr < p.OH) v = p.dy[((long long)(n * p.K + kk) * p.OH + oh0 + tr) * p.OW + ow];
+      dys[kk * p.dpitch + tr * p.OWP + ow] = v;
+    }
+    for (int e = tid; e < xtile; e += nthr) {
+      const int j = e % p.xpitch, t = e / p.xpitch;
+      const int rr = t % p.xrows, c = t / p.xrows;
+      const int ih = oh0 + rr - p.pad_t, iw = j - p.pad_l;
+      float v = 0.f;
+      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = p.x[((long long)(n * p.C + c) * p.H + ih) * p.W + iw];
+      xs[e] = v;
+    }
+    __syncthreads();
+    const float* drow = dys + (kg * KT) * p.dpitch;
+    for (int si = ps; si < nstrips; si += p.PSN) {
+      const int tr = si / spr, ow0 = (si - tr * spr) << 2;
+      float4 d[KT];
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk) d[kk] = *reinterpret_cast<const float4*>(drow + kk * p.dpitch + tr * p.OWP + ow0);
+#pragma unroll
+      for (int q = 0; q < RPG; ++q) {
+        if (!live[q]) continue;
+        const float* xr = xs + xoff[q] + tr * p.xpitch + ow0;
+        const float4 a = *reinterpret_cast<const float4*>(xr);
+        const float4 b = *reinterpret_cast<const float4*>(xr + 4);
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+          acc[kk][q][0] = fmaf(d[kk].x, a.x, fmaf(d[kk].y, a.y, fmaf(d[kk].z, a.z, fmaf(d[kk].w, a.w, acc[kk][q][0]))));
+          acc[kk][q][1] = fmaf(d[kk].x, a.y, fmaf(d[kk].y, a.z, fmaf(d[kk].z, a.w, fmaf(d[kk].w, b.x, acc[kk][q][1]))));
+          acc[kk][q][2] = fmaf(d[kk].x, a.z, fmaf(d[kk].y, a.w, fmaf(d[kk].z, b.x, fmaf(d[kk].w, b.y, acc[kk][q][2]))));
+        }
+      }
+    }
+  }
+  // fold the PSN strip subsets (fixed order), then one partial per CTA
+  __syncthreads();
+  constexpr int NA = KT * RPG * 3;
+  if (ps > 0) {
+    float* slot = sm + ((size_t)(ps - 1) * base + tb) * NA;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+      for (int q = 0; q < RPG; ++q)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) slot[(kk * RPG + q) * 3 + t] = acc[kk][q][t];
+  }
+  __syncthreads();
+  if (ps == 0) {
+    for (int o = 1; o < p.PSN; ++o) {
+      const float* slot = sm + ((size_t)(o - 1) * base + tb) * NA;
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+        for (int q = 0; q < RPG; ++q)
+#pragma unroll
+          for (int t = 0; t < 3; ++t) acc[kk][q][t] += slot[(kk * RPG + q) * 3 + t];
+    }
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      float* out = p.ws + ((long long)blockIdx.x * p.K + kg * KT + kk) * (p.NR * 3);
+#pragma unroll
+      for (int q = 0; q < RPG; ++q) {
+        if (!live[q]) continue;
+        const int row = g * RPG + q;
+        out[row * 3 + 0] = acc[kk][q][0];
+        out[row * 3 + 1] = acc[kk][q][1];
+        out[row * 3 + 2] = acc[kk][q][2];
+      }
+    }
+  }
+}
+
+// Returns 0 when done, -1 when the shape is not one the direct kernel takes, > 0 on error.
+static int launch_wgrad_direct(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
+                               int stride, int pad_t, int pad_l, int OH, int OW) {
+  // measured (config 1, batch 256): C = K = 16: 96 us against 130 us for the split-K implicit GEMM; C = K = 32: 266 us
+  // against 222 us, so the implicit GEMM (or, in the FP32-accurate default, the 3xTF32 tensor-core kernel) keeps those
+  if (S != 3 || stride != 1 || C > 32 || K > 32 || C < 8 || K % 2 != 0 || C * K > 512) return -1;
+#ifdef NG_EMU
+  const long long min_pixels = 1024;
+#else
+  const long long min_pixels = 65536;
+#endif
+  if ((long long)N * OH * OW < min_pixels) return -1;
+  constexpr int KT = 2, RPG = 3;
+  WgradDirectP q;
+  memset(&q, 0, sizeof(q));
+  q.x = x; q.dy = dy;
+  q.N = N; q.C = C; q.H = H; q.W = W; q.K = K; q.R = R; q.OH = OH; q.OW = OW;
+  q.OWP = (OW + 3) & ~3;
+  q.pad_t = pad_t; q.pad_l = pad_l;
+  q.NR = C * R;
+  q.KG = K / KT;
+  q.G = (q.NR + RPG - 1) / RPG;
+  const int base = q.KG * q.G;
+  if (base > 512 || base < 32) return -1;
+  q.PSN = 512 / base;            // strip subsets: fill the CTA up to 512 threads
+  if (q.PSN > 8) q.PSN = 8;
+  const int threads = base * q.PSN;
+  q.xpitch = q.OWP + 4;
+  // the largest row block whose dy and x tiles fit 44 KB of shared memory
+  int TR = OH;
+  for (;; --TR) {
+    if (TR < 1) return -1;
+    const size_t bytes = sizeof(float) * ((size_t)K * (TR * q.OWP + 4) + (size_t)C * (TR + R - 1) * q.xpitch);
+    if (bytes <= 44 * 1024) break;
+  }
+  q.TR = TR;
+  q.row_blocks = (int)ceil_div(OH, TR);
+  q.tiles = N * q.row_blocks;
+  q.xrows = TR + R - 1;
+  q.dpitch = TR * q.OWP + 4;
+  size_t smem = sizeof(float) * ((size_t)K * q.dpitch + (size_t)C * q.xrows * q.xpitch);
+  const size_t fold = sizeof(float) * (size_t)(q.PSN - 1) * base * KT * RPG * 3;   // reuses the tile memory at the end
+  if (fold > smem) smem = fold;
+  if (smem > 48 * 1024) return -1;
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  int ctas_per_sm = (int)((200u * 1024u) / (smem + 1024u));
+  if (ctas_per_sm > 2048 / threads) ctas_per_sm = 2048 / threads;
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int grid = sms * ctas_per_sm;
+  if (grid > q.tiles) grid = q.tiles;
+  const long long out_elems = (long long)K * q.NR * 3;
+  float* ws = nullptr;
+  if (pool_alloc((void**)&ws, (uint64_t)((long long)grid * out_elems) * sizeof(float))) return 1;
+  q.ws = ws;
+  ProfScope prof_(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
+                  4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
+  NG_LAUNCH((conv_wgrad_direct_kernel<KT, RPG>), grid, threads, smem, q);
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(splitk_reduce_wide_kernel, (int)ceil_div(out_elems, 64), 512, 0, dw, (const float*)ws, grid, out_elems);
+  NG_CHECK_LAUNCH();
+  pool_free(ws);
+  return 0;
+}
+
 }  // namespace ng
 
 using namespace ng;
@@ -1005,6 +1325,7 @@ int ng_conv2d_fprop(uint64_t y, uint64_t x, uint64_t w, uint64_t bias, int N, in
   if (rc < 0 && C <= 4 && R == 3 && S == 3 && stride == 1 && OW % 4 == 0 && (y & 15u) == 0 &&
       (long long)N * OH * OW >= 4096)
     rc = launch_fprop_smallc(p, N, C, H, W, K, OH, OW, pad_t, pad_l);
+  if (rc < 0 && stride == 1) rc = launch_conv_direct(p, R, S, false, N, OH, OW);
   if (rc < 0) rc = launch_conv_gather(p, false);
   prof_end(tok);
   return rc;
@@ -1055,6 +1376,7 @@ int ng_conv2d_dgrad(uint64_t dx, uint64_t dy, uint64_t w, int N, int C, int H, i
 #endif
   if (rc < 0 && (flags & (NG_F_DY_NHWC | NG_F_W_STAGED)))
     rc = set_error("ng_conv2d_dgrad: staged operands given but this shape does not take the tensor-core kernel");
+  if (rc < 0 && stride == 1) rc = launch_conv_direct(p, R, S, true, N, H, W);
   if (rc < 0) rc = launch_conv_gather(p, stride > 1);
   prof_end(tok);
   return rc;
@@ -1219,6 +1541,12 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
 #endif
   NG_REQUIRE(!(flags & (NG_F_X_NHWC | NG_F_DY_NHWC)),
              "ng_conv2d_wgrad: staged NHWC operands given but this shape does not take the tensor-core kernel");
+  {
+    // narrow layers (both channel counts <= 32): direct kernel (see conv_wgrad_direct_kernel)
+    const int rc = launch_wgrad_direct(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R, S,
+                                       stride, pad_t, pad_l, OH, OW);
+    if (rc >= 0) return rc;
+  }
   const int sms_all = g_sm_count > 0 ? g_sm_count : 148;
   {
     // tiny layer: direct kernel over whole images in shared memory (see conv_wgrad_tiny_kernel)
