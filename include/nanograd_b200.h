@@ -321,6 +321,11 @@ int ng_bn2d_act_bwd_sums(uint64_t dgamma, uint64_t dbeta, uint64_t sums, uint64_
                          int64_t N, int64_t C, int64_t HW, int act);
 int ng_bn2d_act_bwd_dx(uint64_t dx, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean,
                        uint64_t save_invstd, uint64_t sums, int64_t N, int64_t C, int64_t HW, int act);
+/* ng_bn2d_act_bwd_dx that also returns chan_sums[c] = sum over (n, h, w) of dx: the bias gradient of the convolution
+ * that produced x (Add.backward's unbroadcast, ops_cpu.py:12-18, module.py:476) without a second pass over dx */
+int ng_bn2d_act_bwd_dx_sum(uint64_t dx, uint64_t chan_sums, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta,
+                           uint64_t save_mean, uint64_t save_invstd, uint64_t sums, int64_t N, int64_t C, int64_t HW,
+                           int act);
 /* ng_bn2d_act_bwd_sums for a layer whose output went through a 2x2 max pooling, with the pooling backward fused
  * in: the gradient of the pooled tensor (dpooled) and the pooled maxima replace dy, which is never written */
 int ng_bn2d_act_bwd_sums_pool(uint64_t dgamma, uint64_t dbeta, uint64_t sums, uint64_t bound_bits, uint64_t dpooled,

@@ -83,6 +83,7 @@ _PROTOTYPES = {
     "ng_bn2d_act_apply": [u64] * 6 + [i64, i64, i64, i32],
     "ng_bn2d_act_bwd_sums": [u64] * 10 + [i64, i64, i64, i32],
     "ng_bn2d_act_bwd_dx": [u64] * 8 + [i64, i64, i64, i32],
+    "ng_bn2d_act_bwd_dx_sum": [u64] * 9 + [i64, i64, i64, i32],
     "ng_bn2d_act_bwd_sums_pool": [u64] * 11 + [i64, i64, i32, i32, i32],
     "ng_conv2d_stage_f16_bnbwd_pool": [u64] * 11 + [i64, i64, i32, i32, i32],
     "ng_maxpool2d_fwd": [u64, u64, i64, i32, i32, i32, i32],

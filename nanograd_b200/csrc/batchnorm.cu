@@ -493,6 +493,99 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(float* __restrict__ dx, 
   }
 }
 
+// dx pass that also returns the per-channel sums of dx (the bias gradient of the convolution that produced this
+// layer's input, Add.backward's unbroadcast, ops_cpu.py:12-18): grid (C, S) like the reduction passes, a block streams
+// its channel's planes of n_per images, writes dx and keeps a running sum; bn_plane_fold_kernel adds the S partials
+// in a fixed order.  Used when the convolution below does not stage its operands (first layer): saves the separate
+// pass over dx that the channel sum would take.
+__global__ void __launch_bounds__(256) bn_bwd_dx_sum_kernel(float* __restrict__ dx, float* __restrict__ partial,
+                                                            const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, const float* __restrict__ sums,
+                                                            int64_t N, int64_t C, int64_t P, int64_t n_per_split,
+                                                            float inv_count, int vec_ok, const float* __restrict__ beta,
+                                                            FastDiv fp4) {
+  __shared__ float scratch[32];
+  const int64_t c = blockIdx.x, s = blockIdx.y;
+  const float inv = invstd[c], mu = mean[c];
+  const float k0 = gamma[c] * inv, k1 = sums[c * 2] * inv_count, k2 = inv * inv * sums[c * 2 + 1] * inv_count;
+  const float zb = beta ? beta[c] : 0.f;
+  const int64_t n0 = s * n_per_split;
+  int64_t n1 = n0 + n_per_split;
+  if (n1 > N) n1 = N;
+  float acc = 0.f;
+  if (vec_ok) {
+    const int64_t P4 = P >> 2;
+    const int64_t items = (n1 - n0) * P4;
+    const bool fast = fp4.d != 0 && items < (1LL << 31);
+    constexpr int U = 2;
+    for (int64_t i0 = threadIdx.x; i0 < items; i0 += U * (int64_t)blockDim.x) {
+      float4 xv[U], gv[U];
+      int64_t off[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * (int64_t)blockDim.x;
+        off[u] = -1;
+        if (i < items) {
+          int64_t n, p4;
+          if (fast) {
+            const uint32_t q = fastdiv((uint32_t)i, fp4);
+            n = n0 + q;
+            p4 = (uint32_t)i - q * fp4.d;
+          } else {
+            n = n0 + i / P4;
+            p4 = i % P4;
+          }
+          off[u] = (n * C + c) * P + (p4 << 2);
+          xv[u] = *reinterpret_cast<const float4*>(x + off[u]);
+          gv[u] = *reinterpret_cast<const float4*>(dy + off[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (off[u] < 0) continue;
+        float4 g = gv[u];
+        if (beta) {
+          if (!(bn_affine(xv[u].x, mu, k0, zb) >= 0.f)) g.x = 0.f;
+          if (!(bn_affine(xv[u].y, mu, k0, zb) >= 0.f)) g.y = 0.f;
+          if (!(bn_affine(xv[u].z, mu, k0, zb) >= 0.f)) g.z = 0.f;
+          if (!(bn_affine(xv[u].w, mu, k0, zb) >= 0.f)) g.w = 0.f;
+        }
+        float4 o;
+        o.x = k0 * (g.x - k1 - (xv[u].x - mu) * k2); o.y = k0 * (g.y - k1 - (xv[u].y - mu) * k2);
+        o.z = k0 * (g.z - k1 - (xv[u].z - mu) * k2); o.w = k0 * (g.w - k1 - (xv[u].w - mu) * k2);
+        *reinterpret_cast<float4*>(dx + off[u]) = o;
+        acc += (o.x + o.y) + (o.z + o.w);
+      }
+    }
+  } else {
+    const int64_t items = (n1 - n0) * P;
+    for (int64_t i = threadIdx.x; i < items; i += blockDim.x) {
+      const int64_t n = n0 + i / P, pp = i % P;
+      const int64_t off = (n * C + c) * P + pp;
+      float g = dy[off];
+      if (beta && !(bn_affine(x[off], mu, k0, zb) >= 0.f)) g = 0.f;
+      const float o = k0 * (g - k1 - (x[off] - mu) * k2);
+      dx[off] = o;
+      acc += o;
+    }
+  }
+  const float t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) partial[s * C + c] = t;
+}
+
+// out[c] = sum_s partial[s][c]  (fixed order; one warp per channel)
+__global__ void __launch_bounds__(256) bn_plane_fold_kernel(float* __restrict__ out, const float* __restrict__ partial,
+                                                            int64_t S, int64_t C) {
+  const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int64_t n = lane; n < S; n += 32) acc += partial[n * C + c];
+  acc = warp_sum(acc);
+  if (lane == 0) out[c] = acc;
+}
+
 // Splits of the batch axis for the reduction passes (grid = C x S blocks, about four blocks per SM).  A search for
 // the split count with the smallest last-wave loss (e.g. 64 channels x 16 splits instead of x 10) was measured and is
 // no better forward and 20 % slower backward (53 vs 44 us at 64 channels x 512 x 32^2): fewer, longer blocks win.
@@ -803,6 +896,30 @@ int ng_bn2d_act_bwd_dx(uint64_t dx, uint64_t dy, uint64_t x, uint64_t gamma, uin
   NG_REQUIRE(act == 0 || (act == 1 && beta != 0), "ng_bn2d_act_bwd_dx: act must be 0, or 1 (ReLU) with beta given");
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0) && ((dx & 15u) == 0);
   return bn_bwd_dx(dx, dy, x, gamma, beta, save_mean, save_invstd, dptr<const float>(sums), N, C, HW, act, vec, 0);
+}
+
+int ng_bn2d_act_bwd_dx_sum(uint64_t dx, uint64_t chan_sums, uint64_t dy, uint64_t x, uint64_t gamma, uint64_t beta,
+                           uint64_t save_mean, uint64_t save_invstd, uint64_t sums, int64_t N, int64_t C, int64_t HW, int act) {
+  NG_ENSURE_INIT();
+  ProfScope prof_(NG_PROF_BN, 0.0, 12.0 * (double)N * C * HW);
+  NG_REQUIRE(N > 0 && C > 0 && HW > 0 && N * C < 2147483647LL, "ng_bn2d_act_bwd_dx_sum: bad dimensions");
+  NG_REQUIRE(act == 0 || (act == 1 && beta != 0), "ng_bn2d_act_bwd_dx_sum: act must be 0, or 1 (ReLU) with beta given");
+  NG_REQUIRE(chan_sums != 0 && sums != 0, "ng_bn2d_act_bwd_dx_sum: chan_sums and sums are required");
+  NG_REQUIRE(C <= 65535, "ng_bn2d_act_bwd_dx_sum: too many channels");
+  int64_t n_per = 0;
+  const int S = bn_split(N, C, HW, &n_per);
+  float* partial = nullptr;
+  if (pool_alloc((void**)&partial, (uint64_t)S * C * sizeof(float))) return 1;
+  const int vec = (HW % 4 == 0) && ((x & 15u) == 0) && ((dy & 15u) == 0) && ((dx & 15u) == 0);
+  NG_LAUNCH(bn_bwd_dx_sum_kernel, dim3((unsigned)C, (unsigned)S), 256, 0, dptr<float>(dx), partial, dptr<const float>(dy),
+            dptr<const float>(x), dptr<const float>(gamma), dptr<const float>(save_mean), dptr<const float>(save_invstd),
+            dptr<const float>(sums), N, C, HW, n_per, 1.f / (float)(N * HW), vec,
+            act ? dptr<const float>(beta) : (const float*)nullptr, make_fastdiv(vec ? HW / 4 : 0));
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(bn_plane_fold_kernel, (int)ceil_div(C, 8), 256, 0, dptr<float>(chan_sums), (const float*)partial, (int64_t)S, C);
+  NG_CHECK_LAUNCH();
+  pool_free(partial);
+  return 0;
 }
 
 int ng_bn2d_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, uint64_t x, uint64_t gamma,

@@ -144,6 +144,16 @@ class LazyBuffer(DeviceBuffer):
             fn(self._ptr)
         return self._ptr
 
+    def materialize_with(self, fn):
+        """Materialise through ``fn(ptr)`` instead of the default kernel (a consumer that wants a by-product of
+        the same pass, e.g. channel sums).  No-op if the buffer was already written."""
+        if self._ptr:
+            return False
+        self._ptr = backend.malloc(self.size * 4)
+        self._materialize = None
+        fn(self._ptr)
+        return True
+
 
 class ScalarBuffer(DeviceBuffer):
     """A Python scalar travelling as a 1-element tensor.

@@ -704,6 +704,17 @@ def _conv_backward_shared(ctx, grad_output, input, weight, stride, padding, want
         # here even for a single pass, so that a BatchNorm recipe upstream is fused into the staging)
         dy_nhwc, db = _stage_nhwc(grad_output, engine, channel_sums=True, sums_out=db_out) if want_db \
             else (_stage_nhwc(grad_output, engine), None)
+    if (want_db and db is None and dy_nhwc is None and isinstance(grad_output, LazyBuffer) and grad_output.pending
+            and grad_output.kind == "bn_bwd"):
+        # the gradient is a BatchNorm recipe and this convolution reads it as a plain NCHW tensor (SIMT / direct
+        # kernels): materialise it with the pass that also yields its channel sums = this layer's bias gradient
+        bdy, bx, gamma, beta, mean, invstd, bn_sums, act, _, _ = grad_output.source
+        n_, c_ = grad_output.shape[0], grad_output.shape[1]
+        hw_ = _numel(grad_output.shape[2:])
+        if grad_output.materialize_with(lambda ptr: _lib().ng_bn2d_act_bwd_dx_sum(
+                ptr, db_out.ptr, bdy.ptr, bx.ptr, gamma.ptr, beta.ptr if act else 0, mean.ptr, invstd.ptr, bn_sums.ptr,
+                n_, c_, hw_, act)):
+            db = db_out
     # wgrad first: it is what the data-parallel gradient arena is waiting for (dgrad only feeds this rank)
     dw = None
     if need_dw:

@@ -289,3 +289,35 @@ def test_bn_backward_with_fused_maxpool_backward(shape, act):
     assert np.all(err <= np.maximum(np.abs(dx) * 2.0 ** -20, dmax * 2e-5)), float(err.max() / dmax)
     np.testing.assert_allclose(chan.numpy(), dx.sum(axis=(0, 2)), rtol=0, atol=1e-4 * float(np.abs(dx).sum(axis=(0, 2)).max()),
                                err_msg="channel sums of the fused dx staging")
+
+
+def _check_dx_with_channel_sums(shape, act):
+    """ng_bn2d_act_bwd_dx_sum: the dx of ng_bn2d_act_bwd_dx bit for bit, plus its channel sums (the bias gradient of
+    the convolution below, which vanishes analytically: compared on the scale of sum |dx|)."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn.buffer import DeviceBuffer
+    lib = B.lib()
+    n, c, h, w = shape
+    hw = h * w
+    host, dev = _setup(n, c, h, w, seed=5 * c + act)
+    one, _, (_, sums, _, mean, invstd) = _one_call_and_split(lib, dev, n, c, hw, act)
+    dx, chan = DeviceBuffer((n, c, hw)), DeviceBuffer((c,))
+    lib.ng_bn2d_act_bwd_dx_sum(dx.ptr, chan.ptr, dev["dy"].ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr if act else 0,
+                               mean.ptr, invstd.ptr, sums.ptr, n, c, hw, act)
+    H.assert_exact(dx.numpy(), one[3], "dx of the pass with channel sums")
+    want = one[3].astype(np.float64).sum(axis=(0, 2))
+    np.testing.assert_allclose(chan.numpy(), want, rtol=0, atol=1e-5 * float(np.abs(one[3]).astype(np.float64).sum(axis=(0, 2)).max()))
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_dx_pass_with_channel_sums_emulated(act):
+    H.use_emulated_library()
+    _check_dx_with_channel_sums((3, 8, 5, 4), act)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("shape", [(3, 8, 5, 4), (16, 64, 32, 32), (7, 192, 9, 5)], ids=lambda s: "x".join(map(str, s)))
+def test_dx_pass_with_channel_sums(shape, act):
+    H.use_cuda_library()
+    _check_dx_with_channel_sums(shape, act)
