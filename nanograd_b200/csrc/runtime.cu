@@ -4,6 +4,7 @@
 // Replaces the PyOpenCL context/queue bootstrap and buffer management of the reference
 // (nanograd/tensor.py:14-30,153-182; nanograd/nn/buffer.py:14-26).
 #include "ng_common.h"
+#include <stdlib.h>
 
 #include <chrono>
 #include <condition_variable>
@@ -185,6 +186,14 @@ int ng_init(int device_ordinal) {
   cudaDeviceProp prop;
   NG_CHECK_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
   g_sm_count = prop.multiProcessorCount;
+  {
+    // NANOGRAD_B200_SM_RESERVE=k: size every grid for k fewer SMs.  The persistent tensor-core kernels run one CTA per
+    // SM; under data parallelism an SM held by an NCCL kernel makes one of their CTAs wait for a whole persistent
+    // loop, so nanograd_b200.dist reserves as many SMs as it lets NCCL use.
+    const char* e = getenv("NANOGRAD_B200_SM_RESERVE");
+    const int k = e ? atoi(e) : 0;
+    if (k > 0 && k < g_sm_count / 2) g_sm_count -= k;
+  }
   NG_CHECK_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   g_device = device_ordinal;
   return 0;

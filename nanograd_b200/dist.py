@@ -268,7 +268,7 @@ class GradBucket:
     # launch an allreduce once >= 128 KB of finished gradients is waiting.  (With 1 MB chunks the last three conv
     # layers of config 2 — 147 k + 74 k + 37 k floats — stayed just under the threshold and went out only after the
     # whole backward, an exposed 1 MB allreduce; now only the first layer's 1.7 k floats are left for the end.)
-    CHUNK_FLOATS = 1 << 15
+    CHUNK_FLOATS = int(os.environ.get("NANOGRAD_B200_DP_CHUNK_FLOATS", 1 << 15))
 
     def __init__(self, params):
         from nanograd_b200 import backend as B
