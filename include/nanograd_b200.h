@@ -305,14 +305,16 @@ int ng_bn2d_act_bwd(uint64_t dx, uint64_t dgamma, uint64_t dbeta, uint64_t dy, u
  * consumer (ng_conv2d_stage_f16_bn / _bnbwd) instead of writing a tensor nobody else reads:
  *   ng_bn2d_act_fwd_stats  statistics + running-stat update; absmax_bits[0] = bits of max|y| of the output the
  *                          apply pass WOULD write (the normalised output is monotone in x per channel, so the
- *                          channel extremes of x, tracked by the statistics pass, give it exactly);
+ *                          channel extremes of x, tracked by the statistics pass, give it exactly); snapshot
+ *                          (optional, 2C floats) receives copies of gamma and beta as they are at the call, so that
+ *                          a normalise pass run after an in-place optimizer step still yields this step's output;
  *   ng_bn2d_act_apply      the normalise (+ activation) pass alone;
  *   ng_bn2d_act_bwd_sums   dgamma, dbeta, sums[2C + 1] = per channel {sum dy, sum dy (x - mean)} + the count,
  *                          bound_bits[0] = bits of an upper bound of max|dx|;
  *   ng_bn2d_act_bwd_dx     the dx pass alone.
  * Single process only (synchronised BatchNorm keeps the one-call forms above). */
 int ng_bn2d_act_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean, uint64_t running_var,
-                          uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits,
+                          uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits, uint64_t snapshot,
                           int64_t N, int64_t C, int64_t HW, float eps, float momentum, int act);
 int ng_bn2d_act_apply(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd,
                       int64_t N, int64_t C, int64_t HW, int act);

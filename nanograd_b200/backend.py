@@ -79,7 +79,7 @@ _PROTOTYPES = {
     "ng_conv2d_stage_filters_f16": [u64, u64, u64, i32, i32, i32],
     "ng_conv2d_stage_f16_bn": [u64] * 7 + [i64, i64, i64, i32],
     "ng_conv2d_stage_f16_bnbwd": [u64] * 10 + [i64, i64, i64, i32],
-    "ng_bn2d_act_fwd_stats": [u64] * 8 + [i64, i64, i64, f32, f32, i32],
+    "ng_bn2d_act_fwd_stats": [u64] * 9 + [i64, i64, i64, f32, f32, i32],
     "ng_bn2d_act_apply": [u64] * 6 + [i64, i64, i64, i32],
     "ng_bn2d_act_bwd_sums": [u64] * 10 + [i64, i64, i64, i32],
     "ng_bn2d_act_bwd_dx": [u64] * 8 + [i64, i64, i64, i32],

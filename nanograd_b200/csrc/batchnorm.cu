@@ -41,6 +41,8 @@ struct BnFin {
   unsigned int* bits;      // forward: bits of max|y|; backward: bits of a bound of max|dx| (null: not wanted)
   float* save_mean;        // forward
   float* save_invstd;
+  float* snap_gamma;       // forward, optional: copies of gamma / beta as they are now (a recipe evaluated after an
+  float* snap_beta;        // in-place optimizer step must not see the updated parameters)
   float* running_mean;
   float* running_var;
   const float* invstd;     // backward
@@ -72,6 +74,10 @@ __device__ __forceinline__ void bn_fwd_fold(const float* partial, const float* x
   const float invstd = 1.f / sqrtf(var_b + f.eps);
   f.save_mean[c] = mean;
   f.save_invstd[c] = invstd;
+  if (f.snap_gamma) {
+    f.snap_gamma[c] = f.gamma[c];
+    f.snap_beta[c] = f.beta[c];
+  }
   if (f.running_mean) {
     const float var_u = ssd / (f.count - 1.f);  // module.py:367-368
     f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
@@ -628,7 +634,7 @@ static unsigned int* fold_counters() {
 
 static int bn_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean, uint64_t running_var,
                         uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits, int64_t N, int64_t C, int64_t HW,
-                        float eps, float momentum, int act, int vec) {
+                        float eps, float momentum, int act, int vec, uint64_t snapshot = 0) {
   int64_t n_per = 0;
   const int S = bn_split(N, C, HW, &n_per);
   const bool extra = absmax_bits != 0;
@@ -642,6 +648,8 @@ static int bn_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t runn
   fin.gamma = dptr<const float>(gamma); fin.beta = dptr<const float>(beta);
   fin.bits = extra ? dptr<unsigned int>(absmax_bits) : nullptr;
   fin.save_mean = dptr<float>(save_mean); fin.save_invstd = dptr<float>(save_invstd);
+  fin.snap_gamma = snapshot ? dptr<float>(snapshot) : nullptr;
+  fin.snap_beta = snapshot ? dptr<float>(snapshot) + C : nullptr;
   fin.running_mean = running_mean ? dptr<float>(running_mean) : nullptr;
   fin.running_var = running_var ? dptr<float>(running_var) : nullptr;
   fin.counter = sync ? nullptr : fold_counters();   // single process: the last block of a channel folds it
@@ -703,8 +711,8 @@ int ng_bn2d_act_fwd_train(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta,
 }
 
 int ng_bn2d_act_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t running_mean, uint64_t running_var,
-                          uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits, int64_t N, int64_t C,
-                          int64_t HW, float eps, float momentum, int act) {
+                          uint64_t save_mean, uint64_t save_invstd, uint64_t absmax_bits, uint64_t snapshot, int64_t N,
+                          int64_t C, int64_t HW, float eps, float momentum, int act) {
   NG_ENSURE_INIT();
   ProfScope prof_(NG_PROF_BN, 0.0, 4.0 * (double)N * C * HW);
   NG_REQUIRE(N > 0 && C > 0 && HW > 0, "ng_bn2d_act_fwd_stats: empty input");
@@ -713,7 +721,7 @@ int ng_bn2d_act_fwd_stats(uint64_t x, uint64_t gamma, uint64_t beta, uint64_t ru
   NG_REQUIRE(absmax_bits != 0, "ng_bn2d_act_fwd_stats: absmax_bits is required");
   const int vec = (HW % 4 == 0) && ((x & 15u) == 0);
   return bn_fwd_stats(x, gamma, beta, running_mean, running_var, save_mean, save_invstd, absmax_bits, N, C, HW, eps,
-                      momentum, act, vec);
+                      momentum, act, vec, snapshot);
 }
 
 int ng_bn2d_act_apply(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, uint64_t save_mean, uint64_t save_invstd,

@@ -1100,13 +1100,17 @@ class BatchNorm2d(Function):
             if _bn_split_ok(input.shape):
                 # statistics now; the normalise pass only if somebody other than an FP16x3 convolution reads y
                 absmax = DeviceBuffer((1,))
+                # the recipe keeps its own copies of gamma / beta (written by the statistics kernel): the optimizers
+                # update parameters in place, and an activation read after optimizer.step() must still be this step's
+                snap = DeviceBuffer((2 * c,))
                 _lib().ng_bn2d_act_fwd_stats(input.ptr, gamma.ptr, beta.ptr, rm, rv, save_mean.ptr, save_invstd.ptr,
-                                             absmax.ptr, n, c, hw, float(eps), float(momentum), act)
+                                             absmax.ptr, snap.ptr, n, c, hw, float(eps), float(momentum), act)
+                gamma_s, beta_s = DeviceBuffer.alias_at(snap, 0, (c,)), DeviceBuffer.alias_at(snap, c, (c,))
 
                 def apply(ptr, x=input):
-                    _lib().ng_bn2d_act_apply(ptr, x.ptr, gamma.ptr, beta.ptr, save_mean.ptr, save_invstd.ptr, n, c, hw, act)
+                    _lib().ng_bn2d_act_apply(ptr, x.ptr, gamma_s.ptr, beta_s.ptr, save_mean.ptr, save_invstd.ptr, n, c, hw, act)
 
-                out = LazyBuffer(input.shape, apply, "bn_fwd", (input, gamma, beta, save_mean, save_invstd, act, absmax))
+                out = LazyBuffer(input.shape, apply, "bn_fwd", (input, gamma_s, beta_s, save_mean, save_invstd, act, absmax))
                 out.absmax = absmax
             else:
                 out = DeviceBuffer(input.shape)

@@ -38,7 +38,7 @@ def _one_call_and_split(lib, dev, n, c, hw, act):
                         m1.ptr, i1.ptr, n, c, hw, act)
     y2, m2, i2, dx2, dg2, db2 = B(n, c, hw), B(c), B(c), B(n, c, hw), B(c), B(c)
     absmax, sums, bound = B(1), B(2 * c + 1), B(1)
-    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, m2.ptr, i2.ptr, absmax.ptr, n, c, hw,
+    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, m2.ptr, i2.ptr, absmax.ptr, 0, n, c, hw,
                               1e-5, 0.1, act)
     lib.ng_bn2d_act_apply(y2.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, m2.ptr, i2.ptr, n, c, hw, act)
     lib.ng_bn2d_act_bwd_sums(dg2.ptr, db2.ptr, sums.ptr, bound.ptr, dev["dy"].ptr, dev["x"].ptr, dev["gamma"].ptr,
@@ -176,7 +176,7 @@ def _check_fused_maxpool(shape, act):
     xq = np.round(host["x"] * 2) / 2
     dev["x"] = DeviceBuffer(xq.shape, hostbuf=xq.astype(np.float32))
     y, mean, invstd, absmax = DeviceBuffer((n, c, h, w)), DeviceBuffer((c,)), DeviceBuffer((c,)), DeviceBuffer((1,))
-    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, mean.ptr, invstd.ptr, absmax.ptr,
+    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, mean.ptr, invstd.ptr, absmax.ptr, 0,
                               n, c, hw, 1e-5, 0.1, act)
     lib.ng_bn2d_act_apply(y.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, mean.ptr, invstd.ptr, n, c, hw, act)
     oh, ow = h // 2, w // 2
@@ -220,7 +220,7 @@ def _pooled_setup(shape, act, seed):
     xq = np.round(host["x"] * 2) / 2   # tie-rich
     dev["x"] = DeviceBuffer(xq.shape, hostbuf=xq.astype(np.float32))
     mean, invstd, absmax = DeviceBuffer((c,)), DeviceBuffer((c,)), DeviceBuffer((1,))
-    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, mean.ptr, invstd.ptr, absmax.ptr,
+    lib.ng_bn2d_act_fwd_stats(dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, mean.ptr, invstd.ptr, absmax.ptr, 0,
                               n, c, hw, 1e-5, 0.1, act)
     oh, ow = h // 2, w // 2
     pooled = DeviceBuffer((n, c, oh, ow))
@@ -321,3 +321,29 @@ def test_dx_pass_with_channel_sums_emulated(act):
 def test_dx_pass_with_channel_sums(shape, act):
     H.use_cuda_library()
     _check_dx_with_channel_sums(shape, act)
+
+
+def test_recipe_is_immune_to_in_place_parameter_updates_emulated():
+    """The optimizers update parameters in place; a BatchNorm output that is materialised only after the step (a user
+    reading an intermediate activation late) must still hold the values of the step that produced it: the recipe
+    carries its own snapshot of gamma / beta."""
+    from nanograd_b200 import backend as B
+    from nanograd_b200.nn import ops_cuda
+    from nanograd_b200.nn.buffer import DeviceBuffer, LazyBuffer
+    H.use_emulated_library()
+    n, c, h, w = 2, 64, 2, 4
+    host, dev = _setup(n, c, h, w, seed=9)
+
+    class Ctx:
+        def save_for_backward(self, *a):
+            self.saved = a
+
+    out = ops_cuda.BatchNorm2d.forward(Ctx(), dev["x"], dev["gamma"], dev["beta"], None, None, training=True, relu=True)
+    assert isinstance(out, LazyBuffer) and out.pending
+    eager = DeviceBuffer((n, c, h, w))
+    m, i = DeviceBuffer((c,)), DeviceBuffer((c,))
+    B.lib().ng_bn2d_act_fwd_train(eager.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, m.ptr, i.ptr, n, c, h * w,
+                                  1e-5, 0.1, 1)
+    dev["gamma"].copy_from_host(host["gamma"] * 3 + 1)      # "optimizer.step()"
+    dev["beta"].copy_from_host(host["beta"] - 2)
+    H.assert_exact(out.numpy(), eager.numpy(), "late materialisation of a BatchNorm recipe")
