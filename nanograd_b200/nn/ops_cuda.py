@@ -1136,6 +1136,10 @@ class BatchNorm2d(Function):
             if _bn_split_ok(input.shape) and _needs(ctx, 0):
                 # reductions now; the dx pass only if somebody other than an FP16x3 convolution reads dx
                 bn_sums, bound = DeviceBuffer((2 * c + 1,)), DeviceBuffer((1,))
+                if isinstance(out, LazyBuffer) and out.kind == "bn_fwd":
+                    # the recipe below reads the forward's private copies of gamma / beta (same values now; the
+                    # parameters themselves change in place at the next optimizer step)
+                    gamma, beta = out.source[1], out.source[2]
                 pooled = None
                 if (isinstance(grad_output, LazyBuffer) and grad_output.pending and grad_output.kind == "pool_bwd"
                         and grad_output.source[2] is out):

@@ -344,6 +344,22 @@ def test_recipe_is_immune_to_in_place_parameter_updates_emulated():
     m, i = DeviceBuffer((c,)), DeviceBuffer((c,))
     B.lib().ng_bn2d_act_fwd_train(eager.ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr, 0, 0, m.ptr, i.ptr, n, c, h * w,
                                   1e-5, 0.1, 1)
+    # the backward recipe (BatchNorm's input gradient) as well
+    ctx = Ctx()
+    ctx.parents = ()
+    out2 = ops_cuda.BatchNorm2d.forward(ctx, dev["x"], dev["gamma"], dev["beta"], None, None, training=True, relu=True)
+    ctx.saved_tensors = list(ctx.saved)
+    needs = ops_cuda._needs
+    ops_cuda._needs = lambda c_, i_: True      # a bare ctx has no parents to ask
+    try:
+        dx, dg, db = ops_cuda.BatchNorm2d.backward(ctx, dev["dy"])
+    finally:
+        ops_cuda._needs = needs
+    assert isinstance(dx, LazyBuffer) and dx.pending
+    dx_eager, dg2, db2 = DeviceBuffer((n, c, h, w)), DeviceBuffer((c,)), DeviceBuffer((c,))
+    B.lib().ng_bn2d_act_bwd(dx_eager.ptr, dg2.ptr, db2.ptr, dev["dy"].ptr, dev["x"].ptr, dev["gamma"].ptr, dev["beta"].ptr,
+                            m.ptr, i.ptr, n, c, h * w, 1)
     dev["gamma"].copy_from_host(host["gamma"] * 3 + 1)      # "optimizer.step()"
     dev["beta"].copy_from_host(host["beta"] - 2)
     H.assert_exact(out.numpy(), eager.numpy(), "late materialisation of a BatchNorm recipe")
+    H.assert_exact(dx.numpy(), dx_eager.numpy(), "late materialisation of a BatchNorm gradient recipe")
