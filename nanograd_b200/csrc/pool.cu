@@ -89,6 +89,65 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(float* __restrict__ y, co
 
 // One thread per output window writes the whole input window of dx.  Rows/columns cropped by
 // the forward pass receive zero from a preceding memset (only when H % ph or W % pw != 0).
+// 2x2 windows, two horizontally adjacent ones per thread: two 128-bit loads, one 64-bit store (a thread of the generic
+// kernel keeps 16 bytes in flight: 3.7 TB/s).  W % 4 == 0, x 16-byte and y 8-byte aligned.
+template <bool IS_MAX, bool BN>
+__global__ void __launch_bounds__(256) pool2x2_fwd_pair_kernel(float* __restrict__ y, const float* __restrict__ x,
+                                                               int64_t NC, int H, int W, FastDiv f_op, FastDiv f_oh,
+                                                               PoolBN bn) {
+  const int OH = H >> 1, OW = W >> 1, OP = OW >> 1;
+  const int64_t total = NC * OH * OP;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    int op, oh;
+    int64_t nc;
+    if (f_op.d && total < (1LL << 31)) {
+      const uint32_t t = fastdiv((uint32_t)o, f_op);
+      op = (int)((uint32_t)o - t * f_op.d);
+      const uint32_t u = fastdiv(t, f_oh);
+      oh = (int)(t - u * f_oh.d);
+      nc = u;
+    } else {
+      op = (int)(o % OP);
+      const int64_t t = o / OP;
+      oh = (int)(t % OH);
+      nc = t / OH;
+    }
+    const float* src = x + (nc * H + 2 * (int64_t)oh) * W + 4 * op;
+    float4 a = *reinterpret_cast<const float4*>(src);
+    float4 b = *reinterpret_cast<const float4*>(src + W);
+    if (BN) {
+      const int c = (int)(nc % bn.C);
+      const float mu = __ldg(bn.mean + c), ka = __ldg(bn.gamma + c) * __ldg(bn.invstd + c), kb = __ldg(bn.beta + c);
+      a.x = pool_bn(a.x, mu, ka, kb, bn.act); a.y = pool_bn(a.y, mu, ka, kb, bn.act);
+      a.z = pool_bn(a.z, mu, ka, kb, bn.act); a.w = pool_bn(a.w, mu, ka, kb, bn.act);
+      b.x = pool_bn(b.x, mu, ka, kb, bn.act); b.y = pool_bn(b.y, mu, ka, kb, bn.act);
+      b.z = pool_bn(b.z, mu, ka, kb, bn.act); b.w = pool_bn(b.w, mu, ka, kb, bn.act);
+    }
+    float2 r;
+    if (IS_MAX) {
+      r.x = fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+      r.y = fmaxf(fmaxf(a.z, a.w), fmaxf(b.z, b.w));
+    } else {
+      r.x = ((a.x + a.y) + (b.x + b.y)) * 0.25f;
+      r.y = ((a.z + a.w) + (b.z + b.w)) * 0.25f;
+    }
+    *reinterpret_cast<float2*>(y + (nc * OH + oh) * OW + 2 * op) = r;
+  }
+}
+
+// true when the pair kernel applies (and launches it)
+template <bool IS_MAX, bool BN>
+static bool launch_pool2x2_pair(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, int pw, const PoolBN& bn) {
+  if (ph != 2 || pw != 2 || H % 2 || W % 4 || (x & 15u) || (y & 7u) || NC <= 0) return false;
+  const int64_t n = NC * (H / 2) * (W / 4);
+  int64_t g = ceil_div(n, 256);
+  const int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 16;
+  if (g > cap) g = cap;
+  NG_LAUNCH((pool2x2_fwd_pair_kernel<IS_MAX, BN>), (int)g, 256, 0, dptr<float>(y), dptr<const float>(x), NC, H, W,
+            make_fastdiv(W / 4), make_fastdiv(H / 2), bn);
+  return true;
+}
+
 template <bool IS_MAX, bool BN = false>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy,
                                                        const float* __restrict__ x, const float* __restrict__ y,
@@ -202,6 +261,10 @@ int ng_maxpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, i
   if (make_pool(p, "ng_maxpool2d_fwd", NC, H, W, ph, pw, x, x)) return 1;
   const int64_t n = NC * p.OH * p.OW;
   if (n <= 0) return 0;
+  if (launch_pool2x2_pair<true, false>(y, x, NC, H, W, ph, pw, PoolBN{nullptr, nullptr, nullptr, nullptr, 1, 0})) {
+    NG_CHECK_LAUNCH();
+    return 0;
+  }
   NG_LAUNCH((pool_fwd_kernel<true>), pgrid(n), 256, 0, dptr<float>(y), dptr<const float>(x), p);
   NG_CHECK_LAUNCH();
   return 0;
@@ -214,6 +277,10 @@ int ng_avgpool2d_fwd(uint64_t y, uint64_t x, int64_t NC, int H, int W, int ph, i
   if (make_pool(p, "ng_avgpool2d_fwd", NC, H, W, ph, pw, x, x)) return 1;
   const int64_t n = NC * p.OH * p.OW;
   if (n <= 0) return 0;
+  if (launch_pool2x2_pair<false, false>(y, x, NC, H, W, ph, pw, PoolBN{nullptr, nullptr, nullptr, nullptr, 1, 0})) {
+    NG_CHECK_LAUNCH();
+    return 0;
+  }
   NG_LAUNCH((pool_fwd_kernel<false>), pgrid(n), 256, 0, dptr<float>(y), dptr<const float>(x), p);
   NG_CHECK_LAUNCH();
   return 0;
@@ -259,6 +326,10 @@ int ng_maxpool2d_fwd_bn(uint64_t y, uint64_t x, uint64_t gamma, uint64_t beta, u
   const int64_t n = NC * p.OH * p.OW;
   if (n <= 0) return 0;
   const PoolBN bn{dptr<const float>(gamma), dptr<const float>(beta), dptr<const float>(mean), dptr<const float>(invstd), C, act};
+  if (launch_pool2x2_pair<true, true>(y, x, NC, H, W, ph, pw, bn)) {
+    NG_CHECK_LAUNCH();
+    return 0;
+  }
   NG_LAUNCH((pool_fwd_kernel<true, true>), pgrid(n), 256, 0, dptr<float>(y), dptr<const float>(x), p, bn);
   NG_CHECK_LAUNCH();
   return 0;
