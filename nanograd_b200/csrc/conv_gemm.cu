@@ -1272,6 +1272,274 @@ static int launch_wgrad_direct(float* dw, const float* dy, const float* x, int N
   return 0;
 }
 
+// =====================================================================================
+// Sliding-window direct wgrad (3 x 3, stride 1, narrow layers with K % 4 == 0): the kernel above spends 8 LDS.128 per
+// 72 FFMA (the shared-memory return path, 128 B/clk/SM, saturates at half the FFMA rate) and stalls the whole CTA on
+// every tile load.  Here thread (kg, c, cs) owns dW[4 kg .. 4 kg + 3][c][0..2][0..2] and walks one 4-pixel column
+// strip down the tile's rows: output row tr needs input rows tr .. tr + 2, two of which are already in registers, so a
+// row costs 4 LDS.128 of dy + one LDS.128 + LDS.64 of x for 144 FFMA.  Tiles are double-buffered with cp.async
+// (zero-filled at the borders), dy is stored [row][strip][k][4] so that a warp's reads are contiguous, the x channel
+// pitch is 4 (mod 32) words.  One partial per CTA, fixed-order reduce (splitk_reduce_wide_kernel).
+// =====================================================================================
+struct WgradSlideP {
+  const float* x;
+  const float* dy;
+  float* ws;  // [gridDim.x][K][C*9]
+  int N, C, H, W, K, OH, OW, OWP, pad_t, pad_l;
+  int TR, row_blocks, tiles, KG, CS, CSN, xrows, xpitch, cpitch, tile_floats;
+  FastDiv f_dcols, f_tr, f_xcols, f_xrows, f_rb;
+};
+
+template <int VEC>
+__device__ __forceinline__ void cp_async_zfill(float* dst, const float* src, bool ok) {
+#ifdef NG_EMU
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) dst[i] = ok ? src[i] : 0.f;
+#else
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int bytes = ok ? VEC * 4 : 0;
+  if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef NG_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef NG_EMU
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+
+template <int VEC>
+__device__ __forceinline__ void wgrad_slide_issue(const WgradSlideP& p, float* buf, int tile) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n = (int)fastdiv((uint32_t)tile, p.f_rb);
+  const int oh0 = (tile - n * p.row_blocks) * p.TR;
+  float* dys = buf;                              // [TR][CS][K][4]
+  float* xs = buf + p.TR * p.OWP * p.K;          // [C][cpitch], rows of xpitch: column j holds input column j - pad_l
+  const int dcols = p.OWP / VEC, dtotal = p.K * p.TR * dcols;
+  for (int e = tid; e < dtotal; e += nthr) {
+    const int row = (int)fastdiv((uint32_t)e, p.f_dcols), ow = (e - row * dcols) * VEC;
+    const int kk = (int)fastdiv((uint32_t)row, p.f_tr), tr = row - kk * p.TR;
+    const bool ok = ow < p.OW && oh0 + tr < p.OH;
+    const float* src = ok ? p.dy + ((long long)(n * p.K + kk) * p.OH + oh0 + tr) * p.OW + ow : p.dy;
+    cp_async_zfill<VEC>(dys + (((tr * p.CS + (ow >> 2)) * p.K + kk) << 2) + (ow & 3), src, ok);
+  }
+  const int xcols = p.xpitch / VEC, xtotal = p.C * p.xrows * xcols;
+  for (int e = tid; e < xtotal; e += nthr) {
+    const int row = (int)fastdiv((uint32_t)e, p.f_xcols), j = (e - row * xcols) * VEC;
+    const int c = (int)fastdiv((uint32_t)row, p.f_xrows), rr = row - c * p.xrows;
+    const int ih = oh0 + rr - p.pad_t, iw = j - p.pad_l;
+    const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+    const float* src = ok ? p.x + ((long long)(n * p.C + c) * p.H + ih) * p.W + iw : p.x;
+    cp_async_zfill<VEC>(xs + c * p.cpitch + rr * p.xpitch + j, src, ok);
+  }
+  cp_async_commit();
+}
+
+template <int KT, int VEC>
+__global__ void __launch_bounds__(512, 1) conv_wgrad_slide_kernel(const __grid_constant__ WgradSlideP p) {
+  NG_DYN_SMEM(float, sm);
+  const int tid = threadIdx.x;
+  const int base = p.KG * p.C;
+  const int ps = tid / base, tb = tid - ps * base;
+  const int kg = tb % p.KG, c = tb / p.KG;
+  float acc[KT][3][3];
+#pragma unroll
+  for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) acc[kk][r][0] = acc[kk][r][1] = acc[kk][r][2] = 0.f;
+  const int dstep = p.CS * p.K * 4;
+  int it = 0;
+  if ((int)blockIdx.x < p.tiles) wgrad_slide_issue<VEC>(p, sm, blockIdx.x);
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    float* buf = sm + (it & 1) * p.tile_floats;
+    const int next = tile + gridDim.x;
+    if (next < p.tiles) {
+      wgrad_slide_issue<VEC>(p, sm + ((it + 1) & 1) * p.tile_floats, next);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int n = (int)fastdiv((uint32_t)tile, p.f_rb);
+    const int oh0 = (tile - n * p.row_blocks) * p.TR;
+    const int rows = p.OH - oh0 < p.TR ? p.OH - oh0 : p.TR;
+    const float* dys = buf;
+    const float* xs = buf + p.TR * p.OWP * p.K + c * p.cpitch;
+    // (threads past base * CSN only round the block up to whole warps: they copy tiles and idle here)
+    for (int cs = ps < p.CSN ? ps : p.CS; cs < p.CS; cs += p.CSN) {
+      const float* xr = xs + cs * 4;
+      const float* dr = dys + ((cs * p.K + kg * KT) << 2);
+      float4 xa[3];
+      float2 xb[3];
+#define NG_SLIDE_LOADX(slot, row)                                               \
+  do {                                                                          \
+    xa[slot] = *reinterpret_cast<const float4*>(xr + (row) * p.xpitch);         \
+    xb[slot] = *reinterpret_cast<const float2*>(xr + (row) * p.xpitch + 4);     \
+  } while (0)
+#define NG_SLIDE_FMA(a3, d, A, B)                                                                         \
+  do {                                                                                                    \
+    a3[0] = fmaf(d.x, A.x, fmaf(d.y, A.y, fmaf(d.z, A.z, fmaf(d.w, A.w, a3[0]))));                        \
+    a3[1] = fmaf(d.x, A.y, fmaf(d.y, A.z, fmaf(d.z, A.w, fmaf(d.w, B.x, a3[1]))));                        \
+    a3[2] = fmaf(d.x, A.z, fmaf(d.y, A.w, fmaf(d.z, B.x, fmaf(d.w, B.y, a3[2]))));                        \
+  } while (0)
+#define NG_SLIDE_STEP(i0, i1, i2)                                                                         \
+  do {                                                                                                    \
+    NG_SLIDE_LOADX(i2, tr + 2);                                                                           \
+    float4 d[KT];                                                                                         \
+    _Pragma("unroll") for (int kk = 0; kk < KT; ++kk) d[kk] = *reinterpret_cast<const float4*>(dr + tr * dstep + kk * 4); \
+    _Pragma("unroll") for (int kk = 0; kk < KT; ++kk) {                                                   \
+      NG_SLIDE_FMA(acc[kk][0], d[kk], xa[i0], xb[i0]);                                                    \
+      NG_SLIDE_FMA(acc[kk][1], d[kk], xa[i1], xb[i1]);                                                    \
+      NG_SLIDE_FMA(acc[kk][2], d[kk], xa[i2], xb[i2]);                                                    \
+    }                                                                                                     \
+  } while (0)
+      NG_SLIDE_LOADX(0, 0);
+      NG_SLIDE_LOADX(1, 1);
+      int tr = 0;
+      while (true) {
+        NG_SLIDE_STEP(0, 1, 2);
+        if (++tr >= rows) break;
+        NG_SLIDE_STEP(1, 2, 0);
+        if (++tr >= rows) break;
+        NG_SLIDE_STEP(2, 0, 1);
+        if (++tr >= rows) break;
+      }
+#undef NG_SLIDE_STEP
+#undef NG_SLIDE_FMA
+#undef NG_SLIDE_LOADX
+    }
+    __syncthreads();   // the buffer is refilled by the next iteration's prefetch
+  }
+  // fold the CSN column-strip subsets (fixed order), then one partial per CTA
+  constexpr int NA = KT * 9;
+  if (ps > 0 && ps < p.CSN) {
+    float* slot = sm + ((size_t)(ps - 1) * base + tb) * NA;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) slot[kk * 9 + r * 3 + t] = acc[kk][r][t];
+  }
+  __syncthreads();
+  if (ps == 0) {
+    for (int o = 1; o < p.CSN; ++o) {
+      const float* slot = sm + ((size_t)(o - 1) * base + tb) * NA;
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int t = 0; t < 3; ++t) acc[kk][r][t] += slot[kk * 9 + r * 3 + t];
+    }
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      float* out = p.ws + ((long long)blockIdx.x * p.K + kg * KT + kk) * (p.C * 9) + c * 9;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) out[r * 3 + t] = acc[kk][r][t];
+    }
+  }
+}
+
+// Returns 0 when done, -1 when the shape is not one this kernel takes, > 0 on error.
+static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
+                              int stride, int pad_t, int pad_l, int OH, int OW) {
+  constexpr int KT = 4;
+  if (R != 3 || S != 3 || stride != 1 || C > 32 || K > 32 || C < 8 || K % KT != 0 || C * K > 512) return -1;
+#ifdef NG_EMU
+  const long long min_pixels = 1024;
+#else
+  const long long min_pixels = 65536;
+#endif
+  if ((long long)N * OH * OW < min_pixels) return -1;
+  WgradSlideP q;
+  memset(&q, 0, sizeof(q));
+  q.x = x; q.dy = dy;
+  q.N = N; q.C = C; q.H = H; q.W = W; q.K = K; q.OH = OH; q.OW = OW;
+  q.OWP = (OW + 3) & ~3;
+  q.pad_t = pad_t; q.pad_l = pad_l;
+  q.KG = K / KT;
+  q.CS = q.OWP / 4;
+  const int base = q.KG * C;
+  if (base > 512 || base < 32) return -1;
+  q.CSN = 512 / base;
+  if (q.CSN > q.CS) q.CSN = q.CS;
+  const int threads = (base * q.CSN + 31) & ~31;
+  q.xpitch = q.OWP + 4;
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  // rows per tile: two tiles must fit 200 KB; among the row-block counts that do, the one with the fewest
+  // (rows + window start-up) x rounds of the persistent grid
+  int best_rb = 0, best_tr = 0, best_cp = 0;
+  double best_cost = 0.0;
+  for (int rb = 1; rb <= OH && rb <= 64; ++rb) {
+    const int TR = (int)ceil_div(OH, rb);
+    if ((int)ceil_div(OH, TR) != rb) continue;
+    int cp = (TR + 2) * q.xpitch;
+    cp += ((4 - cp % 32) + 32) % 32;   // channel pitch == 4 (mod 32) words: 8 channels' float4 reads hit 32 distinct banks
+    const size_t tile = (size_t)K * TR * q.OWP + (size_t)C * cp;
+    if (2 * tile * sizeof(float) > 200u * 1024u) continue;
+    const long long tiles = (long long)N * rb;
+    const long long grid = tiles < sms ? tiles : sms;
+    const double cost = (double)ceil_div(tiles, grid) * (TR + 2);
+    if (best_rb == 0 || cost < best_cost) { best_rb = rb; best_tr = TR; best_cp = cp; best_cost = cost; }
+  }
+  if (best_rb == 0) return -1;
+  q.TR = best_tr;
+  q.row_blocks = best_rb;
+  q.tiles = N * best_rb;
+  q.xrows = best_tr + 2;
+  q.cpitch = best_cp;
+  q.tile_floats = K * q.TR * q.OWP + C * q.cpitch;
+  size_t smem = 2 * sizeof(float) * (size_t)q.tile_floats;
+  const size_t fold = sizeof(float) * (size_t)(q.CSN - 1) * base * KT * 9;
+  if (fold > smem) smem = fold;
+  if (smem > 220u * 1024u) return -1;
+  // 8-byte copies when every row start and every zero-fill boundary is even
+  const bool vec2 = OW % 2 == 0 && W % 2 == 0 && pad_l % 2 == 0 && (((uintptr_t)x | (uintptr_t)dy) & 7) == 0;
+  q.f_dcols = make_fastdiv(q.OWP / (vec2 ? 2 : 1));
+  q.f_xcols = make_fastdiv(q.xpitch / (vec2 ? 2 : 1));
+  q.f_tr = make_fastdiv(q.TR);
+  q.f_xrows = make_fastdiv(q.xrows);
+  q.f_rb = make_fastdiv(q.row_blocks);
+  const int grid = q.tiles < sms ? q.tiles : sms;
+  const long long out_elems = (long long)K * C * 9;
+  float* ws = nullptr;
+  if (pool_alloc((void**)&ws, (uint64_t)((long long)grid * out_elems) * sizeof(float))) return 1;
+  q.ws = ws;
+#ifndef NG_EMU
+  {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_slide_kernel<KT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_wgrad_slide_kernel<KT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) {
+        pool_free(ws);
+        return set_error("conv_wgrad_slide_kernel: %s", cudaGetErrorString(e));
+      }
+      attr_done = true;
+    }
+  }
+#endif
+  ProfScope prof_(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
+                  4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
+  if (vec2) NG_LAUNCH((conv_wgrad_slide_kernel<KT, 2>), grid, threads, smem, q);
+  else NG_LAUNCH((conv_wgrad_slide_kernel<KT, 1>), grid, threads, smem, q);
+  NG_CHECK_LAUNCH();
+  NG_LAUNCH(splitk_reduce_wide_kernel, (int)ceil_div(out_elems, 64), 512, 0, dw, (const float*)ws, grid, out_elems);
+  NG_CHECK_LAUNCH();
+  pool_free(ws);
+  return 0;
+}
+
 }  // namespace ng
 
 using namespace ng;
@@ -1542,8 +1810,11 @@ int ng_conv2d_wgrad(uint64_t dw, uint64_t dy, uint64_t x, int N, int C, int H, i
   NG_REQUIRE(!(flags & (NG_F_X_NHWC | NG_F_DY_NHWC)),
              "ng_conv2d_wgrad: staged NHWC operands given but this shape does not take the tensor-core kernel");
   {
-    // narrow layers (both channel counts <= 32): direct kernel (see conv_wgrad_direct_kernel)
-    const int rc = launch_wgrad_direct(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R, S,
+    // narrow layers (both channel counts <= 32): direct kernels (see conv_wgrad_slide_kernel, conv_wgrad_direct_kernel)
+    int rc = launch_wgrad_slide(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R, S, stride,
+                                pad_t, pad_l, OH, OW);
+    if (rc >= 0) return rc;
+    rc = launch_wgrad_direct(dptr<float>(dw), dptr<const float>(dy), dptr<const float>(x), N, C, H, W, K, R, S,
                                        stride, pad_t, pad_l, OH, OW);
     if (rc >= 0) return rc;
   }

@@ -29,12 +29,15 @@ def _truth(x, w, dy, pad):
     return y, dx, dw
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
-def test_narrow_layer_kernels_match_float64(shape):
+# fixture-sized shapes for the host emulation (>= 1024 output pixels): even / odd widths (8- and 4-byte cp.async tiles
+# of the sliding-window wgrad), padding 0 / 1, K % 4 != 0 (the register-tile wgrad), ragged last row block
+EMU_SHAPES = [(5, 16, 18, 18, 16, 3, 3, 0), (6, 8, 16, 15, 8, 3, 3, 1), (5, 12, 17, 18, 20, 3, 3, 1),
+              (6, 16, 16, 16, 10, 3, 3, 0), (3, 32, 22, 20, 16, 3, 3, 0)]
+
+
+def _check(shape):
     from nanograd_b200 import backend as B
     from nanograd_b200.nn.buffer import DeviceBuffer
-    H.use_cuda_library()
     lib = B.lib()
     N, C, Hh, W, K, R, S, pad = shape
     OH, OW = Hh + 2 * pad - R + 1, W + 2 * pad - S + 1
@@ -54,3 +57,16 @@ def test_narrow_layer_kernels_match_float64(shape):
     H.assert_close(y.numpy(), ty, H.RTOL_FP32, f"fprop {shape}")
     H.assert_close(dx.numpy(), tdx, H.RTOL_FP32, f"dgrad {shape}")
     H.assert_close(dw.numpy(), tdw, H.RTOL_FP32, f"wgrad {shape}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", SHAPES + EMU_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_narrow_layer_kernels_match_float64(shape):
+    H.use_cuda_library()
+    _check(shape)
+
+
+@pytest.mark.parametrize("shape", EMU_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_narrow_layer_kernels_match_float64_emulated(shape):
+    H.use_emulated_library()
+    _check(shape)
