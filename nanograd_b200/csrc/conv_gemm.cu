@@ -1278,28 +1278,48 @@ static int launch_wgrad_direct(float* dw, const float* dy, const float* x, int N
 // every tile load.  Here thread (kg, c, cs) owns dW[4 kg .. 4 kg + 3][c][0..2][0..2] and walks one 4-pixel column
 // strip down the tile's rows: output row tr needs input rows tr .. tr + 2, two of which are already in registers, so a
 // row costs 4 LDS.128 of dy + one LDS.128 + LDS.64 of x for 144 FFMA.  Tiles are double-buffered with cp.async
-// (zero-filled at the borders), dy is stored [row][strip][k][4] so that a warp's reads are contiguous, the x channel
-// pitch is 4 (mod 32) words.  One partial per CTA, fixed-order reduce (splitk_reduce_wide_kernel).
+// (zero-filled at the borders), dy is stored [row][strip][k][4] (+ 4 pad words per strip) so that a warp's reads are
+// contiguous and the tile writes conflict-free, the x channel pitch is 4 (mod 32) words.  One partial per CTA, fixed-order reduce (splitk_reduce_wide_kernel).
 // =====================================================================================
 struct WgradSlideP {
   const float* x;
   const float* dy;
   float* ws;  // [gridDim.x][K][C*9]
   int N, C, H, W, K, OH, OW, OWP, pad_t, pad_l;
-  int TR, row_blocks, tiles, KG, CS, CSN, xrows, xpitch, cpitch, tile_floats;
-  FastDiv f_dcols, f_tr, f_xcols, f_xrows, f_rb;
+  int TR, row_blocks, tiles, KG, CS, CSN, SP, xrows, xpitch, cpitch, tile_floats;
+  int d_lshift, x_lshift;   // log2 of the lanes that span a dy / x tile row in the copy
+  FastDiv f_rb;
 };
 
+// cp.async of VEC floats with the ignore-src predicate: zeros are written when !ok (the source-size form costs ~20 extra
+// instructions per copy).  dst is a shared-window address (a generic pointer under the host emulation).
+#ifdef NG_EMU
+typedef float* smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(float* p) { return p; }
+#define NG_SMEM_STEP(words) (words)
+#else
+typedef uint32_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(float* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#define NG_SMEM_STEP(words) (4 * (words))
+#endif
 template <int VEC>
-__device__ __forceinline__ void cp_async_zfill(float* dst, const float* src, bool ok) {
+__device__ __forceinline__ void cp_async_zfill(smem_addr_t dst, const float* src, bool ok) {
 #ifdef NG_EMU
 #pragma unroll
   for (int i = 0; i < VEC; ++i) dst[i] = ok ? src[i] : 0.f;
 #else
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-  const int bytes = ok ? VEC * 4 : 0;
-  if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
-  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+  if (VEC == 4)
+    asm volatile("{\n .reg .pred p;\n setp.eq.u32 p, %2, 0;\n cp.async.cg.shared.global [%0], [%1], 16, p;\n}\n" ::"r"(dst),
+                 "l"(src), "r"((int)ok)
+                 : "memory");
+  else if (VEC == 2)
+    asm volatile("{\n .reg .pred p;\n setp.eq.u32 p, %2, 0;\n cp.async.ca.shared.global [%0], [%1], 8, p;\n}\n" ::"r"(dst),
+                 "l"(src), "r"((int)ok)
+                 : "memory");
+  else
+    asm volatile("{\n .reg .pred p;\n setp.eq.u32 p, %2, 0;\n cp.async.ca.shared.global [%0], [%1], 4, p;\n}\n" ::"r"(dst),
+                 "l"(src), "r"((int)ok)
+                 : "memory");
 #endif
 }
 __device__ __forceinline__ void cp_async_commit() {
@@ -1314,34 +1334,58 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
-template <int VEC>
+// Tile copy: a warp owns whole channels and walks their rows with (a power-of-two group of) lanes across a row; the
+// column tests are hoisted and source offset / destination address advance by a constant per row, so a copy costs about
+// ten instructions (a flat element index costs two divisions per copy: a third of the kernel's issue slots).
+template <int KT, int VD, int VX>
 __device__ __forceinline__ void wgrad_slide_issue(const WgradSlideP& p, float* buf, int tile) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int n = (int)fastdiv((uint32_t)tile, p.f_rb);
   const int oh0 = (tile - n * p.row_blocks) * p.TR;
-  float* dys = buf;                              // [TR][CS][K][4]
-  float* xs = buf + p.TR * p.OWP * p.K;          // [C][cpitch], rows of xpitch: column j holds input column j - pad_l
-  const int dcols = p.OWP / VEC, dtotal = p.K * p.TR * dcols;
-  for (int e = tid; e < dtotal; e += nthr) {
-    const int row = (int)fastdiv((uint32_t)e, p.f_dcols), ow = (e - row * dcols) * VEC;
-    const int kk = (int)fastdiv((uint32_t)row, p.f_tr), tr = row - kk * p.TR;
-    const bool ok = ow < p.OW && oh0 + tr < p.OH;
-    const float* src = ok ? p.dy + ((long long)(n * p.K + kk) * p.OH + oh0 + tr) * p.OW + ow : p.dy;
-    cp_async_zfill<VEC>(dys + (((tr * p.CS + (ow >> 2)) * p.K + kk) << 2) + (ow & 3), src, ok);
+  // dy tile [TR][CS][SP]: per strip KG groups of KT float4 + 4 pad words
+  {
+    const float* img = p.dy + (long long)n * p.K * p.OH * p.OW;
+    const int cols = p.OWP / VD, lpr = 1 << p.d_lshift, rpi = 32 >> p.d_lshift;
+    const int lcol = lane & (lpr - 1), lsub = lane >> p.d_lshift;
+    const int dplane = p.OH * p.OW, drows = p.OH - oh0, rstep = p.CS * p.SP;
+    for (int col = lcol; col < cols; col += lpr) {
+      const int ow = col * VD;
+      const bool cok = ow < p.OW;
+      for (int kk = warp; kk < p.K; kk += nwarps) {
+        int off = kk * dplane + (oh0 + lsub) * p.OW + ow;
+        smem_addr_t dst = smem_addr(buf + (kk / KT) * (KT * 4 + 4) + ((kk % KT) << 2) + lsub * rstep + (ow >> 2) * p.SP + (ow & 3));
+        for (int tr = lsub; tr < p.TR; tr += rpi, off += rpi * p.OW, dst += NG_SMEM_STEP(rpi * rstep)) {
+          const bool ok = cok && tr < drows;
+          cp_async_zfill<VD>(dst, img + (ok ? off : 0), ok);
+        }
+      }
+    }
   }
-  const int xcols = p.xpitch / VEC, xtotal = p.C * p.xrows * xcols;
-  for (int e = tid; e < xtotal; e += nthr) {
-    const int row = (int)fastdiv((uint32_t)e, p.f_xcols), j = (e - row * xcols) * VEC;
-    const int c = (int)fastdiv((uint32_t)row, p.f_xrows), rr = row - c * p.xrows;
-    const int ih = oh0 + rr - p.pad_t, iw = j - p.pad_l;
-    const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-    const float* src = ok ? p.x + ((long long)(n * p.C + c) * p.H + ih) * p.W + iw : p.x;
-    cp_async_zfill<VEC>(xs + c * p.cpitch + rr * p.xpitch + j, src, ok);
+  // x tile [C][cpitch], rows of xpitch: column j holds input column j - pad_l
+  {
+    const float* img = p.x + (long long)n * p.C * p.H * p.W;
+    float* xs = buf + p.TR * p.CS * p.SP;
+    const int cols = p.xpitch / VX, lpr = 1 << p.x_lshift, rpi = 32 >> p.x_lshift;
+    const int lcol = lane & (lpr - 1), lsub = lane >> p.x_lshift;
+    const int xplane = p.H * p.W;
+    const int rr_lo = p.pad_t - oh0, rr_hi = p.H + p.pad_t - oh0;   // valid rr in [rr_lo, rr_hi)
+    for (int col = lcol; col < cols; col += lpr) {
+      const int j = col * VX;
+      const bool cok = j >= p.pad_l && j < p.W + p.pad_l;
+      for (int c = warp; c < p.C; c += nwarps) {
+        int off = c * xplane + (oh0 - p.pad_t + lsub) * p.W + j - p.pad_l;
+        smem_addr_t dst = smem_addr(xs + c * p.cpitch + lsub * p.xpitch + j);
+        for (int rr = lsub; rr < p.xrows; rr += rpi, off += rpi * p.W, dst += NG_SMEM_STEP(rpi * p.xpitch)) {
+          const bool ok = cok && rr >= rr_lo && rr < rr_hi;
+          cp_async_zfill<VX>(dst, img + (ok ? off : 0), ok);
+        }
+      }
+    }
   }
   cp_async_commit();
 }
 
-template <int KT, int VEC>
+template <int KT, int VD, int VX>
 __global__ void __launch_bounds__(512, 1) conv_wgrad_slide_kernel(const __grid_constant__ WgradSlideP p) {
   NG_DYN_SMEM(float, sm);
   const int tid = threadIdx.x;
@@ -1353,14 +1397,14 @@ __global__ void __launch_bounds__(512, 1) conv_wgrad_slide_kernel(const __grid_c
   for (int kk = 0; kk < KT; ++kk)
 #pragma unroll
     for (int r = 0; r < 3; ++r) acc[kk][r][0] = acc[kk][r][1] = acc[kk][r][2] = 0.f;
-  const int dstep = p.CS * p.K * 4;
+  const int dstep = p.CS * p.SP;
   int it = 0;
-  if ((int)blockIdx.x < p.tiles) wgrad_slide_issue<VEC>(p, sm, blockIdx.x);
+  if ((int)blockIdx.x < p.tiles) wgrad_slide_issue<KT, VD, VX>(p, sm, blockIdx.x);
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
     float* buf = sm + (it & 1) * p.tile_floats;
     const int next = tile + gridDim.x;
     if (next < p.tiles) {
-      wgrad_slide_issue<VEC>(p, sm + ((it + 1) & 1) * p.tile_floats, next);
+      wgrad_slide_issue<KT, VD, VX>(p, sm + ((it + 1) & 1) * p.tile_floats, next);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -1370,11 +1414,11 @@ __global__ void __launch_bounds__(512, 1) conv_wgrad_slide_kernel(const __grid_c
     const int oh0 = (tile - n * p.row_blocks) * p.TR;
     const int rows = p.OH - oh0 < p.TR ? p.OH - oh0 : p.TR;
     const float* dys = buf;
-    const float* xs = buf + p.TR * p.OWP * p.K + c * p.cpitch;
+    const float* xs = buf + p.TR * p.CS * p.SP + c * p.cpitch;
     // (threads past base * CSN only round the block up to whole warps: they copy tiles and idle here)
     for (int cs = ps < p.CSN ? ps : p.CS; cs < p.CS; cs += p.CSN) {
       const float* xr = xs + cs * 4;
-      const float* dr = dys + ((cs * p.K + kg * KT) << 2);
+      const float* dr = dys + cs * p.SP + kg * (KT * 4 + 4);
       float4 xa[3];
       float2 xb[3];
 #define NG_SLIDE_LOADX(slot, row)                                               \
@@ -1468,6 +1512,11 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
   q.pad_t = pad_t; q.pad_l = pad_l;
   q.KG = K / KT;
   q.CS = q.OWP / 4;
+  // a strip holds KG groups of KT float4 + 4 pad words (group pitch 20 words: the four groups a warp reads together sit in
+  // distinct banks); strip pitch = 4 x odd words, so the 8-byte tile writes of 8 neighbouring strips (one dy row
+  // segment) land in 32 distinct banks
+  q.SP = q.KG * (KT * 4 + 4);
+  if ((q.SP / 4) % 2 == 0) q.SP += 4;
   const int base = q.KG * C;
   if (base > 512 || base < 32) return -1;
   q.CSN = 512 / base;
@@ -1479,16 +1528,18 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
   // (rows + window start-up) x rounds of the persistent grid
   int best_rb = 0, best_tr = 0, best_cp = 0;
   double best_cost = 0.0;
+  static const int rb_forced = getenv("NG_WGRAD_SLIDE_RB") ? atoi(getenv("NG_WGRAD_SLIDE_RB")) : 0;   // tuning runs
   for (int rb = 1; rb <= OH && rb <= 64; ++rb) {
+    if (rb_forced > 0 && rb != rb_forced) continue;
     const int TR = (int)ceil_div(OH, rb);
     if ((int)ceil_div(OH, TR) != rb) continue;
     int cp = (TR + 2) * q.xpitch;
     cp += ((4 - cp % 32) + 32) % 32;   // channel pitch == 4 (mod 32) words: 8 channels' float4 reads hit 32 distinct banks
-    const size_t tile = (size_t)K * TR * q.OWP + (size_t)C * cp;
+    const size_t tile = (size_t)TR * q.CS * q.SP + (size_t)C * cp;
     if (2 * tile * sizeof(float) > 200u * 1024u) continue;
     const long long tiles = (long long)N * rb;
     const long long grid = tiles < sms ? tiles : sms;
-    const double cost = (double)ceil_div(tiles, grid) * (TR + 2);
+    const double cost = (double)ceil_div(tiles, grid) * (TR + 1.0);
     if (best_rb == 0 || cost < best_cost) { best_rb = rb; best_tr = TR; best_cp = cp; best_cost = cost; }
   }
   if (best_rb == 0) return -1;
@@ -1497,17 +1548,18 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
   q.tiles = N * best_rb;
   q.xrows = best_tr + 2;
   q.cpitch = best_cp;
-  q.tile_floats = K * q.TR * q.OWP + C * q.cpitch;
+  q.tile_floats = q.TR * q.CS * q.SP + C * q.cpitch;
   size_t smem = 2 * sizeof(float) * (size_t)q.tile_floats;
   const size_t fold = sizeof(float) * (size_t)(q.CSN - 1) * base * KT * 9;
   if (fold > smem) smem = fold;
   if (smem > 220u * 1024u) return -1;
-  // 8-byte copies when every row start and every zero-fill boundary is even
-  const bool vec2 = OW % 2 == 0 && W % 2 == 0 && pad_l % 2 == 0 && (((uintptr_t)x | (uintptr_t)dy) & 7) == 0;
-  q.f_dcols = make_fastdiv(q.OWP / (vec2 ? 2 : 1));
-  q.f_xcols = make_fastdiv(q.xpitch / (vec2 ? 2 : 1));
-  q.f_tr = make_fastdiv(q.TR);
-  q.f_xrows = make_fastdiv(q.xrows);
+  // widest copies for which every row start and every zero-fill boundary is aligned: dy rows 8 bytes (even OW), x rows
+  // 16 bytes (W % 4 == 0, no left padding) or 8
+  const int vd = (OW % 2 == 0 && ((uintptr_t)dy & 7) == 0) ? 2 : 1;
+  const int vx = (W % 4 == 0 && pad_l % 4 == 0 && ((uintptr_t)x & 15) == 0) ? 4
+                 : (W % 2 == 0 && pad_l % 2 == 0 && ((uintptr_t)x & 7) == 0) ? 2 : 1;
+  for (q.d_lshift = 0; q.d_lshift < 5 && (1 << q.d_lshift) < q.OWP / vd; ++q.d_lshift) {}
+  for (q.x_lshift = 0; q.x_lshift < 5 && (1 << q.x_lshift) < q.xpitch / vx; ++q.x_lshift) {}
   q.f_rb = make_fastdiv(q.row_blocks);
   const int grid = q.tiles < sms ? q.tiles : sms;
   const long long out_elems = (long long)K * C * 9;
@@ -1518,9 +1570,11 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
   {
     static bool attr_done = false;
     if (!attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_slide_kernel<KT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_wgrad_slide_kernel<KT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      const int big = 220 * 1024;
+      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_slide_kernel<KT, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_slide_kernel<KT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_slide_kernel<KT, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_slide_kernel<KT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
       if (e != cudaSuccess) {
         pool_free(ws);
         return set_error("conv_wgrad_slide_kernel: %s", cudaGetErrorString(e));
@@ -1531,8 +1585,10 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
 #endif
   ProfScope prof_(NG_PROF_CONV_WGRAD, 2.0 * N * K * C * R * S * (double)OH * OW,
                   4.0 * ((double)N * C * H * W + (double)K * C * R * S + (double)N * K * OH * OW));
-  if (vec2) NG_LAUNCH((conv_wgrad_slide_kernel<KT, 2>), grid, threads, smem, q);
-  else NG_LAUNCH((conv_wgrad_slide_kernel<KT, 1>), grid, threads, smem, q);
+  if (vd == 2 && vx == 4) NG_LAUNCH((conv_wgrad_slide_kernel<KT, 2, 4>), grid, threads, smem, q);
+  else if (vd == 2 && vx == 2) NG_LAUNCH((conv_wgrad_slide_kernel<KT, 2, 2>), grid, threads, smem, q);
+  else if (vd == 2) NG_LAUNCH((conv_wgrad_slide_kernel<KT, 2, 1>), grid, threads, smem, q);
+  else NG_LAUNCH((conv_wgrad_slide_kernel<KT, 1, 1>), grid, threads, smem, q);
   NG_CHECK_LAUNCH();
   NG_LAUNCH(splitk_reduce_wide_kernel, (int)ceil_div(out_elems, 64), 512, 0, dw, (const float*)ws, grid, out_elems);
   NG_CHECK_LAUNCH();
