@@ -1288,6 +1288,7 @@ struct WgradSlideP {
   int N, C, H, W, K, OH, OW, OWP, pad_t, pad_l;
   int TR, row_blocks, tiles, KG, CS, CSN, SP, xrows, xpitch, cpitch, tile_floats;
   int d_lshift, x_lshift;   // log2 of the lanes that span a dy / x tile row in the copy
+  int d_iters, x_iters;     // row iterations of a warp per channel
   FastDiv f_rb;
 };
 
@@ -1354,7 +1355,9 @@ __device__ __forceinline__ void wgrad_slide_issue(const WgradSlideP& p, float* b
       for (int kk = warp; kk < p.K; kk += nwarps) {
         int off = kk * dplane + (oh0 + lsub) * p.OW + ow;
         smem_addr_t dst = smem_addr(buf + (kk / KT) * (KT * 4 + 4) + ((kk % KT) << 2) + lsub * rstep + (ow >> 2) * p.SP + (ow & 3));
-        for (int tr = lsub; tr < p.TR; tr += rpi, off += rpi * p.OW, dst += NG_SMEM_STEP(rpi * rstep)) {
+        // (trip counts come from the host: a loop with a run-time stride makes the compiler divide for the count)
+        for (int i = 0, tr = lsub; i < p.d_iters; ++i, tr += rpi, off += rpi * p.OW, dst += NG_SMEM_STEP(rpi * rstep)) {
+          if (tr >= p.TR) break;      // (only the last iteration of the upper lane group)
           const bool ok = cok && tr < drows;
           cp_async_zfill<VD>(dst, img + (ok ? off : 0), ok);
         }
@@ -1375,7 +1378,8 @@ __device__ __forceinline__ void wgrad_slide_issue(const WgradSlideP& p, float* b
       for (int c = warp; c < p.C; c += nwarps) {
         int off = c * xplane + (oh0 - p.pad_t + lsub) * p.W + j - p.pad_l;
         smem_addr_t dst = smem_addr(xs + c * p.cpitch + lsub * p.xpitch + j);
-        for (int rr = lsub; rr < p.xrows; rr += rpi, off += rpi * p.W, dst += NG_SMEM_STEP(rpi * p.xpitch)) {
+        for (int i = 0, rr = lsub; i < p.x_iters; ++i, rr += rpi, off += rpi * p.W, dst += NG_SMEM_STEP(rpi * p.xpitch)) {
+          if (rr >= p.xrows) break;   // (only the last iteration of the upper lane group)
           const bool ok = cok && rr >= rr_lo && rr < rr_hi;
           cp_async_zfill<VX>(dst, img + (ok ? off : 0), ok);
         }
@@ -1419,12 +1423,20 @@ __global__ void __launch_bounds__(512, 1) conv_wgrad_slide_kernel(const __grid_c
     for (int cs = ps < p.CSN ? ps : p.CS; cs < p.CS; cs += p.CSN) {
       const float* xr = xs + cs * 4;
       const float* dr = dys + cs * p.SP + kg * (KT * 4 + 4);
-      float4 xa[3];
-      float2 xb[3];
+      // rows tr .. tr + 2 of the window and dy row tr are in registers when a step starts; the step first issues the
+      // loads of the next one (window row tr + 3 into the fourth slot, dy row tr + 1 into the other d buffer: past the
+      // tile's last row these read the slack behind it and are never used), then runs its 144 FFMA
+      float4 xa[4];
+      float2 xb[4];
+      float4 d[2][KT];
 #define NG_SLIDE_LOADX(slot, row)                                               \
   do {                                                                          \
     xa[slot] = *reinterpret_cast<const float4*>(xr + (row) * p.xpitch);         \
     xb[slot] = *reinterpret_cast<const float2*>(xr + (row) * p.xpitch + 4);     \
+  } while (0)
+#define NG_SLIDE_LOADD(db, row)                                                                                        \
+  do {                                                                                                                  \
+    _Pragma("unroll") for (int kk = 0; kk < KT; ++kk) d[db][kk] = *reinterpret_cast<const float4*>(dr + (row) * dstep + kk * 4); \
   } while (0)
 #define NG_SLIDE_FMA(a3, d, A, B)                                                                         \
   do {                                                                                                    \
@@ -1432,30 +1444,34 @@ __global__ void __launch_bounds__(512, 1) conv_wgrad_slide_kernel(const __grid_c
     a3[1] = fmaf(d.x, A.y, fmaf(d.y, A.z, fmaf(d.z, A.w, fmaf(d.w, B.x, a3[1]))));                        \
     a3[2] = fmaf(d.x, A.z, fmaf(d.y, A.w, fmaf(d.z, B.x, fmaf(d.w, B.y, a3[2]))));                        \
   } while (0)
-#define NG_SLIDE_STEP(i0, i1, i2)                                                                         \
+#define NG_SLIDE_STEP(i0, i1, i2, i3, db)                                                                 \
   do {                                                                                                    \
-    NG_SLIDE_LOADX(i2, tr + 2);                                                                           \
-    float4 d[KT];                                                                                         \
-    _Pragma("unroll") for (int kk = 0; kk < KT; ++kk) d[kk] = *reinterpret_cast<const float4*>(dr + tr * dstep + kk * 4); \
+    NG_SLIDE_LOADX(i3, tr + 3);                                                                           \
+    NG_SLIDE_LOADD((db) ^ 1, tr + 1);                                                                     \
     _Pragma("unroll") for (int kk = 0; kk < KT; ++kk) {                                                   \
-      NG_SLIDE_FMA(acc[kk][0], d[kk], xa[i0], xb[i0]);                                                    \
-      NG_SLIDE_FMA(acc[kk][1], d[kk], xa[i1], xb[i1]);                                                    \
-      NG_SLIDE_FMA(acc[kk][2], d[kk], xa[i2], xb[i2]);                                                    \
+      NG_SLIDE_FMA(acc[kk][0], d[db][kk], xa[i0], xb[i0]);                                                \
+      NG_SLIDE_FMA(acc[kk][1], d[db][kk], xa[i1], xb[i1]);                                                \
+      NG_SLIDE_FMA(acc[kk][2], d[db][kk], xa[i2], xb[i2]);                                                \
     }                                                                                                     \
   } while (0)
       NG_SLIDE_LOADX(0, 0);
       NG_SLIDE_LOADX(1, 1);
+      NG_SLIDE_LOADX(2, 2);
+      NG_SLIDE_LOADD(0, 0);
       int tr = 0;
       while (true) {
-        NG_SLIDE_STEP(0, 1, 2);
+        NG_SLIDE_STEP(0, 1, 2, 3, 0);
         if (++tr >= rows) break;
-        NG_SLIDE_STEP(1, 2, 0);
+        NG_SLIDE_STEP(1, 2, 3, 0, 1);
         if (++tr >= rows) break;
-        NG_SLIDE_STEP(2, 0, 1);
+        NG_SLIDE_STEP(2, 3, 0, 1, 0);
+        if (++tr >= rows) break;
+        NG_SLIDE_STEP(3, 0, 1, 2, 1);
         if (++tr >= rows) break;
       }
 #undef NG_SLIDE_STEP
 #undef NG_SLIDE_FMA
+#undef NG_SLIDE_LOADD
 #undef NG_SLIDE_LOADX
     }
     __syncthreads();   // the buffer is refilled by the next iteration's prefetch
@@ -1549,7 +1565,8 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
   q.xrows = best_tr + 2;
   q.cpitch = best_cp;
   q.tile_floats = q.TR * q.CS * q.SP + C * q.cpitch;
-  size_t smem = 2 * sizeof(float) * (size_t)q.tile_floats;
+  // + slack for the window row prefetched past the last channel's rows of the second buffer
+  size_t smem = sizeof(float) * (2 * (size_t)q.tile_floats + q.xpitch + 8);
   const size_t fold = sizeof(float) * (size_t)(q.CSN - 1) * base * KT * 9;
   if (fold > smem) smem = fold;
   if (smem > 220u * 1024u) return -1;
@@ -1561,6 +1578,8 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
   for (q.d_lshift = 0; q.d_lshift < 5 && (1 << q.d_lshift) < q.OWP / vd; ++q.d_lshift) {}
   for (q.x_lshift = 0; q.x_lshift < 5 && (1 << q.x_lshift) < q.xpitch / vx; ++q.x_lshift) {}
   q.f_rb = make_fastdiv(q.row_blocks);
+  q.d_iters = (int)ceil_div(q.TR, 32 >> q.d_lshift);
+  q.x_iters = (int)ceil_div(q.xrows, 32 >> q.x_lshift);
   const int grid = q.tiles < sms ? q.tiles : sms;
   const long long out_elems = (long long)K * C * 9;
   float* ws = nullptr;
