@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) conv_fprop_smallc_kernel(const __grid_con
 // =====================================================================================
 template <int JT, int S, bool FLIP>
 __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant__ ConvGatherP p, int n_img, int OH, int OW,
-                                                          int strips_per_row, long long total_strips) {
+                                                          int strips_per_row, long long total_strips, int vec_ok) {
   // square S x S filters; blockIdx.y = tile of JT output channels (a grid dimension rather than a loop: the strips
   // alone leave a 256 x 30 x 30 output at 13 warps per SM)
   NG_DYN_SMEM(float, wsm);   // [KC][S*S][JT]
@@ -337,6 +337,10 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
     bool colok[S + 3];
 #pragma unroll
     for (int i = 0; i < S + 3; ++i) colok[i] = (ix0 + i >= 0) && (ix0 + i < p.a_w);
+    // widest aligned loads of a window row: every strip starts at 4 * sx + const, so the mode is uniform
+    const int ix_const = p.x_add + (FLIP ? -(S - 1) : 0);
+    const int vmode = !vec_ok ? 0 : ((ix_const & 3) == 0 && (p.a_w & 3) == 0 && vec_ok == 2) ? 1
+                      : ((ix_const & 1) == 0 && (p.a_w & 1) == 0) ? 2 : 0;
     for (int kc = 0; kc < p.KC; ++kc) {
       const float* plane = img + (long long)kc * p.a_chan_stride;
       // the S rows of this channel's window: all loads issued before the first use
@@ -346,8 +350,31 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
         const int iy = iy0 + rr;
         const bool rowok = iy >= 0 && iy < p.a_h;
         const float* rowp = plane + (long long)iy * p.a_w + ix0;
+        if (vmode == 1) {
+          // ix0 % 4 == 0 and a_w % 4 == 0: 128-bit pieces (+ a 64-bit tail), each wholly inside or outside the row
 #pragma unroll
-        for (int i = 0; i < S + 3; ++i) in[rr][i] = (rowok && colok[i]) ? rowp[i] : 0.f;
+          for (int i = 0; i + 4 <= S + 3; i += 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok && colok[i]) v = *reinterpret_cast<const float4*>(rowp + i);
+            in[rr][i] = v.x; in[rr][i + 1] = v.y; in[rr][i + 2] = v.z; in[rr][i + 3] = v.w;
+          }
+          if ((S + 3) % 4 != 0) {
+            float2 v = make_float2(0.f, 0.f);
+            if (rowok && colok[S + 1]) v = *reinterpret_cast<const float2*>(rowp + S + 1);
+            in[rr][S + 1] = v.x; in[rr][S + 2] = v.y;
+          }
+        } else if (vmode == 2) {
+          // ix0 and a_w even: 64-bit pieces
+#pragma unroll
+          for (int i = 0; i < S + 3; i += 2) {
+            float2 v = make_float2(0.f, 0.f);
+            if (rowok && colok[i]) v = *reinterpret_cast<const float2*>(rowp + i);
+            in[rr][i] = v.x; in[rr][i + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < S + 3; ++i) in[rr][i] = (rowok && colok[i]) ? rowp[i] : 0.f;
+        }
       }
 #pragma unroll
       for (int r = 0; r < S; ++r) {
@@ -413,10 +440,13 @@ static int launch_conv_direct(const ConvGatherP& p, int R, int S, bool flip, int
   long long g = ceil_div(total, 128);
   if (g > (long long)sms * 16) g = (long long)sms * 16;
   const dim3 grid((unsigned)g, (unsigned)ceil_div(p.J, JT));
+  // vector loads of the window rows need the planes' starts aligned: base pointer and channel / image strides
+  const int vec_ok = (((uintptr_t)p.a & 15) == 0 && p.a_chan_stride % 4 == 0 && p.a_img_stride % 4 == 0) ? 2
+                     : (((uintptr_t)p.a & 7) == 0 && p.a_chan_stride % 2 == 0 && p.a_img_stride % 2 == 0) ? 1 : 0;
 #define NG_DIRECT(JT_, S_)                                                                                        \
   do {                                                                                                            \
-    if (flip) NG_LAUNCH((conv_direct_kernel<JT_, S_, true>), grid, 128, smem, p, n_img, OH, OW, strips_per_row, total); \
-    else NG_LAUNCH((conv_direct_kernel<JT_, S_, false>), grid, 128, smem, p, n_img, OH, OW, strips_per_row, total);     \
+    if (flip) NG_LAUNCH((conv_direct_kernel<JT_, S_, true>), grid, 128, smem, p, n_img, OH, OW, strips_per_row, total, vec_ok); \
+    else NG_LAUNCH((conv_direct_kernel<JT_, S_, false>), grid, 128, smem, p, n_img, OH, OW, strips_per_row, total, vec_ok);     \
   } while (0)
 #define NG_DIRECT_S(JT_)                                                                                          \
   do {                                                                                                            \
