@@ -1,5 +1,5 @@
 """Direct convolution kernels for narrow layers (both channel counts <= 32, stride 1: BASELINE configs[1] at
-C = K = 16 / 32): conv_direct_kernel (fprop, dgrad) and conv_wgrad_direct_kernel against a float64 evaluation of
+C = K = 16 / 32): conv_direct_kernel (fprop, dgrad), conv_wgrad_slide_kernel and conv_wgrad_direct_kernel against a float64 evaluation of
 ops_cpu.py:345-400's definition, over ragged output widths (strips of 4 with a tail), 1x1 / 3x3 / 5x5 filters,
 padding, output-channel tiles of 8 / 16 / 32.  The same kernels run under the host emulation in the CPU suite
 (fixture-sized cases of tests/test_device_parity.py)."""
