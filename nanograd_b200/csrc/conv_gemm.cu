@@ -1543,7 +1543,7 @@ __global__ void __launch_bounds__(512, 1) conv_wgrad_slide_kernel(const __grid_c
 static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N, int C, int H, int W, int K, int R, int S,
                               int stride, int pad_t, int pad_l, int OH, int OW) {
   constexpr int KT = 4;
-  if (R != 3 || S != 3 || stride != 1 || C > 32 || K > 32 || C < 8 || K % KT != 0 || C * K > 512) return -1;
+  if (R != 3 || S != 3 || stride != 1 || C > 32 || K > 32 || C < 8 || K % KT != 0 || C * K > 1024) return -1;
 #ifdef NG_EMU
   const long long min_pixels = 1024;
 #else

@@ -32,7 +32,7 @@ def _truth(x, w, dy, pad):
 # fixture-sized shapes for the host emulation (>= 1024 output pixels): even / odd widths (8- and 4-byte cp.async tiles
 # of the sliding-window wgrad), padding 0 / 1, K % 4 != 0 (the register-tile wgrad), ragged last row block
 EMU_SHAPES = [(5, 16, 18, 18, 16, 3, 3, 0), (6, 8, 16, 15, 8, 3, 3, 1), (5, 12, 17, 18, 20, 3, 3, 1),
-              (6, 16, 16, 16, 10, 3, 3, 0), (3, 32, 22, 20, 16, 3, 3, 0)]
+              (6, 16, 16, 16, 10, 3, 3, 0), (3, 32, 22, 20, 16, 3, 3, 0), (3, 32, 20, 20, 32, 3, 3, 1)]
 
 
 def _check(shape):
