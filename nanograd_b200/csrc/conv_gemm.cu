@@ -1565,11 +1565,18 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
   if ((q.SP / 4) % 2 == 0) q.SP += 4;
   const int base = q.KG * C;
   if (base > 512 || base < 32) return -1;
-  q.CSN = 512 / base;
+  // CTA size: 512 threads, one CTA per SM, or (NG_WGRAD_SLIDE_THREADS=256) two 256-thread CTAs whose barriers and tile
+  // copies interleave
+  static const int tmax_env = getenv("NG_WGRAD_SLIDE_THREADS") ? atoi(getenv("NG_WGRAD_SLIDE_THREADS")) : 512;
+  const int tmax = tmax_env == 256 ? 256 : 512;
+  q.CSN = tmax / base;
+  if (q.CSN < 1) q.CSN = 1;
   if (q.CSN > q.CS) q.CSN = q.CS;
   const int threads = (base * q.CSN + 31) & ~31;
+  const int ctas_per_sm = threads <= 256 ? 2 : 1;
+  const size_t tile_budget = ctas_per_sm == 2 ? 108u * 1024u : 200u * 1024u;
   q.xpitch = q.OWP + 4;
-  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  const int sms = (g_sm_count > 0 ? g_sm_count : 148) * ctas_per_sm;
   // rows per tile: two tiles must fit 200 KB; among the row-block counts that do, the one with the fewest
   // (rows + window start-up) x rounds of the persistent grid
   int best_rb = 0, best_tr = 0, best_cp = 0;
@@ -1582,7 +1589,7 @@ static int launch_wgrad_slide(float* dw, const float* dy, const float* x, int N,
     int cp = (TR + 2) * q.xpitch;
     cp += ((4 - cp % 32) + 32) % 32;   // channel pitch == 4 (mod 32) words: 8 channels' float4 reads hit 32 distinct banks
     const size_t tile = (size_t)TR * q.CS * q.SP + (size_t)C * cp;
-    if (2 * tile * sizeof(float) > 200u * 1024u) continue;
+    if (2 * tile * sizeof(float) > tile_budget) continue;
     const long long tiles = (long long)N * rb;
     const long long grid = tiles < sms ? tiles : sms;
     const double cost = (double)ceil_div(tiles, grid) * (TR + 1.0);
