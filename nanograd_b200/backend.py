@@ -18,6 +18,7 @@ _lib = None
 _lib_path = None
 
 u64, i64, i32, f32 = c_uint64, c_int64, c_int, c_float
+_byref = ctypes.byref
 p_i64, p_u64, p_i32 = POINTER(c_int64), POINTER(c_uint64), POINTER(c_int32)
 
 # name -> argtypes ; every function returns int status except ng_last_error
@@ -238,14 +239,15 @@ def is_available():
 
 # ------------------------------------------------------------------ thin helpers -----------
 def malloc(nbytes):
-    init()
+    if not _initialised:
+        init()
     out = u64(0)
-    _lib.ng_malloc(ctypes.byref(out), max(int(nbytes), 1))
+    _lib.ng_malloc(_byref(out), nbytes if nbytes > 0 else 1)
     return out.value
 
 
 def free(ptr):
-    if _lib is not None and ptr:
+    if ptr and _lib is not None:
         _lib.ng_free(ptr)
 
 

@@ -8,6 +8,7 @@ allocation belongs to the base buffer and returns to the library's stream-ordere
 the last alias is garbage-collected.
 """
 import ctypes
+import math
 
 import numpy as np
 
@@ -15,34 +16,33 @@ from nanograd_b200 import backend
 
 
 def _numel(shape):
-    n = 1
-    for s in shape:
-        n *= int(s)
-    return n
+    return math.prod(map(int, shape))
 
 
 class DeviceBuffer:
     def __init__(self, shape, hostbuf=None):
-        if isinstance(shape, (int, np.integer)):
-            shape = (int(shape),)
-        self.shape = tuple(int(s) for s in shape)
+        # a training step builds ~110 of these: the common case (a tuple of Python ints, no host data) stays short
+        if type(shape) is not tuple or not all(type(s) is int for s in shape):
+            shape = (int(shape),) if isinstance(shape, (int, np.integer)) else tuple(map(int, shape))
+        self.shape = shape
         self.dtype = np.float32
-        self.size = _numel(self.shape)
+        self.size = size = math.prod(shape)
         self._base = None
         self._ptr = 0
-        if isinstance(hostbuf, DeviceBuffer):
-            if hostbuf.size != self.size:
+        if hostbuf is None:
+            self._ptr = backend.malloc(size * 4)
+        elif isinstance(hostbuf, DeviceBuffer):
+            if hostbuf.size != size:
                 raise Exception(f"cannot view a buffer of {hostbuf.size} elements as shape {self.shape}")
             self._base = hostbuf._base if hostbuf._base is not None else hostbuf
             self._ptr = hostbuf.ptr
         else:
-            self._ptr = backend.malloc(self.size * 4)
-            if hostbuf is not None:
-                host = np.ascontiguousarray(hostbuf, dtype=np.float32)
-                if host.size != self.size:
-                    raise Exception(f"host array of {host.size} elements does not fill shape {self.shape}")
-                if self.size:
-                    backend.lib().ng_h2d(self._ptr, host.ctypes.data_as(ctypes.c_void_p), self.size * 4)
+            self._ptr = backend.malloc(size * 4)
+            host = np.ascontiguousarray(hostbuf, dtype=np.float32)
+            if host.size != size:
+                raise Exception(f"host array of {host.size} elements does not fill shape {self.shape}")
+            if size:
+                backend.lib().ng_h2d(self._ptr, host.ctypes.data_as(ctypes.c_void_p), size * 4)
 
     @property
     def ptr(self):
@@ -61,9 +61,9 @@ class DeviceBuffer:
         """Zero-copy alias of ``numel(shape)`` elements of ``base`` starting at ``offset_elems`` (slots of
         the data-parallel gradient arena)."""
         out = cls.__new__(cls)
-        out.shape = tuple(int(s) for s in shape)
+        out.shape = tuple(map(int, shape))
         out.dtype = np.float32
-        out.size = _numel(out.shape)
+        out.size = math.prod(out.shape)
         if offset_elems < 0 or offset_elems + out.size > base.size:
             raise Exception(f"alias of {out.size} elements at {offset_elems} does not fit a buffer of {base.size}")
         out._base = base._base if base._base is not None else base
@@ -122,9 +122,9 @@ class LazyBuffer(DeviceBuffer):
     of a plain ``DeviceBuffer``."""
 
     def __init__(self, shape, materialize, kind=None, source=None):
-        self.shape = tuple(int(s) for s in shape)
+        self.shape = tuple(map(int, shape))
         self.dtype = np.float32
-        self.size = _numel(self.shape)
+        self.size = math.prod(self.shape)
         self._base = None
         self._ptr = 0
         self._materialize = materialize
