@@ -75,3 +75,39 @@ def test_readme_cnn_step_dispatch():
     assert c["ng_maxpool2d_fwd"] == 2 and c["ng_maxpool2d_bwd"] == 2 and c["ng_multi_sgd"] == 1
     assert r["library_calls_per_step"] <= 30
     assert r["live_growth_one_step"] == 0 and r["live_growth_timed_steps"] == 0
+
+
+@pytest.mark.parametrize("world,sync_bn", [(2, False), (8, False), (8, True)])
+def test_data_parallel_step_dispatch(world, sync_bn):
+    """Rank 0 of a data-parallel group over the null library (its collectives are no-ops): gradients go straight
+    into the flat arena (no pack copy), the arena is all-reduced in chunks while the backward runs and the
+    optimizer waits for the tail once; SyncBN keeps the one-call BatchNorm kernels."""
+    r = _run("--model", "vgg", "--world", str(world), *(["--sync-bn"] if sync_bn else []))
+    c = r["calls"]
+    assert r["world"] == world
+    assert c["ng_nccl_allreduce_begin"] >= 2, "the gradient arena must be reduced in several chunks during backward"
+    assert c["ng_nccl_allreduce_end"] == 1 and c["ng_multi_adam"] == 1
+    assert "ng_multi_pack" not in c and "ng_multi_unpack" not in c and "ng_nccl_allreduce_sum" not in c
+    assert c["ng_conv2d_fprop"] == 6 and c["ng_conv2d_wgrad"] == 6 and c["ng_conv2d_dgrad"] == 5
+    if sync_bn:
+        assert c["ng_bn2d_act_fwd_train"] == 6 and c["ng_bn2d_act_bwd"] == 6 and "ng_bn2d_act_fwd_stats" not in c
+    else:
+        assert c["ng_bn2d_act_fwd_stats"] == 6 and c["ng_conv2d_stage_f16_bn"] == 3
+    assert r["live_growth_one_step"] == 0 and r["live_growth_timed_steps"] == 0
+
+
+def test_reference_classes_reach_the_same_fused_path():
+    """The unmodified reference's Tensor / Module / Optimizer, bound with nanograd_b200.integrate.install(), issue the
+    same library calls per step as this package's host mirror (the backward seed apart: the reference uploads
+    np.ones, tensor.py:226) — the drop-in reaches the fused tensor-core path without edits to user code."""
+    import helpers
+    if helpers.load_reference() is None:
+        pytest.skip("the reference is not present (oracle/_ref is installed by __graft_entry__.build())")
+    ours = _run("--model", "vgg")["calls"]
+    theirs = _run("--model", "vgg", "--reference")
+    assert theirs["reference_classes"] is True
+    c = dict(theirs["calls"])
+    assert c.pop("ng_h2d") == 1 and "ng_fill" not in c
+    ours.pop("ng_fill")
+    assert c == ours
+    assert theirs["live_growth_one_step"] == 0 and theirs["live_growth_timed_steps"] == 0

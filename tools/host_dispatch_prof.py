@@ -110,6 +110,11 @@ def main():
     ap.add_argument("--math", default="fp32")
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--top", type=int, default=30)
+    ap.add_argument("--world", type=int, default=1, help="> 1: this process plays rank 0 of a data-parallel group whose "
+                    "collectives are the null library's no-ops (host logic of the gradient arena / chunked allreduce)")
+    ap.add_argument("--sync-bn", action="store_true")
+    ap.add_argument("--reference", action="store_true", help="drive the step through the unmodified reference's own "
+                    "Tensor / Module / Optimizer (oracle/_ref or /root/reference) bound with nanograd_b200.integrate")
     ap.add_argument("--json", action="store_true", help="one JSON line: calls per step by entry point, allocation balance")
     args = ap.parse_args()
 
@@ -118,10 +123,25 @@ def main():
     handle = B.load_library(build_null_library())
     B.init(0)
     B.set_math_mode(args.math)
-    import nanograd_b200.nn.module as nn
-    import nanograd_b200.optim.optimizer as optim
-    from nanograd_b200.device import Device
-    from nanograd_b200.tensor import Tensor
+    if args.world > 1:
+        import tempfile
+        from nanograd_b200 import dist
+        os.environ.update(WORLD_SIZE=str(args.world), RANK="0", LOCAL_RANK="0", MASTER_PORT="0",
+                          NANOGRAD_B200_RDZV_DIR=tempfile.mkdtemp(prefix="ng_null_rdzv_"))
+        dist.init(use_device=True, sync_bn=args.sync_bn)
+    if args.reference:
+        import helpers
+        ref = helpers.load_reference()
+        if ref is None:
+            raise SystemExit("the reference is not present (run tools/make_oracle_ref.sh where /root/reference exists)")
+        import nanograd_b200.integrate as integrate
+        integrate.install(ref["package"], library=B.library_path())
+        nn, optim, Device, Tensor = ref["module"], ref["optim"], ref["device"].Device, ref["tensor"].Tensor
+    else:
+        import nanograd_b200.nn.module as nn
+        import nanograd_b200.optim.optimizer as optim
+        from nanograd_b200.device import Device
+        from nanograd_b200.tensor import Tensor
 
     np.random.seed(0)
     if args.model == "vgg":
@@ -161,7 +181,7 @@ def main():
     # steady state: one step's calls by entry point, and the allocations a step leaves behind (must be none)
     live0, c0 = B.mem_stats(), call_counts(handle)
     loss = step()
-    float(loss.numpy()[0])
+    float(loss.data.numpy()[0])
     del loss
     live1, c1 = B.mem_stats(), call_counts(handle)
     per_step = {n: c1[n] - c0[n] for n in c1 if c1[n] != c0[n]}
@@ -176,7 +196,7 @@ def main():
     live2 = B.mem_stats()
     if args.json:
         import json
-        print(json.dumps({"model": args.model, "batch": batch, "math": args.math, "host_ms_per_step": round(best * 1e3, 4),
+        print(json.dumps({"model": args.model, "batch": batch, "math": args.math, "world": args.world, "reference_classes": bool(args.reference), "host_ms_per_step": round(best * 1e3, 4),
                           "library_calls_per_step": calls, "calls": per_step,
                           "allocs_per_step": live1["device_allocs"] - live0["device_allocs"],
                           "live_growth_one_step": live1["live_bytes"] - live0["live_bytes"],
