@@ -104,7 +104,7 @@ def call_counts(handle):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--model", default="vgg", choices=["vgg", "mnist"])
+    ap.add_argument("--model", default="vgg", choices=["vgg", "mnist", "attention"])
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--batch", type=int, default=0, help="0 = the BASELINE batch (512 / 128)")
     ap.add_argument("--math", default="fp32")
@@ -151,6 +151,28 @@ def main():
         model.gpu()
         opt = optim.Adam(model.parameters(), lr=1e-3)
         X = np.zeros((batch, 3, 32, 32), np.float32)
+    elif args.model == "attention":
+        # BASELINE configs[3] as bench.attention_extra composes it: seq 512, d 256, MSE loss, AdamW
+        seq, d = args.batch or 512, 256
+
+        class Attn(nn.Module):
+            def __init__(self):
+                super().__init__()
+                mk = lambda: Tensor((np.random.randn(d, d) / np.sqrt(d)).astype(np.float32), requires_grad=True,
+                                    is_parameter=True)
+                self.wq, self.wk, self.wv, self.wo = mk(), mk(), mk(), mk()
+
+            def forward(self, x):
+                q, k, v = x @ self.wq, x @ self.wk, x @ self.wv
+                s = (q @ k.T) * (1.0 / np.sqrt(d))
+                p = s.log_softmax().exp()
+                return (p @ v) @ self.wo
+
+        batch = seq
+        model = Attn()
+        model.gpu()
+        opt = optim.AdamW(model.parameters(), lr=1e-3)
+        X = np.zeros((seq, d), np.float32)
     else:
         import helpers
         batch = args.batch or 128
@@ -158,8 +180,8 @@ def main():
         model.gpu()
         opt = optim.SGD(model.parameters(), lr=0.01, momentum=0)
         X = np.zeros((batch, 784), np.float32)
-    Y = np.zeros(batch, np.float32)
-    crit = nn.NLLLoss()
+    Y = np.zeros((batch, 256) if args.model == "attention" else batch, np.float32)
+    crit = nn.MSELoss() if args.model == "attention" else nn.NLLLoss()
     xb, yb = Tensor(X, device=Device.GPU), Tensor(Y, device=Device.GPU)
 
     def step():
