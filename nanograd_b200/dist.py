@@ -46,6 +46,19 @@ def shard_bounds(global_batch, world=None, rnk=None):
     return start, start + base + (1 if rnk < rem else 0)
 
 
+def shard_loss_weight(global_batch, world=None, rnk=None):
+    """Factor a rank multiplies its shard's *mean* loss by before ``backward()`` so that the data-parallel
+    step equals the single-process step on the global batch when the shards are unequal.
+
+    The losses of this API are means over the rows they see (NLLLoss: module.py:684-686, MSELoss: :712) and the
+    optimizer averages the summed gradients with 1/world; with ``n_r`` rows on rank r the global-batch gradient is
+    ``sum_r (n_r / N) g_r``, i.e. each rank's loss carries ``n_r * world / N``.  Equal shards (every BASELINE
+    configuration: 4096 rows over 1/2/4/8 ranks) give exactly 1.0 and need no change to the training loop."""
+    world = world_size() if world is None else world
+    lo, hi = shard_bounds(global_batch, world, rnk)
+    return (hi - lo) * float(world) / float(global_batch)
+
+
 def _rendezvous_path():
     """File through which rank 0 hands the NCCL ids to the other ranks of this launch.  The
     parent process (the torchrun agent, or whatever spawned the ranks) and MASTER_PORT identify

@@ -38,6 +38,24 @@ def test_shard_bounds_partition_the_batch():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_loss_weight_restores_the_global_batch_gradient():
+    """Unequal shards: mean-loss gradients averaged with 1/world are not the global-batch gradient unless each
+    rank's loss carries n_r * world / N (1.0 for the equal shards of every BASELINE configuration)."""
+    import numpy as np
+    from nanograd_b200 import dist
+    assert dist.shard_loss_weight(4096, 8, 3) == 1.0 and dist.shard_loss_weight(512, 1, 0) == 1.0
+    rng = np.random.RandomState(0)
+    for batch, world in [(10, 4), (7, 2), (33, 8)]:
+        X, y, w = rng.randn(batch, 5), rng.randn(batch), rng.randn(5)
+        grad = lambda lo, hi: 2.0 * X[lo:hi].T @ (X[lo:hi] @ w - y[lo:hi]) / (hi - lo)   # d/dw mean((Xw - y)^2)
+        want = grad(0, batch)
+        spans = [dist.shard_bounds(batch, world, r) for r in range(world)]
+        plain = sum(grad(lo, hi) for lo, hi in spans) / world
+        weighted = sum(dist.shard_loss_weight(batch, world, r) * grad(lo, hi) for r, (lo, hi) in enumerate(spans)) / world
+        assert np.allclose(weighted, want, rtol=1e-12, atol=1e-12)
+        assert not np.allclose(plain, want, rtol=1e-6)
+
+
 def test_world2_gloo_control_plane_and_dp_gradient_math():
     res = _torchrun("cpu")
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
