@@ -144,7 +144,14 @@ def _reduce(op, x, axes, keepdims=False, out=None):
     full = [1 if mask[i] else x.shape[i] for i in range(nd)]
     if out is None:
         out = DeviceBuffer(kept if kept else (1,))
-    _lib().ng_reduce(op, out.ptr, x.ptr, nd, B.i64_array(x.shape), B.i32_array(mask))
+    if x.size == 0 and out.size:
+        # an empty reduced axis: NumPy's sum is 0, its max / min have no identity and raise (ops_cpu.py:100-146)
+        if op != B.R_SUM:
+            raise ValueError("zero-size array to reduction operation %s which has no identity"
+                             % ("maximum" if op == B.R_MAX else "minimum"))
+        _lib().ng_memset_zero(out.ptr, out.size * 4)
+    else:
+        _lib().ng_reduce(op, out.ptr, x.ptr, nd, B.i64_array(x.shape), B.i32_array(mask))
     if keepdims:
         return out.view(full)
     return out

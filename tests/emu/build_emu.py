@@ -29,7 +29,16 @@ def _deps():
 
 
 def build(force=False, verbose=False):
+    """Build (or reuse) the emulated library.  Safe under pytest-xdist: one process builds at a time (file lock),
+    objects and the library are written under temporary names and renamed into place."""
+    import fcntl
     os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build_locked(force, verbose)
+
+
+def _build_locked(force, verbose):
     srcs = _sources() + [os.path.join(HERE, "ng_emu.cpp")]
     newest = max(os.path.getmtime(p) for p in srcs + _deps())
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
@@ -43,15 +52,19 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(obj)
                 and os.path.getmtime(obj) >= max(os.path.getmtime(src), max(os.path.getmtime(d) for d in _deps()))):
             return obj
-        cmd = ["g++", "-x", "c++"] + flags + ["-c", src, "-o", obj]
+        tmp = obj + ".tmp%d" % os.getpid()
+        cmd = ["g++", "-x", "c++"] + flags + ["-c", src, "-o", tmp]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
+        os.replace(tmp, obj)
         return obj
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, srcs))
-    subprocess.run(["g++", "-shared", "-pthread", "-o", LIB] + objs, check=True)
+    tmp = LIB + ".tmp%d" % os.getpid()
+    subprocess.run(["g++", "-shared", "-pthread", "-o", tmp] + objs, check=True)
+    os.replace(tmp, LIB)
     return LIB
 
 

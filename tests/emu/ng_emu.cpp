@@ -68,6 +68,13 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     fprintf(stderr, "ng_emu: unsupported block shape (%u,%u,%u)\n", block.x, block.y, block.z);
     abort();
   }
+  // the limits a real launch has (a violation is cudaErrorInvalidConfiguration on the B200, silently fine on a host loop)
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535u || grid.z > 65535u || grid.x > 2147483647u ||
+      smem > 227u * 1024u) {
+    fprintf(stderr, "ng_emu: launch configuration a GPU would reject: grid (%u,%u,%u), %zu bytes of dynamic shared memory\n",
+            grid.x, grid.y, grid.z, smem);
+    abort();
+  }
   const int T = (int)block.x;
   Pool*& pool = pools()[T];
   if (!pool) pool = new Pool(T);
