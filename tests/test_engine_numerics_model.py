@@ -114,3 +114,29 @@ def test_wide_dynamic_range_keeps_absolute_accuracy():
     spike = a.copy()
     spike[0, 0] = np.float32(1e30)
     assert scaled_err(f16x3_matmul(spike, b), spike.astype(np.float64) @ b.astype(np.float64)) <= H.RTOL_FP32 / 20
+
+
+# ---- the 3xTF32 engine: shapes FP16x3 does not take, and GEMM ----------------------------------
+def tf32_trunc(x):
+    """What the tensor core reads from an FP32 word under kind::tf32: the 13 low mantissa bits are ignored."""
+    return (x.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tf32x3_matmul(a, b):
+    """hi = the word as the hardware truncates it, lo = v - trunc(v) (itself read truncated);
+    D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi with FP32 accumulation (csrc/umma_common.cuh)."""
+    a_hi, b_hi = tf32_trunc(a), tf32_trunc(b)
+    a_lo, b_lo = tf32_trunc(a - a_hi), tf32_trunc(b - b_hi)
+    return (a_lo @ b_hi + a_hi @ b_lo) + a_hi @ b_hi
+
+
+def test_tf32x3_model_meets_the_fp32_bar_and_plain_tf32_does_not():
+    rng = np.random.RandomState(4)
+    a = rng.randn(4096, 288).astype(np.float32)             # a 32 -> 64, 3x3 layer: K = 32 * 9
+    b = (rng.randn(288, 64) / np.sqrt(288)).astype(np.float32)
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    err3 = scaled_err(tf32x3_matmul(a, b), want)
+    err1 = scaled_err(tf32_trunc(a) @ tf32_trunc(b), want)
+    assert err3 <= 2e-6, err3                                # measured on the B200: <= 1e-5
+    assert err1 > H.RTOL_FP32, err1                          # truncated TF32 inputs alone: the rtol 1e-2 mode
+    assert err1 <= H.RTOL_TF32
