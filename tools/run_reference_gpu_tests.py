@@ -30,6 +30,10 @@ def main():
     ap.add_argument("--primitives-only", action="store_true",
                     help="bind the boundary only (integrate.install(fused=False)): every layer runs the reference's own "
                          "composition over the 21 registered primitives")
+    ap.add_argument("--mnist-synthetic", type=int, default=0, metavar="STEPS",
+                    help="also run the reference's tests/test_mnist.py flow (its models, its train() / evaluate() loops, "
+                         "the optimizer built before model.gpu()) on Device.GPU for STEPS steps per model, on a synthetic "
+                         "idx-gz data set written to a scratch directory (the MNIST files are not shipped)")
     ap.add_argument("modules", nargs="*", default=["tests.test_ops", "tests.test_step", "tests.test_module"])
     args = ap.parse_args()
     if not os.path.isdir(os.path.join(REFERENCE, "tests")):
@@ -60,7 +64,61 @@ def main():
                 suite.addTests(unittest.defaultTestLoader.loadTestsFromTestCase(obj))
     res = unittest.TextTestRunner(verbosity=0, stream=sys.stderr).run(suite)
     print("REFTESTS run=%d failures=%d errors=%d skipped=%d" % (res.testsRun, len(res.failures), len(res.errors), len(res.skipped)))
-    return 0 if res.wasSuccessful() and res.testsRun > 0 else 1
+    ok = res.wasSuccessful() and res.testsRun > 0
+    if args.mnist_synthetic > 0:
+        ok = mnist_flow(args.mnist_synthetic) and ok
+    return 0 if ok else 1
+
+
+def _write_synthetic_mnist(root, n_train=2048, n_test=512):
+    """Ten fixed random 28x28 prototypes plus noise, in the idx-gz layout tests/test_mnist.py:20-38 reads."""
+    import gzip
+    import numpy as np
+    rng = np.random.RandomState(7)
+    protos = rng.rand(10, 784) > 0.7
+    os.makedirs(os.path.join(root, "data"), exist_ok=True)
+    for split, n in (("train", n_train), ("t10k", n_test)):
+        y = rng.randint(0, 10, n).astype(np.uint8)
+        x = np.clip(protos[y] * 200.0 + rng.randn(n, 784) * 40.0, 0, 255).astype(np.uint8)
+        with open(os.path.join(root, "data", f"{split}-images-idx3-ubyte.gz"), "wb") as f:
+            f.write(gzip.compress(bytes(16) + x.tobytes()))
+        with open(os.path.join(root, "data", f"{split}-labels-idx1-ubyte.gz"), "wb") as f:
+            f.write(gzip.compress(bytes(8) + y.tobytes()))
+
+
+def mnist_flow(steps):
+    """tests/test_mnist.py:88-109 on Device.GPU (the reference keeps that class commented out, :112-115): for each of
+    its three models, `optim.Adam(model.parameters())` on the host model, `train(..., device=Device.GPU)` (which calls
+    model.gpu() after the optimizer exists and reads out / loss back every step), then `evaluate`.  The same seeded run
+    on Device.CPU (the reference's NumPy path) is the yardstick."""
+    import tempfile
+    import numpy as np
+    scratch = tempfile.mkdtemp(prefix="ng_ref_mnist_")
+    _write_synthetic_mnist(scratch)
+    cwd = os.getcwd()
+    os.chdir(scratch)                     # tests/test_mnist.py opens 'data/...' relative to the working directory
+    try:
+        tm = importlib.import_module("tests.test_mnist")
+    finally:
+        os.chdir(cwd)
+    from nanograd.device import Device
+    import nanograd.optim.optimizer as optim
+    ok = True
+    for model_cls in (tm.LinearModel, tm.CNNModel1d, tm.CNNModel2d):
+        acc = {}
+        for device in (Device.CPU, Device.GPU):
+            np.random.seed(0)
+            model = model_cls()
+            optimizer = optim.Adam(model.parameters(), lr=1e-3)
+            tm.train(model, tm.X_train, tm.Y_train, optimizer, steps=steps, batch_size=64, device=device)
+            acc[device.name] = float(tm.evaluate(model, tm.X_test, tm.Y_test, device=device))
+        # the yardstick is the reference's own NumPy run of the same seeded loop (a few dozen steps do not reach the
+        # > 0.91 of tests/test_mnist.py:105-109 on every model): same accuracy within 2 points, and well above chance
+        good = acc["GPU"] > 0.5 and abs(acc["GPU"] - acc["CPU"]) <= 0.02
+        ok = ok and good
+        print("REFMNIST %s steps=%d accuracy cpu=%.4f gpu=%.4f %s" % (model_cls.__name__, steps, acc["CPU"], acc["GPU"],
+                                                                       "ok" if good else "MISMATCH"))
+    return ok
 
 
 if __name__ == "__main__":
