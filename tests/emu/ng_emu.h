@@ -2,8 +2,9 @@
 //
 // Host emulation of the small slice of CUDA that nanograd_b200/csrc uses, so the kernel
 // *sources* can be compiled with g++ (-DNG_EMU) and executed in the GPU-less build container:
-// every CUDA thread of a block runs as a host thread, __syncthreads() is a real barrier and
-// warp shuffles exchange values between the 32 host threads of a warp.  It exists to catch
+// every CUDA thread of a block runs as its own execution context (a user-level fiber by default, a host thread with
+// NG_EMU_THREADS=1), __syncthreads() is a real barrier and warp shuffles exchange values between the 32 contexts of a
+// warp; launches are checked against a real GPU's limits (grid dimensions, dynamic shared memory).  It exists to catch
 // indexing / marshalling bugs before GPU time is spent; it is neither a fallback nor a product
 // path (the shipped library is built by nvcc for sm_100a and ng_init fails without a GPU).
 #pragma once

@@ -9,12 +9,7 @@ import pytest
 
 import helpers as H
 
-import os
-
 BIG = 70001   # > 65535 and odd
-# one emulated block per row / image makes three of the cases take 20-50 s each on the host emulation: they run with
-# NG_SLOW_TESTS=1 (last run green with the launch limits enforced: this file's commit), the rest always
-slow = pytest.mark.skipif(os.environ.get("NG_SLOW_TESTS", "0") != "1", reason="slow on the host emulation; set NG_SLOW_TESTS=1")
 
 
 @pytest.fixture(autouse=True)
@@ -28,7 +23,6 @@ def test_large_leading_dimension_elementwise_reduce_softmax():
     H.check_op([(BIG, 3)], lambda x: x.max(axis=1), loc=0.0)
 
 
-@slow
 def test_large_row_count_log_softmax():
     H.check_op([(BIG, 10)], lambda x: x.log_softmax(), loc=0.0)
 
@@ -44,12 +38,10 @@ def test_large_batch_pooling():
     H.check_op([(BIG, 1, 2, 2)], lambda x: x.avg_pool2d(), loc=0.0)
 
 
-@slow
 def test_large_batch_conv():
     H.check_op([(BIG, 1, 1, 1), (2, 1, 1, 1)], lambda x, w: x.conv2d(w, stride=1), loc=0.0)
 
 
-@slow
 def test_large_batch_batchnorm_and_loss():
     from nanograd_b200.device import Device
     fw_g, fw_c = H.device_framework(Device.GPU), H.device_framework(Device.CPU)
