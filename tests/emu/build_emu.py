@@ -28,23 +28,36 @@ def _deps():
     return hdrs
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, tsan=None):
     """Build (or reuse) the emulated library.  Safe under pytest-xdist: one process builds at a time (file lock),
-    objects and the library are written under temporary names and renamed into place."""
+    objects and the library are written under temporary names and renamed into place.
+
+    tsan=True (or NG_EMU_TSAN=1): a ThreadSanitizer-instrumented build in tests/emu/_build_tsan, for
+    tools/kernel_race_check.py — run with NG_EMU_THREADS=1 (one host thread per CUDA thread) and libtsan preloaded,
+    it reports shared-memory races (a missing __syncthreads) in the kernel sources."""
     import fcntl
-    os.makedirs(OUT_DIR, exist_ok=True)
-    with open(os.path.join(OUT_DIR, ".lock"), "w") as lock:
+    global OUT_DIR, LIB
+    if tsan is None:
+        tsan = os.environ.get("NG_EMU_TSAN", "0") == "1"
+    out_dir = os.path.join(HERE, "_build_tsan" if tsan else "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, ".lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
-        return _build_locked(force, verbose)
+        OUT_DIR, LIB = out_dir, os.path.join(out_dir, "libng_emu.so")
+        return _build_locked(force, verbose, tsan)
 
 
-def _build_locked(force, verbose):
+def _build_locked(force, verbose, tsan=False):
     srcs = _sources() + [os.path.join(HERE, "ng_emu.cpp")]
     newest = max(os.path.getmtime(p) for p in srcs + _deps())
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     flags = ["-std=c++20", "-O2", "-g", "-DNG_EMU", "-fPIC", "-pthread", "-I", HERE, "-I", CSRC,
              "-Wno-unused-result", "-Wno-attributes"]
+    link = []
+    if tsan:
+        flags = [f for f in flags if f != "-O2"] + ["-O1", "-fsanitize=thread", "-Wno-tsan"]
+        link = ["-fsanitize=thread"]
     objs = []
 
     def compile_one(src):
@@ -63,7 +76,7 @@ def _build_locked(force, verbose):
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, srcs))
     tmp = LIB + ".tmp%d" % os.getpid()
-    subprocess.run(["g++", "-shared", "-pthread", "-o", tmp] + objs, check=True)
+    subprocess.run(["g++", "-shared", "-pthread"] + link + ["-o", tmp] + objs, check=True)
     os.replace(tmp, LIB)
     return LIB
 
