@@ -75,8 +75,12 @@ static uint64_t g_next_graph = 1;
 
 static uint64_t round_size(uint64_t b) {
   if (b == 0) b = 1;
+#ifdef NG_EMU_EXACT_ALLOC
+  return b;   // AddressSanitizer build of the host emulation (tools/kernel_memcheck.py): no slack behind a tensor
+#else
   const uint64_t q = (b < (1u << 20)) ? 512 : (1u << 16);
   return (b + q - 1) / q * q;
+#endif
 }
 
 static void release_pooled_locked(Pool& P) {

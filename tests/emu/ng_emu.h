@@ -77,9 +77,15 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullpt
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return cudaSuccess; }
 inline cudaError_t cudaMalloc(void** p, size_t n) {
+#ifdef NG_EMU_EXACT_ALLOC
+  // AddressSanitizer build (tools/kernel_memcheck.py): exactly n bytes, so that one element past the end is reported
+  if (posix_memalign(p, 256, n ? n : 1) != 0) *p = nullptr;
+  if (*p) memset(*p, 0xCD, n);
+#else
   // 256-byte aligned like cudaMalloc, plus a poisoned tail to expose overruns in tests
   *p = aligned_alloc(256, (n + 255) / 256 * 256);
   if (*p) memset(*p, 0xCD, (n + 255) / 256 * 256);
+#endif
   return *p ? cudaSuccess : 2;
 }
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
