@@ -28,7 +28,7 @@ def _deps():
     return hdrs
 
 
-def build(force=False, verbose=False, tsan=None, asan=None):
+def build(force=False, verbose=False, tsan=None, asan=None, ubsan=None):
     """Build (or reuse) the emulated library.  Safe under pytest-xdist: one process builds at a time (file lock),
     objects and the library are written under temporary names and renamed into place.
 
@@ -43,15 +43,19 @@ def build(force=False, verbose=False, tsan=None, asan=None):
         asan = os.environ.get("NG_EMU_ASAN", "0") == "1"
     # asan=True (or NG_EMU_ASAN=1): AddressSanitizer build in tests/emu/_build_asan whose cudaMalloc hands out
     # exactly-sized blocks (tools/kernel_memcheck.py: out-of-bounds reads / writes of the kernels)
-    out_dir = os.path.join(HERE, "_build_tsan" if tsan else "_build_asan" if asan else "_build")
+    if ubsan is None:
+        ubsan = os.environ.get("NG_EMU_UBSAN", "0") == "1"
+    # ubsan=True (or NG_EMU_UBSAN=1): UndefinedBehaviorSanitizer build in tests/emu/_build_ubsan — misaligned vector
+    # accesses (an illegal-address fault on the GPU), signed index overflow, bad shifts (tools/kernel_ubcheck.py)
+    out_dir = os.path.join(HERE, "_build_tsan" if tsan else "_build_asan" if asan else "_build_ubsan" if ubsan else "_build")
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, ".lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
         OUT_DIR, LIB = out_dir, os.path.join(out_dir, "libng_emu.so")
-        return _build_locked(force, verbose, tsan, asan and not tsan)
+        return _build_locked(force, verbose, tsan, asan and not tsan, ubsan and not tsan and not asan)
 
 
-def _build_locked(force, verbose, tsan=False, asan=False):
+def _build_locked(force, verbose, tsan=False, asan=False, ubsan=False):
     srcs = _sources() + [os.path.join(HERE, "ng_emu.cpp")]
     newest = max(os.path.getmtime(p) for p in srcs + _deps())
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
@@ -65,6 +69,9 @@ def _build_locked(force, verbose, tsan=False, asan=False):
     if asan:
         flags = [f for f in flags if f != "-O2"] + ["-O1", "-fsanitize=address", "-fno-omit-frame-pointer", "-DNG_EMU_EXACT_ALLOC"]
         link = ["-fsanitize=address"]
+    if ubsan:
+        flags = [f for f in flags if f != "-O2"] + ["-O1", "-fsanitize=undefined", "-fno-omit-frame-pointer"]
+        link = ["-fsanitize=undefined"]
     objs = []
 
     def compile_one(src):
