@@ -106,6 +106,9 @@ int pool_alloc(void** out, uint64_t bytes) {
     it->second.pop_back();
     if (!rec) P.pooled -= sz;
     P.live += sz;
+#ifdef NG_EMU
+    ng_emu_poison_nan(*out, sz);   // host emulation only (tools/kernel_initcheck.py): recycled blocks look unwritten
+#endif
     return 0;
   }
   void* p = nullptr;
@@ -125,6 +128,9 @@ int pool_alloc(void** out, uint64_t bytes) {
   P.size_of[p] = Block{sz, g_capturing};
   if (rec) rec->bytes += sz;
   P.live += sz;
+#ifdef NG_EMU
+  ng_emu_poison_nan(p, sz);
+#endif
   *out = p;
   return 0;
 }

@@ -76,6 +76,12 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return cudaSuccess; }
+// NG_EMU_POISON_NAN=1 (tools/kernel_initcheck.py): every block the caching allocator hands out — fresh or recycled —
+// is filled with NaNs, so a kernel that consumes device memory nobody wrote turns its result into NaN.
+inline void ng_emu_poison_nan(void* p, size_t n) {
+  static const bool on = [] { const char* e = getenv("NG_EMU_POISON_NAN"); return e && e[0] == '1'; }();
+  if (on && p) memset(p, 0xFF, n);
+}
 inline cudaError_t cudaMalloc(void** p, size_t n) {
 #ifdef NG_EMU_EXACT_ALLOC
   // AddressSanitizer build (tools/kernel_memcheck.py): exactly n bytes, so that one element past the end is reported
